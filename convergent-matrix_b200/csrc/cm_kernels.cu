@@ -1,0 +1,671 @@
+// cm_kernels.cu — sm_100a kernels of the ConvergentMatrix assembly path.
+//
+// Reference (swfrench/convergent-matrix, include/convergent_matrix.hpp) -> kernel:
+//   owner map + local index (:606-610)            k_map_group
+//   Bin::append per owner, column-major (:605-613) k_scan_dest + k_pack (per-owner segments)
+//   XBuff wire format (:128-133)                   WireHdr / WireSeg written by k_pack
+//   apply<T>: elts[inds[i]] += data[i] (:178-187)  k_apply (RED.ADD into the local block)
+//
+// All of this is HBM-bound integer / gather-scatter work: no tensor cores. The design
+// levers are (a) O(m+n) index work per update instead of O(m*n) (owner and local index are
+// separable in i and j), (b) values-only wire format, (c) a column-sorted sweep of the local
+// block so that repeated hits on a sector meet in L2 instead of DRAM.
+#include <cub/cub.cuh>
+
+#include "cm_kernels.h"
+
+namespace cmb {
+
+size_t dtype_size(int dtype) { return dtype == 0 ? 8 : 4; }
+
+int kernel_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+__device__ __forceinline__ uint64_t encode_item(long seg, int col, int chunk) {
+  return ((uint64_t)seg << (kItemColBits + kItemChunkBits)) | ((uint64_t)(uint32_t)col << kItemChunkBits) |
+         (uint64_t)(uint32_t)chunk;
+}
+
+// ------------------------------------------------------------------------------------
+// (1) owner map + stable grouping.  grid (nupd, 2): y = 0 rows (ix), y = 1 columns (jx).
+// For every index: owner coordinate p (:606/:609) and local index l (:607/:610). Output is
+// grouped by p, stable within a group (== the order the reference appends to bin (p,*)).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ descs, Geom g, MapArenas ma) {
+  const int u = blockIdx.x;
+  const int axis = blockIdx.y;
+  const UpdDesc d = descs[u];
+  const long *__restrict__ idx = axis == 0 ? d.ix : d.jx;
+  const int len = axis == 0 ? d.m : d.n;
+  const long blk = axis == 0 ? g.mb : g.nb;
+  const int np = (int)(axis == 0 ? g.nprow : g.npcol);
+  const long base = axis == 0 ? d.rbase : d.cbase;
+  int *__restrict__ lout = (axis == 0 ? ma.rl : ma.cl) + base;
+  int *__restrict__ pout = (axis == 0 ? ma.rpos : ma.cpos) + base;
+  int *__restrict__ off_out = (axis == 0 ? ma.roff : ma.coff) + (long)u * (np + 1);
+
+  const int tid = threadIdx.x;
+  if (np == 1) {  // single owner along this axis: identity grouping
+    bool rep = false;
+    for (int k = tid; k < len; k += blockDim.x) {
+      lout[k] = (int)local_index(idx[k], blk, 1);
+      pout[k] = k;
+      if (k > 0) rep |= idx[k] <= idx[k - 1];
+    }
+    if (axis == 0 && rep) atomicOr(&ma.uflags[u], kSegRowsMayRepeat);
+    if (tid == 0) {
+      off_out[0] = 0;
+      off_out[1] = len;
+    }
+    return;
+  }
+
+  __shared__ int cnt[kMaxGridDim];
+  __shared__ int gbase[kMaxGridDim + 1];
+  __shared__ int run[kMaxGridDim];
+  __shared__ int wcnt[8][kMaxGridDim];
+  const int lane = tid & 31, warp = tid >> 5;
+
+  if (tid < np) {
+    cnt[tid] = 0;
+    run[tid] = 0;
+  }
+  for (int k = tid; k < 8 * kMaxGridDim; k += blockDim.x) (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  // pass 1: group sizes
+  for (int k = tid; k < len; k += blockDim.x) atomicAdd(&cnt[owner_coord(idx[k], blk, np)], 1);
+  if (axis == 0) {
+    bool rep = false;
+    for (int k = tid + 1; k < len; k += blockDim.x) rep |= idx[k] <= idx[k - 1];
+    if (rep) atomicOr(&ma.uflags[u], kSegRowsMayRepeat);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int p = 0; p < np; ++p) {
+      gbase[p] = acc;
+      off_out[p] = acc;
+      acc += cnt[p];
+    }
+    gbase[np] = acc;
+    off_out[np] = acc;
+  }
+  __syncthreads();
+  // pass 2: stable placement, 256 entries at a time
+  for (int c0 = 0; c0 < len; c0 += blockDim.x) {
+    const int k = c0 + tid;
+    const bool valid = k < len;
+    long gi = 0;
+    int p = np;  // sentinel group for lanes past the end
+    if (valid) {
+      gi = idx[k];
+      p = owner_coord(gi, blk, np);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, p);
+    const int r = __popc(peers & ((1u << lane) - 1u));
+    if (valid && r == 0) wcnt[warp][p] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      int off = gbase[p] + run[p] + r;
+      for (int w = 0; w < warp; ++w) off += wcnt[w][p];
+      lout[off] = (int)local_index(gi, blk, np);
+      pout[off] = k;
+    }
+    __syncthreads();
+    if (tid < np) {
+      int s = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        s += wcnt[w][tid];
+        wcnt[w][tid] = 0;
+      }
+      run[tid] += s;
+    }
+    __syncthreads();
+  }
+}
+
+void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma, cudaStream_t s) {
+  if (nupd <= 0) return;
+  k_map_group<<<dim3(nupd, 2), 256, 0, s>>>(d_descs, g, ma);
+}
+
+// ------------------------------------------------------------------------------------
+// (2) per-owner exclusive scans over the staged updates. grid = P blocks (one per owner).
+// ------------------------------------------------------------------------------------
+struct Long3 {
+  long a, b, c;
+  __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c}; }
+};
+
+__global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas ma, ScanArenas sa) {
+  using BlockScan = cub::BlockScan<Long3, 256>;
+  __shared__ typename BlockScan::TempStorage tmp;
+  const int dst = blockIdx.x;
+  const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
+  const int npr = (int)g.nprow + 1, npc = (int)g.npcol + 1;
+  Long3 running{0, 0, 0};
+  for (int c0 = 0; c0 < nupd; c0 += 256) {
+    const int u = c0 + threadIdx.x;
+    Long3 v{0, 0, 0};
+    if (u < nupd) {
+      const int nr = ma.roff[(long)u * npr + p + 1] - ma.roff[(long)u * npr + p];
+      const int nc = ma.coff[(long)u * npc + q + 1] - ma.coff[(long)u * npc + q];
+      const long nv = (long)nr * nc;
+      if (nv > 0) {
+        v.a = nv;
+        v.b = nr + nc;
+        v.c = (long)nc * ((nr + kRowChunk - 1) / kRowChunk);
+      }
+    }
+    Long3 excl, total;
+    BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0}, cub::Sum(), total);
+    if (u < nupd) {
+      sa.valoff[(long)dst * nupd + u] = running.a + excl.a;
+      sa.idxoff[(long)dst * nupd + u] = running.b + excl.b;
+      sa.itemoff[(long)dst * nupd + u] = running.c + excl.c;
+    }
+    running = running + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sa.totals[dst] = MsgCounts{running.a, running.b, (long)nupd, running.c};
+}
+
+__global__ void k_finalize_msgs(int P, ScanArenas sa, char *send_meta) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long vb = 0, mbs = 0;
+  for (int d = 0; d < P; ++d) {
+    const MsgCounts c = sa.totals[d];
+    sa.val_base[d] = vb;
+    sa.meta_base[d] = mbs;
+    WireHdr *h = reinterpret_cast<WireHdr *>(send_meta + mbs);
+    h->nseg = c.nseg;
+    h->nvals = c.nvals;
+    h->nidx = c.nidx;
+    h->nitems = c.nitems;
+    vb += c.nvals;
+    mbs += meta_bytes(c.nseg, c.nidx);
+  }
+  sa.val_base[P] = vb;
+  sa.meta_base[P] = mbs;
+}
+
+void launch_scan(const UpdDesc *, int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
+                 char *d_send_meta, cudaStream_t s) {
+  const int P = (int)(g.nprow * g.npcol);
+  k_scan_dest<<<P, 256, 0, s>>>(nupd, g, ma, sa);
+  k_finalize_msgs<<<1, 32, 0, s>>>(P, sa, d_send_meta);
+}
+
+// ------------------------------------------------------------------------------------
+// (3) pack. grid (nupd, ytiles): block (u, y) handles grouped columns y, y+ytiles, ...
+// of update u: for every owner row p it gathers the rows R_p of that column into the
+// (p,q) segment — contiguous, coalesced stores; gathers hit every sector of the source
+// column exactly once per block. Block y == 0 also writes the update's wire metadata.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs, int nupd, Geom g, MapArenas ma,
+                                              ScanArenas sa, T *__restrict__ send_vals, char *__restrict__ send_meta) {
+  const int u = blockIdx.x;
+  const UpdDesc d = descs[u];
+  const int nprow = (int)g.nprow, npcol = (int)g.npcol;
+  __shared__ int roff[kMaxGridDim + 1];
+  __shared__ int coff[kMaxGridDim + 1];
+  const int tid = threadIdx.x;
+  if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
+  if (tid <= npcol) coff[tid] = ma.coff[(long)u * (npcol + 1) + tid];
+  __syncthreads();
+  const T *__restrict__ data = static_cast<const T *>(d.data);
+  const int *__restrict__ rpos = ma.rpos + d.rbase;
+  const int *__restrict__ cpos = ma.cpos + d.cbase;
+
+  for (int kc = blockIdx.y; kc < d.n; kc += gridDim.y) {
+    int q = 0;
+    while (kc >= coff[q + 1]) ++q;
+    const int b = kc - coff[q];
+    const long j = cpos[kc];
+    for (int p = 0; p < nprow; ++p) {
+      const int nr = roff[p + 1] - roff[p];
+      if (nr == 0) continue;
+      const int dst = p * npcol + q;
+      T *__restrict__ out = send_vals + sa.val_base[dst] + sa.valoff[(long)dst * nupd + u] + (long)b * nr;
+      const int *__restrict__ rp = rpos + roff[p];
+      if (!d.trans) {
+        const T *__restrict__ col = data + d.ld * j;
+        for (int a = tid; a < nr; a += blockDim.x) out[a] = col[rp[a]];
+      } else {
+        const T *__restrict__ col = data + j;
+        for (int a = tid; a < nr; a += blockDim.x) out[a] = col[(long)rp[a] * d.ld];
+      }
+    }
+  }
+
+  if (blockIdx.y == 0) {
+    const int *__restrict__ rl = ma.rl + d.rbase;
+    const int *__restrict__ cl = ma.cl + d.cbase;
+    for (int dst = 0; dst < nprow * npcol; ++dst) {
+      const int p = dst / npcol, q = dst % npcol;
+      const int nr = roff[p + 1] - roff[p], nc = coff[q + 1] - coff[q];
+      char *mb = send_meta + sa.meta_base[dst];
+      WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
+      const bool empty = (long)nr * nc == 0;
+      const long ioff = sa.idxoff[(long)dst * nupd + u];
+      if (tid == 0) {
+        ws->nr = empty ? 0 : nr;
+        ws->nc = empty ? 0 : nc;
+        ws->mask = d.mask;
+        ws->flags = ma.uflags[u];
+        ws->val_off = sa.valoff[(long)dst * nupd + u];
+        ws->idx_off = ioff;
+        ws->item_off = sa.itemoff[(long)dst * nupd + u];
+      }
+      if (!empty) {
+        int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nupd * sizeof(WireSeg)) + ioff;
+        for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
+        for (int c = tid; c < nc; c += blockDim.x) iw[nr + c] = cl[coff[q] + c];
+      }
+    }
+  }
+}
+
+static int pick_ytiles(int nupd, long max_cols) {
+  const int target = kernel_sm_count() * 8;
+  long y = (target + nupd - 1) / nupd;
+  if (y < 1) y = 1;
+  if (y > max_cols) y = max_cols;
+  if (y > 1024) y = 1024;
+  if (y < 1) y = 1;
+  return (int)y;
+}
+
+void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
+                 const ScanArenas &sa, void *d_send_vals, char *d_send_meta, cudaStream_t s) {
+  if (nupd <= 0) return;
+  const dim3 grid(nupd, pick_ytiles(nupd, 4096));
+  switch (dtype) {
+    case 0:
+      k_pack<double><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<double *>(d_send_vals), d_send_meta);
+      break;
+    case 1:
+      k_pack<float><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<float *>(d_send_vals), d_send_meta);
+      break;
+    default:
+      k_pack<int><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<int *>(d_send_vals), d_send_meta);
+      break;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (4a) single-rank path: one Seg per staged update, pointing at the payload itself.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_direct(const UpdDesc *__restrict__ descs, const long *__restrict__ item_base,
+                                                      int esz, MapArenas ma, Seg *__restrict__ segs,
+                                                      uint32_t *__restrict__ keys, uint64_t *__restrict__ items) {
+  const int u = blockIdx.x;
+  const UpdDesc d = descs[u];
+  const int *cl = ma.cl + d.cbase;
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    Seg s;
+    s.vals = d.data;
+    s.lrow = ma.rl + d.rbase;
+    s.lcol = cl;
+    s.row_stride = d.trans ? d.ld : 1;
+    s.col_stride = d.trans ? 1 : d.ld;
+    s.nr = d.m;
+    s.nc = d.n;
+    s.mask = d.mask;
+    s.flags = ma.uflags[u];
+    segs[u] = s;
+  }
+  const int nch = (d.m + kRowChunk - 1) / kRowChunk;
+  const long total = (long)d.n * nch;
+  const long ib = item_base[u];
+  for (long t = (long)blockIdx.y * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.y * blockDim.x) {
+    const int b = (int)(t / nch), ch = (int)(t % nch);
+    keys[ib + t] = (uint32_t)cl[b];
+    items[ib + t] = encode_item(u, b, ch);
+  }
+  (void)esz;
+}
+
+void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd, const Geom &,
+                         const MapArenas &ma, Seg *d_segs, uint32_t *d_keys, uint64_t *d_items, cudaStream_t s) {
+  if (nupd <= 0) return;
+  const dim3 grid(nupd, pick_ytiles(nupd, 64));
+  k_build_direct<<<grid, 256, 0, s>>>(d_descs, d_item_base, (int)dtype_size(dtype), ma, d_segs, d_keys, d_items);
+}
+
+// ------------------------------------------------------------------------------------
+// (4b) owner side: received messages -> Seg table + (key, item) pairs. One warp per segment.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_recv(const MsgRef *__restrict__ msgs, int esz, Seg *__restrict__ segs,
+                                                    uint32_t *__restrict__ keys, uint64_t *__restrict__ items) {
+  const MsgRef m = msgs[blockIdx.y];
+  const WireHdr *h = reinterpret_cast<const WireHdr *>(m.meta);
+  const long nseg = h->nseg;
+  const WireSeg *wsegs = reinterpret_cast<const WireSeg *>(m.meta + sizeof(WireHdr));
+  const int *idx = reinterpret_cast<const int *>(m.meta + sizeof(WireHdr) + nseg * sizeof(WireSeg));
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long u = warp; u < nseg; u += nwarps) {
+    const WireSeg ws = wsegs[u];
+    const long sid = m.seg_base + u;
+    const int *lrow = idx + ws.idx_off;
+    const int *lcol = lrow + ws.nr;
+    if (lane == 0) {
+      Seg s;
+      s.vals = static_cast<const char *>(m.vals) + ws.val_off * esz;
+      s.lrow = lrow;
+      s.lcol = lcol;
+      s.row_stride = 1;
+      s.col_stride = ws.nr;
+      s.nr = ws.nr;
+      s.nc = ws.nc;
+      s.mask = ws.mask;
+      s.flags = ws.flags;
+      segs[sid] = s;
+    }
+    const int nch = (ws.nr + kRowChunk - 1) / kRowChunk;
+    const long total = (long)ws.nc * nch;
+    const long ib = m.item_base + ws.item_off;
+    for (long t = lane; t < total; t += 32) {
+      const int b = (int)(t / nch), ch = (int)(t % nch);
+      keys[ib + t] = (uint32_t)lcol[b];
+      items[ib + t] = encode_item(sid, b, ch);
+    }
+  }
+}
+
+void launch_build_recv(int dtype, const MsgRef *d_msgs, int nmsgs, long max_seg_per_msg, Seg *d_segs, uint32_t *d_keys,
+                       uint64_t *d_items, cudaStream_t s) {
+  if (nmsgs <= 0 || max_seg_per_msg <= 0) return;
+  long blocks = (max_seg_per_msg + 7) / 8;  // 8 warps per block, one warp per segment
+  const long cap = (long)kernel_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  k_build_recv<<<dim3((unsigned)blocks, nmsgs), 256, 0, s>>>(d_msgs, (int)dtype_size(dtype), d_segs, d_keys, d_items);
+}
+
+// ------------------------------------------------------------------------------------
+// (5) sort items by destination column (stable LSD radix sort, CUB).
+// ------------------------------------------------------------------------------------
+size_t sort_temp_bytes(long nitems, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (const uint64_t *)nullptr, (uint64_t *)nullptr, nitems, 0, end_bit);
+  return bytes;
+}
+
+void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint64_t *items_in,
+                 uint64_t *items_out, long nitems, int end_bit, cudaStream_t s) {
+  if (nitems <= 0) return;
+  cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, keys_out, items_in, items_out, nitems, 0, end_bit, s);
+}
+
+// ------------------------------------------------------------------------------------
+// (6) scatter-add: apply<T> of the reference (:178-187). One warp per item (one column
+// chunk of one segment). Values stream in coalesced; every destination element is a
+// RED.ADD at  local[lcol[b]*LLD + lrow[a]].  Items arrive sorted by destination column, so
+// the active window of the local block is a few columns wide and stays in L2.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void red_add(T *p, T v) {
+  atomicAdd(p, v);  // result unused -> RED.E.ADD.{F64,F32,S32}.STRONG.GPU
+}
+
+__device__ __forceinline__ bool mask_keep(int mask, long grow, long gcol) {
+  return mask == 1 ? (grow <= gcol) : (grow > gcol);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply(const Seg *__restrict__ segs, const uint64_t *__restrict__ items,
+                                               long nitems, T *__restrict__ local, Geom g) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long t = warp; t < nitems; t += nwarps) {
+    const uint64_t it = items[t];
+    const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
+    const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
+    const int ch = (int)(it & ((1u << kItemChunkBits) - 1u));
+    const Seg s = segs[sid];
+    const int a0 = ch * kRowChunk;
+    const int a1 = min(s.nr, a0 + kRowChunk);
+    const int lc = s.lcol[b];
+    T *__restrict__ dcol = local + (long)lc * g.lld;
+    const T *__restrict__ v = static_cast<const T *>(s.vals) + (long)b * s.col_stride;
+    const int *__restrict__ lrow = s.lrow;
+    if (s.mask == 0 && s.row_stride == 1) {
+      int a = a0 + lane;
+      // 4 independent value/index loads in flight per lane before the REDs
+      for (; a + 96 < a1; a += 128) {
+        const T x0 = v[a], x1 = v[a + 32], x2 = v[a + 64], x3 = v[a + 96];
+        const int r0 = lrow[a], r1 = lrow[a + 32], r2 = lrow[a + 64], r3 = lrow[a + 96];
+        red_add(dcol + r0, x0);
+        red_add(dcol + r1, x1);
+        red_add(dcol + r2, x2);
+        red_add(dcol + r3, x3);
+      }
+      for (; a < a1; a += 32) red_add(dcol + lrow[a], v[a]);
+    } else {
+      const long gcol = global_index(lc, g.nb, g.npcol, g.mypcol);
+      for (int a = a0 + lane; a < a1; a += 32) {
+        const int r = lrow[a];
+        if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
+        red_add(dcol + r, v[(long)a * s.row_stride]);
+      }
+    }
+  }
+}
+
+void launch_apply(int dtype, const Seg *d_segs, const uint64_t *d_items, long nitems, void *d_local, const Geom &g,
+                  cudaStream_t s) {
+  if (nitems <= 0) return;
+  const long warps_per_block = 8;
+  long blocks = (nitems + warps_per_block - 1) / warps_per_block;
+  const long cap = (long)kernel_sm_count() * 8;  // 8 blocks x 8 warps = 64 warps per SM
+  if (blocks > cap) blocks = cap;
+  switch (dtype) {
+    case 0:
+      k_apply<double><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<double *>(d_local), g);
+      break;
+    case 1:
+      k_apply<float><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<float *>(d_local), g);
+      break;
+    default:
+      k_apply<int><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<int *>(d_local), g);
+      break;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------
+// (6') deterministic order: the items are stably sorted by destination column, so all the
+// contributions to one column form one run in a fixed order (source rank, update, column of
+// the update, row chunk). One warp owns one column: it walks the run item by item and does a
+// plain load-add-store per element (no atomics; lanes of one item hit distinct rows when the
+// update's row indices are strictly increasing, otherwise lane 0 applies the item serially).
+// Accumulation order per element is therefore fixed => bit-exact run to run.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_det(const Seg *__restrict__ segs, const uint32_t *__restrict__ keys,
+                                                   const uint64_t *__restrict__ items, long nitems, T *local, Geom g,
+                                                   long ncols) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long c = warp; c < ncols; c += nwarps) {
+    long lo = 0, hi = nitems;  // lower_bound(keys, c)
+    while (lo < hi) {
+      const long mid = (lo + hi) >> 1;
+      if (keys[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+    }
+    T *dcol = local + c * g.lld;
+    const long gcol = global_index(c, g.nb, g.npcol, g.mypcol);
+    for (long t = lo; t < nitems && keys[t] == (uint32_t)c; ++t) {
+      const uint64_t it = items[t];
+      const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
+      const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
+      const int ch = (int)(it & ((1u << kItemChunkBits) - 1u));
+      const Seg s = segs[sid];
+      const int a0 = ch * kRowChunk;
+      const int a1 = min(s.nr, a0 + kRowChunk);
+      const T *__restrict__ v = static_cast<const T *>(s.vals) + (long)b * s.col_stride;
+      const int *__restrict__ lrow = s.lrow;
+      if (s.flags & kSegRowsMayRepeat) {
+        if (lane == 0)
+          for (int a = a0; a < a1; ++a) {
+            const int r = lrow[a];
+            if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
+            __stcg(dcol + r, __ldcg(dcol + r) + v[(long)a * s.row_stride]);
+          }
+      } else {
+        for (int a = a0 + lane; a < a1; a += 32) {
+          const int r = lrow[a];
+          if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
+          __stcg(dcol + r, __ldcg(dcol + r) + v[(long)a * s.row_stride]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+void launch_apply_det(int dtype, const Seg *d_segs, const uint32_t *d_sorted_keys, const uint64_t *d_sorted_items,
+                      long nitems, void *d_local, long n_local, const Geom &g, cudaStream_t s) {
+  if (nitems <= 0) return;
+  long blocks = (n_local + 7) / 8;
+  const long cap = (long)kernel_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  switch (dtype) {
+    case 0:
+      k_apply_det<double><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
+                                                          static_cast<double *>(d_local), g, n_local);
+      break;
+    case 1:
+      k_apply_det<float><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
+                                                         static_cast<float *>(d_local), g, n_local);
+      break;
+    default:
+      k_apply_det<int><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
+                                                       static_cast<int *>(d_local), g, n_local);
+      break;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// COO path (elemental updates, reference :623-629 -> :183)
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_coo(const long *__restrict__ inds, const T *__restrict__ vals, long n,
+                                                   T *__restrict__ local) {
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x)
+    red_add(local + inds[k], vals[k]);
+}
+
+void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local, cudaStream_t s) {
+  if (n <= 0) return;
+  long blocks = (n + 255) / 256;
+  const long cap = (long)kernel_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  switch (dtype) {
+    case 0:
+      k_apply_coo<double><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const double *>(d_vals), n,
+                                                          static_cast<double *>(d_local));
+      break;
+    case 1:
+      k_apply_coo<float><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const float *>(d_vals), n,
+                                                         static_cast<float *>(d_local));
+      break;
+    default:
+      k_apply_coo<int><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const int *>(d_vals), n,
+                                                       static_cast<int *>(d_local));
+      break;
+  }
+}
+
+
+// deterministic COO: stable sort of (destination, arrival position); the thread at the head
+// of each run adds the run's values in arrival order
+__global__ void k_iota_u32(uint32_t *out, long n) {
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) out[k] = (uint32_t)k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_coo_det(const unsigned long long *__restrict__ sorted_inds,
+                                                       const uint32_t *__restrict__ perm, const T *__restrict__ vals,
+                                                       long n, T *local) {
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+    const unsigned long long ij = sorted_inds[k];
+    if (k > 0 && sorted_inds[k - 1] == ij) continue;  // not a run head
+    T acc = local[ij];
+    for (long t = k; t < n && sorted_inds[t] == ij; ++t) acc += vals[perm[t]];
+    local[ij] = acc;
+  }
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+size_t coo_det_temp_bytes(long n) {
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, n);
+  return align256(sort_bytes) + align256(8 * (size_t)n) + 2 * align256(4 * (size_t)n);
+}
+
+void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local, void *d_temp,
+                          size_t temp_bytes, cudaStream_t s) {
+  if (n <= 0) return;
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, n);
+  char *base = static_cast<char *>(d_temp);
+  void *sort_tmp = base;
+  unsigned long long *sorted = reinterpret_cast<unsigned long long *>(base + align256(sort_bytes));
+  uint32_t *iota = reinterpret_cast<uint32_t *>(base + align256(sort_bytes) + align256(8 * (size_t)n));
+  uint32_t *perm = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(iota) + align256(4 * (size_t)n));
+  (void)temp_bytes;
+  long blocks = (n + 255) / 256;
+  const long cap = (long)kernel_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  k_iota_u32<<<(unsigned)blocks, 256, 0, s>>>(iota, n);
+  cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, reinterpret_cast<const unsigned long long *>(d_inds), sorted, iota,
+                                  perm, n, 0, 64, s);
+  switch (dtype) {
+    case 0:
+      k_apply_coo_det<double><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const double *>(d_vals), n,
+                                                              static_cast<double *>(d_local));
+      break;
+    case 1:
+      k_apply_coo_det<float><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const float *>(d_vals), n,
+                                                             static_cast<float *>(d_local));
+      break;
+    default:
+      k_apply_coo_det<int><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const int *>(d_vals), n,
+                                                           static_cast<int *>(d_local));
+      break;
+  }
+}
+
+// global indices of local indices 0..count-1 on process p (:697, :699)
+__global__ void k_iota_global(long *out, long count, long blk, long np, long p) {
+  for (long l = (long)blockIdx.x * blockDim.x + threadIdx.x; l < count; l += (long)gridDim.x * blockDim.x)
+    out[l] = global_index(l, blk, np, p);
+}
+
+void launch_iota_global(long *d_out, long count, long blk, long np, long p, cudaStream_t s) {
+  if (count <= 0) return;
+  long blocks = (count + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  k_iota_global<<<(unsigned)blocks, 256, 0, s>>>(d_out, count, blk, np, p);
+}
+
+}  // namespace cmb

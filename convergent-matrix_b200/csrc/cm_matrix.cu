@@ -1,0 +1,1193 @@
+// cm_matrix.cu — host side of ConvergentMatrix on one rank + the C ABI (include/cm_b200.h).
+//
+// Replaces, per reference include/convergent_matrix.hpp:
+//   ctor/roc/zero-fill (:379-448)      Matrix::create
+//   update()  (:604-615)               stage_slice(): append an UpdDesc; payload either stays
+//                                      where the caller put it in HBM (device API, borrowed)
+//                                      or is copied H2D into the staging arena (host API)
+//   flush(thresh) (:330-375)           flush_local(): single-rank map + sorted scatter-add
+//   commit() (:723-742)                commit(): map -> scan -> pack -> counts all-gather ->
+//                                      all-to-all-v -> build -> sort -> scatter-add -> barrier
+//   Bin<T> for elemental updates       host COO bins per owner (:192-208, :623-629)
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/cm_b200.h"
+#include "cm_common.h"
+#include "cm_kernels.h"
+#include "cm_transport.h"
+
+namespace cmb {
+
+// ------------------------------------------------------------------------------------
+// small memory helpers
+// ------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return CM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(CM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return CM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+};
+
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return CM_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(CM_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return CM_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// device bump arena with stable addresses (block list); reset() consolidates
+struct DevArena {
+  struct Block {
+    char *d;
+    size_t cap, used;
+  };
+  std::vector<Block> blocks;
+  size_t min_block;
+  explicit DevArena(size_t min_block_bytes) : min_block(min_block_bytes) {}
+  int alloc(size_t bytes, void **out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (blocks.empty() || blocks.back().used + bytes > blocks.back().cap) {
+      Block b;
+      b.cap = std::max(bytes, min_block);
+      b.used = 0;
+      cudaError_t e = cudaMalloc((void **)&b.d, b.cap);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CM_ERR_NOMEM, "staging arena: cudaMalloc(%zu) failed: %s", b.cap, cudaGetErrorString(e));
+      }
+      blocks.push_back(b);
+    }
+    Block &b = blocks.back();
+    *out = b.d + b.used;
+    b.used += bytes;
+    return CM_OK;
+  }
+  size_t used() const {
+    size_t u = 0;
+    for (auto &b : blocks) u += b.used;
+    return u;
+  }
+  // caller guarantees no kernel still reads the arena
+  void reset() {
+    if (blocks.size() > 1) {
+      size_t total = 0;
+      for (auto &b : blocks) {
+        total += b.cap;
+        cudaFree(b.d);
+      }
+      blocks.clear();
+      Block nb;
+      nb.cap = total;
+      nb.used = 0;
+      if (cudaMalloc((void **)&nb.d, nb.cap) == cudaSuccess)
+        blocks.push_back(nb);
+      else
+        cudaGetLastError();
+    } else if (!blocks.empty()) {
+      blocks[0].used = 0;
+    }
+  }
+  void release() {
+    for (auto &b : blocks) cudaFree(b.d);
+    blocks.clear();
+  }
+};
+
+// pinned host arena with a device twin per block (raw ix/jx of the host API)
+struct MirrorArena {
+  struct Block {
+    char *h, *d;
+    size_t cap, used;
+  };
+  std::vector<Block> blocks;
+  size_t min_block;
+  explicit MirrorArena(size_t min_block_bytes) : min_block(min_block_bytes) {}
+  int alloc(size_t bytes, void **h_out, void **d_out) {
+    bytes = (bytes + 15) & ~(size_t)15;
+    if (blocks.empty() || blocks.back().used + bytes > blocks.back().cap) {
+      Block b;
+      b.cap = std::max(bytes, min_block);
+      b.used = 0;
+      if (cudaMallocHost((void **)&b.h, b.cap) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CM_ERR_NOMEM, "index arena: cudaMallocHost(%zu) failed", b.cap);
+      }
+      if (cudaMalloc((void **)&b.d, b.cap) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFreeHost(b.h);
+        return fail(CM_ERR_NOMEM, "index arena: cudaMalloc(%zu) failed", b.cap);
+      }
+      blocks.push_back(b);
+    }
+    Block &b = blocks.back();
+    *h_out = b.h + b.used;
+    *d_out = b.d + b.used;
+    b.used += bytes;
+    return CM_OK;
+  }
+  int upload(cudaStream_t s, long *bytes_moved) {
+    for (auto &b : blocks)
+      if (b.used) {
+        CM_CUDA_TRY(cudaMemcpyAsync(b.d, b.h, b.used, cudaMemcpyHostToDevice, s));
+        *bytes_moved += (long)b.used;
+      }
+    return CM_OK;
+  }
+  void reset() {
+    if (blocks.size() > 1) {
+      size_t total = 0;
+      for (auto &b : blocks) {
+        total += b.cap;
+        cudaFreeHost(b.h);
+        cudaFree(b.d);
+      }
+      blocks.clear();
+      Block nb;
+      nb.cap = total;
+      nb.used = 0;
+      if (cudaMallocHost((void **)&nb.h, nb.cap) == cudaSuccess) {
+        if (cudaMalloc((void **)&nb.d, nb.cap) == cudaSuccess)
+          blocks.push_back(nb);
+        else
+          cudaFreeHost(nb.h);
+      }
+      cudaGetLastError();
+    } else if (!blocks.empty()) {
+      blocks[0].used = 0;
+    }
+  }
+  void release() {
+    for (auto &b : blocks) {
+      cudaFreeHost(b.h);
+      cudaFree(b.d);
+    }
+    blocks.clear();
+  }
+};
+
+// host COO bin for elemental updates (reference Bin<T>, :192-208)
+struct CooBin {
+  std::vector<long> inds;
+  std::vector<unsigned char> vals;
+};
+
+struct PendingTimer {
+  int kind;  // 0 apply, 1 pack, 2 exchange
+  cudaEvent_t a, b;
+  long elements;
+};
+
+}  // namespace cmb
+
+using namespace cmb;
+
+// ------------------------------------------------------------------------------------
+// the matrix object (opaque to C callers)
+// ------------------------------------------------------------------------------------
+struct cm_matrix {
+  RankCtx *ctx = nullptr;
+  int dtype = 0;
+  size_t esz = 8;
+  Geom g{};
+  int P = 1, me = 0;
+  long m_local = 0, n_local = 0;
+  size_t local_elems = 0;
+  void *d_local = nullptr;
+  void *h_mirror = nullptr;
+  bool mirror_valid = false;
+  std::vector<void *> peer_local;  // remote read (operator(), :585-596): IPC / same-process
+  std::vector<bool> peer_ipc_open;
+
+  cudaStream_t stream = nullptr;
+  long flush_threshold = CM_DEFAULT_FLUSH_THRESHOLD;
+  int progress_interval = 1;
+  int deterministic = 0;
+  int sorted_sweep = 1;
+  int profiling = 0;
+  int keep_wire = 0;
+
+  // staged updates
+  std::vector<UpdDesc> descs;
+  std::vector<long> item_base;  // single-rank path: first item of each update
+  long staged_elems = 0, staged_rows = 0, staged_cols = 0, staged_items = 0;
+  bool borrowed_pending = false;  // device-API payloads staged since the last flush
+  DevArena payload_arena{64ull << 20};
+  MirrorArena index_arena{4ull << 20};
+  std::vector<CooBin> coo;  // [owner]
+  long coo_total = 0;
+
+  // fill_lower scratch (global indices of local columns / rows)
+  DevBuf d_fill_ix, d_fill_jx;
+
+  // device work buffers
+  DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_coo_tmp;
+  DevBuf d_valoff, d_idxoff, d_itemoff, d_totals, d_val_base, d_meta_base;
+  DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
+  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp;
+  PinBuf h_counts;
+
+  cm_stats stats{};
+  std::vector<PendingTimer> timers;
+  std::vector<cudaEvent_t> event_pool;
+
+  // wire capture (parity tests)
+  std::vector<char> dbg_meta;
+  std::vector<char> dbg_vals;
+  std::vector<long> dbg_meta_base, dbg_val_base;
+  std::vector<CooBin> dbg_coo;
+  bool dbg_valid = false;
+};
+
+namespace {
+
+int roc_ok(long v) { return v > 0; }
+
+cudaEvent_t get_event(cm_matrix *M) {
+  if (!M->event_pool.empty()) {
+    cudaEvent_t e = M->event_pool.back();
+    M->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ScopedTimer {
+  cm_matrix *M;
+  int kind;
+  long elements;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ScopedTimer(cm_matrix *m, int k, long el) : M(m), kind(k), elements(el) {
+    if (M->profiling) {
+      a = get_event(M);
+      b = get_event(M);
+      cudaEventRecord(a, M->stream);
+    }
+  }
+  ~ScopedTimer() {
+    if (M->profiling) {
+      cudaEventRecord(b, M->stream);
+      M->timers.push_back(PendingTimer{kind, a, b, elements});
+    }
+  }
+};
+
+// stream must be synchronised
+void resolve_timers(cm_matrix *M) {
+  for (auto &t : M->timers) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      if (t.kind == 0) {
+        M->stats.apply_ms += ms;
+        M->stats.apply_launches += 1;
+        M->stats.apply_elements += t.elements;
+      } else if (t.kind == 1) {
+        M->stats.pack_ms += ms;
+      } else {
+        M->stats.exchange_ms += ms;
+      }
+    } else {
+      cudaGetLastError();
+    }
+    M->event_pool.push_back(t.a);
+    M->event_pool.push_back(t.b);
+  }
+  M->timers.clear();
+}
+
+int ceil_log2(long v) {
+  int b = 0;
+  while ((1L << b) < v) ++b;
+  return b;
+}
+
+void clear_staged(cm_matrix *M) {
+  M->descs.clear();
+  M->item_base.clear();
+  M->staged_elems = M->staged_rows = M->staged_cols = M->staged_items = 0;
+  M->borrowed_pending = false;
+  M->payload_arena.reset();
+  M->index_arena.reset();
+  for (auto &b : M->coo) {
+    b.inds.clear();
+    b.vals.clear();
+  }
+  M->coo_total = 0;
+}
+
+int upload_staged(cm_matrix *M) {
+  const int nupd = (int)M->descs.size();
+  CM_TRY(M->index_arena.upload(M->stream, &M->stats.h2d_bytes));
+  CM_TRY(M->d_descs.ensure(sizeof(UpdDesc) * (size_t)std::max(nupd, 1)));
+  if (nupd)
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, cudaMemcpyHostToDevice,
+                                M->stream));
+  const int npr = (int)M->g.nprow + 1, npc = (int)M->g.npcol + 1;
+  CM_TRY(M->d_rl.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
+  CM_TRY(M->d_rpos.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
+  CM_TRY(M->d_cl.ensure(4 * (size_t)std::max(M->staged_cols, 1L)));
+  CM_TRY(M->d_cpos.ensure(4 * (size_t)std::max(M->staged_cols, 1L)));
+  CM_TRY(M->d_roff.ensure(4 * (size_t)npr * std::max(nupd, 1)));
+  CM_TRY(M->d_coff.ensure(4 * (size_t)npc * std::max(nupd, 1)));
+  CM_TRY(M->d_uflags.ensure(4 * (size_t)std::max(nupd, 1)));
+  CM_CUDA_TRY(cudaMemsetAsync(M->d_uflags.p, 0, 4 * (size_t)std::max(nupd, 1), M->stream));
+  return CM_OK;
+}
+
+MapArenas map_arenas(cm_matrix *M) {
+  MapArenas ma;
+  ma.rl = M->d_rl.as<int>();
+  ma.rpos = M->d_rpos.as<int>();
+  ma.roff = M->d_roff.as<int>();
+  ma.cl = M->d_cl.as<int>();
+  ma.cpos = M->d_cpos.as<int>();
+  ma.coff = M->d_coff.as<int>();
+  ma.uflags = M->d_uflags.as<int>();
+  return ma;
+}
+
+// sort (optional) + scatter-add over nitems (key,item) pairs sitting in keys0/items0
+int sort_and_apply(cm_matrix *M, long nitems, long elements) {
+  if (nitems <= 0) return CM_OK;
+  const uint64_t *items = M->d_items0.as<uint64_t>();
+  if (M->sorted_sweep || M->deterministic) {
+    const int end_bit = std::max(1, ceil_log2(std::max(M->n_local, 2L)));
+    const size_t tmp = sort_temp_bytes(nitems, end_bit);
+    CM_TRY(M->d_sort_tmp.ensure(tmp));
+    CM_TRY(M->d_keys1.ensure(4 * (size_t)nitems));
+    CM_TRY(M->d_items1.ensure(8 * (size_t)nitems));
+    launch_sort(M->d_sort_tmp.p, tmp, M->d_keys0.as<uint32_t>(), M->d_keys1.as<uint32_t>(), M->d_items0.as<uint64_t>(),
+                M->d_items1.as<uint64_t>(), nitems, end_bit, M->stream);
+    M->stats.kernel_launches += 3;  // CUB radix sort passes (library metadata sort, not the hot op)
+    items = M->d_items1.as<uint64_t>();
+  }
+  {
+    ScopedTimer t(M, 0, elements);
+    if (M->deterministic)
+      launch_apply_det(M->dtype, M->d_segs.as<Seg>(), M->d_keys1.as<uint32_t>(), items, nitems, M->d_local, M->n_local,
+                       M->g, M->stream);
+    else
+      launch_apply(M->dtype, M->d_segs.as<Seg>(), items, nitems, M->d_local, M->g, M->stream);
+    M->stats.kernel_launches += 1;
+  }
+  CM_CUDA_TRY(cudaGetLastError());
+  return CM_OK;
+}
+
+// local[inds[k]] += vals[k] for a COO blob already in HBM ([inds x n][vals x n])
+int apply_coo_blob(cm_matrix *M, const char *blob, long n) {
+  const long *inds = reinterpret_cast<const long *>(blob);
+  const void *vals = blob + (size_t)n * 8;
+  if (M->deterministic) {
+    const size_t tmp = coo_det_temp_bytes(n);
+    CM_TRY(M->d_coo_tmp.ensure(tmp));
+    launch_apply_coo_det(M->dtype, inds, vals, n, M->d_local, M->d_coo_tmp.p, tmp, M->stream);
+    M->stats.kernel_launches += 4;
+  } else {
+    launch_apply_coo(M->dtype, inds, vals, n, M->d_local, M->stream);
+    M->stats.kernel_launches += 1;
+  }
+  M->stats.elements_applied += n;
+  return CM_OK;
+}
+
+int apply_coo_local(cm_matrix *M, const CooBin &bin) {
+  const long n = (long)bin.inds.size();
+  if (n == 0) return CM_OK;
+  CM_TRY(M->d_send_coo.ensure((size_t)n * (8 + M->esz)));
+  char *d = M->d_send_coo.as<char>();
+  CM_CUDA_TRY(cudaMemcpyAsync(d, bin.inds.data(), (size_t)n * 8, cudaMemcpyHostToDevice, M->stream));
+  CM_CUDA_TRY(cudaMemcpyAsync(d + (size_t)n * 8, bin.vals.data(), (size_t)n * M->esz, cudaMemcpyHostToDevice, M->stream));
+  M->stats.h2d_bytes += n * (long)(8 + M->esz);
+  return apply_coo_blob(M, d, n);
+}
+
+// ---- single-rank flush: map -> (sort) -> scatter-add straight from the staged payloads ----
+int flush_direct(cm_matrix *M) {
+  const int nupd = (int)M->descs.size();
+  if (nupd == 0 && M->coo_total == 0) return CM_OK;
+  if (nupd) {
+    CM_TRY(upload_staged(M));
+    const long nitems = M->staged_items;
+    CM_TRY(M->d_item_base.ensure(8 * (size_t)nupd));
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, cudaMemcpyHostToDevice, M->stream));
+    CM_TRY(M->d_segs.ensure(sizeof(Seg) * (size_t)nupd));
+    CM_TRY(M->d_keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
+    CM_TRY(M->d_items0.ensure(8 * (size_t)std::max(nitems, 1L)));
+    const MapArenas ma = map_arenas(M);
+    {
+      ScopedTimer t(M, 1, 0);
+      launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
+      launch_build_direct(M->dtype, M->d_descs.as<UpdDesc>(), M->d_item_base.as<long>(), nupd, M->g, ma,
+                          M->d_segs.as<Seg>(), M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
+      M->stats.kernel_launches += 2;
+    }
+    CM_TRY(sort_and_apply(M, nitems, M->staged_elems));
+    M->stats.elements_applied += M->staged_elems;
+  }
+  if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  CM_CUDA_TRY(cudaGetLastError());
+  resolve_timers(M);
+  M->stats.flushes += 1;
+  M->mirror_valid = false;
+  clear_staged(M);
+  return CM_OK;
+}
+
+// ---- general commit path: pack -> exchange -> scatter-add (also used for P == 1 when the
+// wire is being captured, so the pack kernels are testable on one rank) ----
+int commit_exchange(cm_matrix *M) {
+  const int P = M->P, me = M->me;
+  const int nupd = (int)M->descs.size();
+  Transport *tp = M->ctx->tp;
+  const size_t esz = M->esz;
+
+  // -- source side: map, scan, pack ----------------------------------------------------
+  CM_TRY(upload_staged(M));
+  const size_t pu = (size_t)P * std::max(nupd, 1);
+  CM_TRY(M->d_valoff.ensure(8 * pu));
+  CM_TRY(M->d_idxoff.ensure(8 * pu));
+  CM_TRY(M->d_itemoff.ensure(8 * pu));
+  CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P));
+  CM_TRY(M->d_val_base.ensure(8 * (size_t)(P + 1)));
+  CM_TRY(M->d_meta_base.ensure(8 * (size_t)(P + 1)));
+  // exact sizes are known on the host: every element goes to exactly one owner, and an
+  // update contributes (npcol*m_u + nprow*n_u) index words at most
+  const size_t send_val_bytes = (size_t)M->staged_elems * esz;
+  const size_t send_meta_cap = (size_t)P * (sizeof(WireHdr) + 16) + (size_t)P * nupd * sizeof(WireSeg) +
+                               4 * ((size_t)M->g.npcol * M->staged_rows + (size_t)M->g.nprow * M->staged_cols);
+  CM_TRY(M->d_send_vals.ensure(std::max(send_val_bytes, (size_t)256)));
+  CM_TRY(M->d_send_meta.ensure(send_meta_cap));
+  const MapArenas ma = map_arenas(M);
+  ScanArenas sa;
+  sa.valoff = M->d_valoff.as<long>();
+  sa.idxoff = M->d_idxoff.as<long>();
+  sa.itemoff = M->d_itemoff.as<long>();
+  sa.totals = M->d_totals.as<MsgCounts>();
+  sa.val_base = M->d_val_base.as<long>();
+  sa.meta_base = M->d_meta_base.as<long>();
+  {
+    ScopedTimer t(M, 1, 0);
+    launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
+    launch_scan(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->d_send_meta.as<char>(), M->stream);
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->d_send_vals.p, M->d_send_meta.as<char>(),
+                M->stream);
+    M->stats.kernel_launches += (nupd ? 2 : 0) + 2;
+  }
+  CM_CUDA_TRY(cudaGetLastError());
+
+  // -- counts: all-gather the per-owner totals, read them back (the one host sync) --------
+  CM_TRY(M->d_counts_all.ensure(sizeof(MsgCounts) * (size_t)P * P));
+  CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, sizeof(MsgCounts) * (size_t)P, M->stream));
+  CM_TRY(M->h_counts.ensure(sizeof(MsgCounts) * (size_t)P * P + 8 * (size_t)P * P));
+  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src * P + dst]
+  CM_CUDA_TRY(cudaMemcpyAsync(counts, M->d_counts_all.p, sizeof(MsgCounts) * (size_t)P * P, cudaMemcpyDeviceToHost,
+                              M->stream));
+  M->stats.d2h_bytes += (long)(sizeof(MsgCounts) * (size_t)P * P);
+  // COO counts travel on the host side of the same exchange
+  long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + sizeof(MsgCounts) * (size_t)P * P);
+  {
+    std::vector<long> mine(P);
+    for (int d = 0; d < P; ++d) mine[d] = (long)M->coo[d].inds.size();
+    CM_TRY(tp->host_allgather(mine.data(), coo_counts, 8 * (size_t)P, M->stream));
+  }
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  // the borrowed device payloads and index arrays are no longer needed: pack has finished
+
+  // -- lay out send / receive regions ---------------------------------------------------
+  std::vector<long> s_val_base(P + 1, 0), s_meta_base(P + 1, 0);
+  for (int d = 0; d < P; ++d) {
+    const MsgCounts &c = counts[(size_t)me * P + d];
+    s_val_base[d + 1] = s_val_base[d] + c.nvals;
+    s_meta_base[d + 1] = s_meta_base[d] + meta_bytes(c.nseg, c.nidx);
+  }
+  // COO blob of n elements: [inds x n (8 B)][vals x n], padded so every blob stays 8-aligned
+  auto coo_blob = [esz](long n) { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); };
+  std::vector<long> r_val_base(P + 1, 0), r_meta_base(P + 1, 0), r_coo_base(P + 1, 0), s_coo_base(P + 1, 0);
+  for (int s = 0; s < P; ++s) {
+    const MsgCounts &c = counts[(size_t)s * P + me];
+    const bool remote = s != me;
+    r_val_base[s + 1] = r_val_base[s] + (remote ? c.nvals : 0);
+    r_meta_base[s + 1] = r_meta_base[s] + (remote ? meta_bytes(c.nseg, c.nidx) : 0);
+    r_coo_base[s + 1] = r_coo_base[s] + (remote ? coo_blob(coo_counts[(size_t)s * P + me]) : 0);
+    s_coo_base[s + 1] = s_coo_base[s] + coo_blob((long)M->coo[s].inds.size());
+  }
+  CM_TRY(M->d_recv_vals.ensure(std::max((size_t)r_val_base[P] * esz, (size_t)256)));
+  CM_TRY(M->d_recv_meta.ensure(std::max((size_t)r_meta_base[P], (size_t)256)));
+  CM_TRY(M->d_recv_coo.ensure(std::max((size_t)r_coo_base[P], (size_t)256)));
+  CM_TRY(M->d_send_coo.ensure(std::max((size_t)s_coo_base[P], (size_t)256)));
+  // COO blobs: per owner [inds x n][vals x n]
+  for (int d = 0; d < P; ++d) {
+    const long n = (long)M->coo[d].inds.size();
+    if (!n) continue;
+    char *dst = M->d_send_coo.as<char>() + s_coo_base[d];
+    CM_CUDA_TRY(cudaMemcpyAsync(dst, M->coo[d].inds.data(), (size_t)n * 8, cudaMemcpyHostToDevice, M->stream));
+    CM_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)n * 8, M->coo[d].vals.data(), (size_t)n * esz, cudaMemcpyHostToDevice,
+                                M->stream));
+    M->stats.h2d_bytes += n * (long)(8 + esz);
+  }
+
+  if (M->keep_wire) {
+    M->dbg_meta.resize((size_t)s_meta_base[P]);
+    M->dbg_vals.resize((size_t)s_val_base[P] * esz);
+    if (!M->dbg_meta.empty())
+      CM_CUDA_TRY(cudaMemcpy(M->dbg_meta.data(), M->d_send_meta.p, M->dbg_meta.size(), cudaMemcpyDeviceToHost));
+    if (!M->dbg_vals.empty())
+      CM_CUDA_TRY(cudaMemcpy(M->dbg_vals.data(), M->d_send_vals.p, M->dbg_vals.size(), cudaMemcpyDeviceToHost));
+    M->dbg_meta_base = s_meta_base;
+    M->dbg_val_base = s_val_base;
+    M->dbg_coo = M->coo;
+    M->dbg_valid = true;
+  }
+
+  // -- exchange: one grouped all-to-all-v with three lanes (values, metadata, coo) ---------
+  std::vector<std::vector<XferSpec>> sends(3, std::vector<XferSpec>(P)), recvs(3, std::vector<XferSpec>(P));
+  long sent = 0, received = 0;
+  for (int r = 0; r < P; ++r) {
+    const MsgCounts &cs = counts[(size_t)me * P + r];
+    const MsgCounts &cr = counts[(size_t)r * P + me];
+    const bool remote = r != me;
+    // an all-empty message (no values) still ships its header so the owner can parse it
+    sends[0][r] = XferSpec{M->d_send_vals.as<char>() + (size_t)s_val_base[r] * esz, remote ? (size_t)cs.nvals * esz : 0};
+    sends[1][r] = XferSpec{M->d_send_meta.as<char>() + s_meta_base[r],
+                           remote && cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
+    sends[2][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r],
+                           remote ? (size_t)coo_blob((long)M->coo[r].inds.size()) : 0};
+    recvs[0][r] = XferSpec{M->d_recv_vals.as<char>() + (size_t)r_val_base[r] * esz, remote ? (size_t)cr.nvals * esz : 0};
+    recvs[1][r] = XferSpec{M->d_recv_meta.as<char>() + r_meta_base[r],
+                           remote && cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
+    recvs[2][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r],
+                           remote ? (size_t)coo_blob(coo_counts[(size_t)r * P + me]) : 0};
+    for (int lane = 0; lane < 3; ++lane) {
+      sent += (long)sends[lane][r].bytes;
+      received += (long)recvs[lane][r].bytes;
+    }
+  }
+  {
+    ScopedTimer t(M, 2, 0);
+    CM_TRY(tp->alltoallv(sends, recvs, M->stream));
+  }
+  M->stats.bytes_sent += sent;
+  M->stats.bytes_received += received;
+
+  // -- owner side: message table -> Seg table + items -> sort -> scatter-add ---------------
+  std::vector<MsgRef> msgs;
+  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+  for (int s = 0; s < P; ++s) {
+    const MsgCounts &c = counts[(size_t)s * P + me];
+    if (c.nvals == 0) continue;
+    MsgRef m;
+    if (s == me) {
+      m.meta = M->d_send_meta.as<char>() + s_meta_base[me];
+      m.vals = M->d_send_vals.as<char>() + (size_t)s_val_base[me] * esz;
+    } else {
+      m.meta = M->d_recv_meta.as<char>() + r_meta_base[s];
+      m.vals = M->d_recv_vals.as<char>() + (size_t)r_val_base[s] * esz;
+    }
+    m.seg_base = seg_total;
+    m.item_base = item_total;
+    seg_total += c.nseg;
+    item_total += c.nitems;
+    elem_total += c.nvals;
+    max_seg = std::max(max_seg, c.nseg);
+    msgs.push_back(m);
+  }
+  if (seg_total >= (1L << kItemSegBits))
+    return fail(CM_ERR_INVALID, "too many segments in one commit (%ld); commit more often", seg_total);
+  if (!msgs.empty()) {
+    CM_TRY(M->d_msgs.ensure(sizeof(MsgRef) * msgs.size()));
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, M->stream));
+    CM_TRY(M->d_segs.ensure(sizeof(Seg) * (size_t)seg_total));
+    CM_TRY(M->d_keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
+    CM_TRY(M->d_items0.ensure(8 * (size_t)std::max(item_total, 1L)));
+    launch_build_recv(M->dtype, M->d_msgs.as<MsgRef>(), (int)msgs.size(), max_seg, M->d_segs.as<Seg>(),
+                      M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
+    M->stats.kernel_launches += 1;
+    CM_TRY(sort_and_apply(M, item_total, elem_total));
+    M->stats.elements_applied += elem_total;
+  }
+  for (int s = 0; s < P; ++s) {
+    const long n = coo_counts[(size_t)s * P + me];
+    if (!n) continue;
+    const char *blob = s == me ? M->d_send_coo.as<char>() + s_coo_base[me] : M->d_recv_coo.as<char>() + r_coo_base[s];
+    CM_TRY(apply_coo_blob(M, blob, n));
+  }
+  CM_CUDA_TRY(cudaGetLastError());
+  // -- quiescence: everybody has applied everything (reference :737-741) --------------------
+  CM_TRY(tp->barrier(M->stream));
+  CM_CUDA_TRY(cudaGetLastError());
+  resolve_timers(M);
+  M->mirror_valid = false;
+  clear_staged(M);
+  return CM_OK;
+}
+
+int do_commit(cm_matrix *M) {
+  int rc;
+  if (M->P == 1 && !M->keep_wire) {
+    rc = flush_direct(M);
+    if (rc == CM_OK) rc = M->ctx->tp->barrier(M->stream);
+  } else {
+    rc = commit_exchange(M);
+  }
+  if (rc == CM_OK) M->stats.commits += 1;
+  return rc;
+}
+
+int check_dims(long m_u, long n_u) {
+  if (m_u < 0 || n_u < 0) return fail(CM_ERR_INVALID, "negative slice dims %ld x %ld", m_u, n_u);
+  if (n_u >= (1L << kItemColBits))
+    return fail(CM_ERR_INVALID, "slice has %ld columns; the limit per update is %ld", n_u, (1L << kItemColBits) - 1);
+  if (m_u > (long)kRowChunk << kItemChunkBits)
+    return fail(CM_ERR_INVALID, "slice has %ld rows; the limit per update is %ld", m_u, (long)kRowChunk << kItemChunkBits);
+  return CM_OK;
+}
+
+// append one staged update whose payload / indices already have device addresses
+int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, int trans, const long *d_ix,
+               const long *d_jx, int mask) {
+  if (m_u == 0 || n_u == 0) return CM_OK;
+  if ((long)M->descs.size() + 1 >= (1L << kItemSegBits)) CM_TRY(M->P == 1 ? flush_direct(M) : fail(CM_ERR_INVALID, "too many staged updates; commit more often"));
+  UpdDesc d;
+  d.data = d_data;
+  d.ix = d_ix;
+  d.jx = d_jx;
+  d.ld = ld;
+  d.m = (int)m_u;
+  d.n = (int)n_u;
+  d.trans = trans ? 1 : 0;
+  d.mask = mask;
+  d.rbase = M->staged_rows;
+  d.cbase = M->staged_cols;
+  M->descs.push_back(d);
+  M->item_base.push_back(M->staged_items);
+  M->staged_rows += m_u;
+  M->staged_cols += n_u;
+  M->staged_elems += m_u * n_u;
+  M->staged_items += n_u * ((m_u + kRowChunk - 1) / kRowChunk);
+  M->stats.updates += 1;
+  M->stats.elements_staged += m_u * n_u;
+  return CM_OK;
+}
+
+// reference flush(thresh) trigger, :346 / :614: strict '>' on the number of staged elements
+int maybe_flush(cm_matrix *M) {
+  if (M->P == 1 && !M->keep_wire && M->staged_elems + M->coo_total > M->flush_threshold) return flush_direct(M);
+  return CM_OK;
+}
+
+int stage_host_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld, int trans, const long *ix,
+                     const long *jx, int mask) {
+  CM_TRY(check_dims(m_u, n_u));
+  if (m_u == 0 || n_u == 0) return CM_OK;
+  if (!data || !ix || !jx) return fail(CM_ERR_INVALID, "null payload or index pointer");
+  // storage footprint: contiguous dim x other dim with leading dimension ld
+  const long rows_s = trans ? n_u : m_u, cols_s = trans ? m_u : n_u;
+  if (ld < rows_s) return fail(CM_ERR_INVALID, "ld (%ld) smaller than the stored leading dimension (%ld)", ld, rows_s);
+  const size_t esz = M->esz;
+  void *d_payload = nullptr;
+  CM_TRY(M->payload_arena.alloc((size_t)rows_s * cols_s * esz, &d_payload));
+  if (ld == rows_s) {
+    CM_CUDA_TRY(cudaMemcpyAsync(d_payload, data, (size_t)rows_s * cols_s * esz, cudaMemcpyHostToDevice, M->stream));
+  } else {
+    CM_CUDA_TRY(cudaMemcpy2DAsync(d_payload, (size_t)rows_s * esz, data, (size_t)ld * esz, (size_t)rows_s * esz,
+                                  (size_t)cols_s, cudaMemcpyHostToDevice, M->stream));
+  }
+  M->stats.h2d_bytes += (long)((size_t)rows_s * cols_s * esz);
+  // reference semantics (:611): the caller may reuse `data` on return. Pageable sources are
+  // consumed before cudaMemcpyAsync returns; pinned / managed sources are DMA'd asynchronously,
+  // so wait for them.
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)
+      CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  } else {
+    cudaGetLastError();
+  }
+  void *h_ix = nullptr, *dv_ix = nullptr, *h_jx = nullptr, *dv_jx = nullptr;
+  CM_TRY(M->index_arena.alloc((size_t)m_u * 8, &h_ix, &dv_ix));
+  memcpy(h_ix, ix, (size_t)m_u * 8);
+  if (jx == ix && m_u == n_u) {
+    dv_jx = dv_ix;
+  } else {
+    CM_TRY(M->index_arena.alloc((size_t)n_u * 8, &h_jx, &dv_jx));
+    memcpy(h_jx, jx, (size_t)n_u * 8);
+  }
+  CM_TRY(stage_desc(M, d_payload, m_u, n_u, rows_s, trans, static_cast<const long *>(dv_ix),
+                    static_cast<const long *>(dv_jx), mask));
+  return maybe_flush(M);
+}
+
+}  // namespace
+
+// ====================================================================================
+// C ABI
+// ====================================================================================
+extern "C" {
+
+long cm_numroc(long m, long np, long ip, long mb) {
+  const long nblocks = m / mb;
+  long loc = (nblocks / np) * mb;
+  if (nblocks % np > ip)
+    loc += mb;
+  else if (nblocks % np == ip)
+    loc += m % mb;
+  return loc;
+}
+
+void cm_owner_of(long i, long j, long nprow, long npcol, long mb, long nb, long lld, int *rank, long *ij) {
+  if (rank) *rank = owner_coord(j, nb, npcol) + (int)npcol * owner_coord(i, mb, nprow);
+  if (ij) *ij = lld * local_index(j, nb, npcol) + local_index(i, mb, nprow);
+}
+
+void cm_descinit_raw(int ictxt, long m, long n, long mb, long nb, long lld, int desc[9]) {
+  desc[0] = 1;  // DTYPE_ = dense
+  desc[1] = ictxt;
+  desc[2] = (int)m;
+  desc[3] = (int)n;
+  desc[4] = (int)mb;
+  desc[5] = (int)nb;
+  desc[6] = 0;  // RSRC_
+  desc[7] = 0;  // CSRC_
+  desc[8] = (int)lld;
+}
+
+int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol, long mb, long nb, long lld) {
+  if (!out) return fail(CM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  RankCtx *ctx = current_ctx();
+  if (!ctx) return fail(CM_ERR_STATE, "runtime not initialised (cm_rt_init) or rank thread not bound");
+  if (dtype != CM_F64 && dtype != CM_F32 && dtype != CM_I32) return fail(CM_ERR_INVALID, "bad dtype %d", dtype);
+  // reference asserts, :417-428
+  if (m <= 0 || n <= 0) return fail(CM_ERR_INVALID, "matrix dims must be positive (%ld x %ld)", m, n);
+  if (mb <= 0 || nb <= 0 || nprow <= 0 || npcol <= 0 || lld <= 0) return fail(CM_ERR_INVALID, "bad distribution parameters");
+  if (nprow * npcol != ctx->nranks)
+    return fail(CM_ERR_INVALID, "NPROW*NPCOL = %ld but rank_n() = %d", nprow * npcol, ctx->nranks);
+  if (nprow > kMaxGridDim || npcol > kMaxGridDim) return fail(CM_ERR_INVALID, "grid dims above %d unsupported", kMaxGridDim);
+  cm_matrix *M = new cm_matrix();
+  M->ctx = ctx;
+  M->dtype = dtype;
+  M->esz = dtype_size(dtype);
+  M->P = (int)(nprow * npcol);
+  M->me = ctx->rank;
+  M->g.m = m;
+  M->g.n = n;
+  M->g.mb = mb;
+  M->g.nb = nb;
+  M->g.nprow = nprow;
+  M->g.npcol = npcol;
+  M->g.lld = lld;
+  M->g.myprow = (int)(ctx->rank / npcol);  // row-major grid (see header)
+  M->g.mypcol = (int)(ctx->rank % npcol);
+  M->m_local = cm_numroc(m, nprow, M->g.myprow, mb);
+  M->n_local = cm_numroc(n, npcol, M->g.mypcol, nb);
+  if (!roc_ok(M->m_local) || !roc_ok(M->n_local) || M->m_local > lld) {
+    const long ml = M->m_local, nl = M->n_local;
+    delete M;
+    return fail(CM_ERR_INVALID, "local block %ld x %ld incompatible with LLD %ld", ml, nl, lld);
+  }
+  if (lld >= (1L << 31) || M->n_local >= (1L << 31)) {
+    delete M;
+    return fail(CM_ERR_INVALID, "local dims must fit in 31 bits");
+  }
+  M->local_elems = (size_t)lld * M->n_local;
+  M->coo.resize(M->P);
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&M->d_local, M->local_elems * M->esz);
+  if (e == cudaSuccess) e = cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream);  // :431-432
+  if (e == cudaSuccess) e = cudaStreamSynchronize(M->stream);
+  if (e != cudaSuccess) {
+    int rc = fail(e == cudaErrorMemoryAllocation ? CM_ERR_NOMEM : CM_ERR_CUDA, "cm_create: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    if (M->d_local) cudaFree(M->d_local);
+    if (M->stream) cudaStreamDestroy(M->stream);
+    delete M;
+    return rc;
+  }
+  // publish local blocks for one-sided reads (dist_object fetch + rget, :589-595)
+  M->peer_local.assign(M->P, nullptr);
+  M->peer_ipc_open.assign(M->P, false);
+  M->peer_local[M->me] = M->d_local;
+  if (M->P > 1) {
+    if (ctx->tp->same_process()) {
+      std::vector<void *> all(M->P);
+      int rc = ctx->tp->host_allgather(&M->d_local, all.data(), sizeof(void *), M->stream);
+      if (rc != CM_OK) return rc;
+      M->peer_local = all;
+    } else {
+      cudaIpcMemHandle_t mine;
+      std::vector<cudaIpcMemHandle_t> all(M->P);
+      memset(&mine, 0, sizeof(mine));
+      const bool have = cudaIpcGetMemHandle(&mine, M->d_local) == cudaSuccess;
+      if (!have) cudaGetLastError();
+      int rc = ctx->tp->host_allgather(&mine, all.data(), sizeof(mine), M->stream);
+      if (rc != CM_OK) return rc;
+      for (int r = 0; r < M->P && have; ++r) {
+        if (r == M->me) continue;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+          M->peer_local[r] = p;
+          M->peer_ipc_open[r] = true;
+        } else {
+          cudaGetLastError();
+        }
+      }
+    }
+  }
+  int rc = ctx->tp->barrier(M->stream);
+  if (rc != CM_OK) return rc;
+  *out = M;
+  return CM_OK;
+}
+
+int cm_destroy(cm_matrix *M) {
+  if (!M) return CM_OK;
+  int rc = do_commit(M);  // :458
+  cudaStreamSynchronize(M->stream);
+  for (int r = 0; r < M->P; ++r)
+    if (M->peer_ipc_open[r]) cudaIpcCloseMemHandle(M->peer_local[r]);
+  M->ctx->tp->barrier(M->stream);  // nobody still reads my block
+  cudaFree(M->d_local);
+  free(M->h_mirror);
+  M->payload_arena.release();
+  M->index_arena.release();
+  DevBuf *bufs[] = {&M->d_fill_ix, &M->d_fill_jx, &M->d_descs, &M->d_item_base, &M->d_rl, &M->d_rpos, &M->d_roff,
+                    &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
+                    &M->d_val_base, &M->d_meta_base, &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
+                    &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_msgs, &M->d_segs,
+                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp};
+  for (DevBuf *b : bufs) b->release();
+  M->h_counts.release();
+  for (auto e : M->event_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(M->stream);
+  delete M;
+  return rc;
+}
+
+int cm_update_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld, int trans, const long *ix,
+                    const long *jx) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  return stage_host_slice(M, data, m_u, n_u, ld, trans, ix, jx, CM_MASK_NONE);
+}
+
+int cm_update_sym(cm_matrix *M, const void *data, long n_u, long ld, int trans, const long *ix) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  return stage_host_slice(M, data, n_u, n_u, ld, trans, ix, ix, CM_MASK_UPPER);
+}
+
+int cm_update_elems(cm_matrix *M, const void *vals, const long *is, const long *js, long n) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (n < 0 || (n > 0 && (!vals || !is || !js))) return fail(CM_ERR_INVALID, "bad elemental update arguments");
+  const unsigned char *v = static_cast<const unsigned char *>(vals);
+  const Geom &g = M->g;
+  for (long k = 0; k < n; ++k) {
+    // :624-627
+    const int rank = owner_coord(js[k], g.nb, g.npcol) + (int)g.npcol * owner_coord(is[k], g.mb, g.nprow);
+    const long ij = g.lld * local_index(js[k], g.nb, g.npcol) + local_index(is[k], g.mb, g.nprow);
+    CooBin &b = M->coo[rank];
+    b.inds.push_back(ij);
+    b.vals.insert(b.vals.end(), v + (size_t)k * M->esz, v + (size_t)(k + 1) * M->esz);
+  }
+  M->coo_total += n;
+  M->stats.elements_staged += n;
+  return maybe_flush(M);
+}
+
+int cm_update_elem(cm_matrix *M, const void *val, long i, long j) { return cm_update_elems(M, val, &i, &j, 1); }
+
+int cm_update_slice_device(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, int trans, const long *d_ix,
+                           const long *d_jx, int mask) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  CM_TRY(check_dims(m_u, n_u));
+  if (m_u == 0 || n_u == 0) return CM_OK;
+  if (!d_data || !d_ix || !d_jx) return fail(CM_ERR_INVALID, "null device pointer");
+  if (mask < 0 || mask > 2) return fail(CM_ERR_INVALID, "bad mask %d", mask);
+  if (ld < (trans ? n_u : m_u)) return fail(CM_ERR_INVALID, "ld too small");
+  CM_TRY(stage_desc(M, d_data, m_u, n_u, ld, trans, d_ix, d_jx, mask));
+  M->borrowed_pending = true;
+  return maybe_flush(M);
+}
+
+// batch forms: identical to `count` consecutive calls; they exist so that harnesses with a
+// slow call path (ctypes) do not measure their own per-call overhead
+int cm_update_slices_device(cm_matrix *M, long count, const void *const *d_data, const long *m_u, const long *n_u,
+                            const long *ld, const int *trans, const long *const *d_ix, const long *const *d_jx,
+                            int mask) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (count < 0 || (count > 0 && (!d_data || !m_u || !n_u || !ld || !d_ix || !d_jx)))
+    return fail(CM_ERR_INVALID, "bad batch arguments");
+  for (long k = 0; k < count; ++k)
+    CM_TRY(cm_update_slice_device(M, d_data[k], m_u[k], n_u[k], ld[k], trans ? trans[k] : 0, d_ix[k], d_jx[k], mask));
+  return CM_OK;
+}
+
+int cm_update_slices(cm_matrix *M, long count, const void *const *data, const long *m_u, const long *n_u,
+                     const long *ld, const int *trans, const long *const *ix, const long *const *jx) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (count < 0 || (count > 0 && (!data || !m_u || !n_u || !ld || !ix || !jx)))
+    return fail(CM_ERR_INVALID, "bad batch arguments");
+  for (long k = 0; k < count; ++k)
+    CM_TRY(cm_update_slice(M, data[k], m_u[k], n_u[k], ld[k], trans ? trans[k] : 0, ix[k], jx[k]));
+  return CM_OK;
+}
+
+int cm_fill_lower(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  // One masked, transposed slice update whose payload is the local block itself: view element
+  // (k,l) = local[l + k*LLD] goes to global (row = gcol(k), col = grow(l)) iff row > col, which
+  // is the loop at :696-709 (ix = global column of local column j, jx = global row of local row i).
+  const Geom &g = M->g;
+  CM_TRY(M->d_fill_ix.ensure(8 * (size_t)M->n_local));
+  CM_TRY(M->d_fill_jx.ensure(8 * (size_t)M->m_local));
+  launch_iota_global(M->d_fill_ix.as<long>(), M->n_local, g.nb, g.npcol, g.mypcol, M->stream);
+  launch_iota_global(M->d_fill_jx.as<long>(), M->m_local, g.mb, g.nprow, g.myprow, M->stream);
+  M->stats.kernel_launches += 2;
+  CM_TRY(check_dims(M->n_local, M->m_local));
+  CM_TRY(stage_desc(M, M->d_local, M->n_local, M->m_local, g.lld, 1, M->d_fill_ix.as<long>(), M->d_fill_jx.as<long>(),
+                    CM_MASK_STRICT_LOWER));
+  // single rank: apply now, so later updates cannot change what fill_lower reads (the
+  // reference reads the block at call time)
+  if (M->P == 1 && !M->keep_wire) return flush_direct(M);
+  return CM_OK;
+}
+
+int cm_flush(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (M->P == 1 && !M->keep_wire) return flush_direct(M);
+  return CM_OK;
+}
+
+int cm_commit(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  return do_commit(M);
+}
+
+int cm_reset(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  CM_TRY(do_commit(M));  // :493
+  CM_CUDA_TRY(cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream));  // :496-497
+  M->mirror_valid = false;
+  return M->ctx->tp->barrier(M->stream);  // :500
+}
+
+int cm_local_data_device(cm_matrix *M, const void **out) {
+  if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  *out = M->d_local;
+  return CM_OK;
+}
+
+int cm_local_data_copy(cm_matrix *M, void *dst_host) {
+  if (!M || !dst_host) return fail(CM_ERR_INVALID, "null argument");
+  CM_CUDA_TRY(cudaMemcpyAsync(dst_host, M->d_local, M->local_elems * M->esz, cudaMemcpyDeviceToHost, M->stream));
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  M->stats.d2h_bytes += (long)(M->local_elems * M->esz);
+  return CM_OK;
+}
+
+int cm_local_data_host(cm_matrix *M, const void **out) {
+  if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  if (!M->h_mirror) {
+    M->h_mirror = malloc(M->local_elems * M->esz);
+    if (!M->h_mirror) return fail(CM_ERR_NOMEM, "host mirror allocation failed");
+    M->mirror_valid = false;
+  }
+  if (!M->mirror_valid) {
+    CM_TRY(cm_local_data_copy(M, M->h_mirror));
+    M->mirror_valid = true;
+  }
+  *out = M->h_mirror;
+  return CM_OK;
+}
+
+int cm_get(cm_matrix *M, long i, long j, void *out) {
+  if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  int rank;
+  long ij;
+  cm_owner_of(i, j, M->g.nprow, M->g.npcol, M->g.mb, M->g.nb, M->g.lld, &rank, &ij);
+  if (rank < 0 || rank >= M->P || !M->peer_local[rank])
+    return fail(CM_ERR_STATE, "local block of rank %d is not mapped on rank %d (CUDA IPC unavailable)", rank, M->me);
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  CM_CUDA_TRY(cudaMemcpy(out, static_cast<const char *>(M->peer_local[rank]) + (size_t)ij * M->esz, M->esz,
+                         cudaMemcpyDefault));
+  M->stats.d2h_bytes += (long)M->esz;
+  return CM_OK;
+}
+
+long cm_m(const cm_matrix *M) { return M ? M->g.m : -1; }
+long cm_n(const cm_matrix *M) { return M ? M->g.n : -1; }
+long cm_m_local(const cm_matrix *M) { return M ? M->m_local : -1; }
+long cm_n_local(const cm_matrix *M) { return M ? M->n_local : -1; }
+long cm_lld(const cm_matrix *M) { return M ? M->g.lld : -1; }
+long cm_pgrid_row(const cm_matrix *M) { return M ? M->g.myprow : -1; }
+long cm_pgrid_col(const cm_matrix *M) { return M ? M->g.mypcol : -1; }
+int cm_dtype(const cm_matrix *M) { return M ? M->dtype : -1; }
+
+long cm_get_flush_threshold(const cm_matrix *M) { return M ? M->flush_threshold : -1; }
+int cm_set_flush_threshold(cm_matrix *M, long elements) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  M->flush_threshold = elements;
+  return CM_OK;
+}
+int cm_get_progress_interval(const cm_matrix *M) { return M ? M->progress_interval : -1; }
+int cm_set_progress_interval(cm_matrix *M, int interval) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  M->progress_interval = interval;
+  return CM_OK;
+}
+int cm_set_deterministic(cm_matrix *M, int on) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  M->deterministic = on ? 1 : 0;
+  return CM_OK;
+}
+int cm_set_sorted_sweep(cm_matrix *M, int on) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  M->sorted_sweep = on ? 1 : 0;
+  return CM_OK;
+}
+int cm_set_profiling(cm_matrix *M, int on) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  M->profiling = on ? 1 : 0;
+  return CM_OK;
+}
+int cm_stream(cm_matrix *M, void **out) {
+  if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  *out = M->stream;
+  return CM_OK;
+}
+
+int cm_descinit(const cm_matrix *M, int ictxt, int desc[9]) {
+  if (!M || !desc) return fail(CM_ERR_INVALID, "null argument");
+  cm_descinit_raw(ictxt, M->g.m, M->g.n, M->g.mb, M->g.nb, M->g.lld, desc);
+  return CM_OK;
+}
+
+int cm_get_stats(cm_matrix *M, cm_stats *out) {
+  if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  *out = M->stats;
+  return CM_OK;
+}
+int cm_reset_stats(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  memset(&M->stats, 0, sizeof(M->stats));
+  return CM_OK;
+}
+
+// ---- parity hooks -------------------------------------------------------------------
+int cm_debug_keep_wire(cm_matrix *M, int on) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "toggle wire capture only with nothing staged");
+  M->keep_wire = on ? 1 : 0;
+  M->dbg_valid = false;
+  return CM_OK;
+}
+
+// expands the compact message to owner `dst` into the reference's (inds, data) stream;
+// pass null outputs to count only
+static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *data_out) {
+  const Geom &g = M->g;
+  const size_t esz = M->esz;
+  const int dp = dst / (int)g.npcol, dq = dst % (int)g.npcol;
+  long n = 0;
+  const char *meta = M->dbg_meta.data() + M->dbg_meta_base[dst];
+  const long meta_len = M->dbg_meta_base[dst + 1] - M->dbg_meta_base[dst];
+  if (meta_len >= (long)sizeof(WireHdr)) {
+    const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
+    const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
+    const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
+    const unsigned char *vals = reinterpret_cast<const unsigned char *>(M->dbg_vals.data()) + (size_t)M->dbg_val_base[dst] * esz;
+    for (long u = 0; u < h->nseg; ++u) {
+      const WireSeg &s = ws[u];
+      const int *lrow = idx + s.idx_off, *lcol = lrow + s.nr;
+      for (int b = 0; b < s.nc; ++b)
+        for (int a = 0; a < s.nr; ++a) {
+          if (s.mask) {
+            const long gr = global_index(lrow[a], g.mb, g.nprow, dp), gc = global_index(lcol[b], g.nb, g.npcol, dq);
+            if (s.mask == CM_MASK_UPPER ? !(gr <= gc) : !(gr > gc)) continue;
+          }
+          if (inds_out) {
+            inds_out[n] = g.lld * (long)lcol[b] + lrow[a];
+            memcpy(data_out + (size_t)n * esz, vals + ((size_t)s.val_off + (size_t)a + (size_t)b * s.nr) * esz, esz);
+          }
+          ++n;
+        }
+    }
+  }
+  const CooBin &cb = M->dbg_coo[dst];
+  for (size_t k = 0; k < cb.inds.size(); ++k) {
+    if (inds_out) {
+      inds_out[n] = cb.inds[k];
+      memcpy(data_out + (size_t)n * esz, cb.vals.data() + k * esz, esz);
+    }
+    ++n;
+  }
+  return n;
+}
+
+int cm_debug_wire_count(cm_matrix *M, int dst, long *n_out) {
+  if (!M || !n_out) return fail(CM_ERR_INVALID, "null argument");
+  if (!M->dbg_valid) return fail(CM_ERR_STATE, "no captured wire (cm_debug_keep_wire + cm_commit first)");
+  if (dst < 0 || dst >= M->P) return fail(CM_ERR_INVALID, "bad owner %d", dst);
+  *n_out = expand_wire(M, dst, nullptr, nullptr);
+  return CM_OK;
+}
+
+int cm_debug_wire_expand(cm_matrix *M, int dst, long *inds_out, void *data_out) {
+  if (!M || !inds_out || !data_out) return fail(CM_ERR_INVALID, "null argument");
+  if (!M->dbg_valid) return fail(CM_ERR_STATE, "no captured wire (cm_debug_keep_wire + cm_commit first)");
+  if (dst < 0 || dst >= M->P) return fail(CM_ERR_INVALID, "bad owner %d", dst);
+  expand_wire(M, dst, inds_out, static_cast<unsigned char *>(data_out));
+  return CM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+"""-m gpu parity tests: CUDA path (through the C ABI) vs the oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+import cm_b200 as cm
+from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,
+                      slice_steps, sorted_unique)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [cm.F64, cm.F32, cm.I32])
+def test_single_rank_slices(dtype):
+    cfg = Cfg(dtype, 2048, 2048, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(11)
+    steps = slice_steps(cfg, rng, 40, 200, 150, commit_every=16)
+    assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
+
+
+def test_single_rank_threshold_flush_and_unsorted_sweep():
+    cfg = Cfg(cm.F64, 2048, 2048, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(12)
+    steps = slice_steps(cfg, rng, 30, 128, 128)
+    want = run_checker(cfg, steps)
+    got = run_cuda(cfg, steps, threshold=50000)
+    assert got["stats"][0]["flushes"] > 5
+    assert_blocks_match(cfg, got, want)
+    assert_blocks_match(cfg, run_cuda(cfg, steps, sorted_sweep=False), want)
+
+
+def test_single_rank_device_api():
+    cfg = Cfg(cm.F64, 2048, 2048, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(13)
+    steps = slice_steps(cfg, rng, 20, 256, 256)
+    got = run_cuda(cfg, steps, device_api=True)
+    assert got["stats"][0]["h2d_bytes"] < 64 * 1024  # payloads never crossed PCIe
+    assert_blocks_match(cfg, got, run_checker(cfg, steps))
+
+
+@pytest.mark.parametrize("dtype", [cm.F64, cm.F32, cm.I32])
+def test_k0_grid_2x2_slices(dtype):
+    """the reference's randomSliceUpdates geometry (test/cm_test.cpp:160-218), seeded, non-unit payloads"""
+    cfg = Cfg(dtype, 2000, 1000, 2, 2, 64, 64, 1024)
+    rng = np.random.default_rng(21)
+    steps = slice_steps(cfg, rng, 3, 800, 500, commit_every=1)
+    assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
+
+
+@pytest.mark.parametrize("grid", [(2, 3, 4, 8, 64, 100, 190), (3, 2, 8, 4, 96, 250, 150), (2, 4, 64, 64, 1024, 2000, 3000),
+                                  (1, 2, 64, 64, 1024, 1000, 2000), (2, 1, 64, 64, 1024, 2000, 1000)])
+def test_nonsquare_grids_wire_bit_exact(grid):
+    nprow, npcol, mb, nb, lld, m, n = grid
+    dtype = cm.F32 if (nprow, npcol) == (3, 2) else cm.F64
+    cfg = Cfg(dtype, m, n, nprow, npcol, mb, nb, lld)
+    rng = np.random.default_rng(31)
+    steps = slice_steps(cfg, rng, 3, min(m, 90), min(n, 70), commit_every=2)
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)  # one message per commit, like ours
+    got = run_cuda(cfg, steps, wire=True)
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+
+
+def test_single_rank_wire_bit_exact():
+    cfg = Cfg(cm.F64, 1000, 1000, 1, 1, 64, 64, 1024)
+    rng = np.random.default_rng(32)
+    steps = slice_steps(cfg, rng, 5, 100, 80)
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
+    got = run_cuda(cfg, steps, wire=True)
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+
+
+def test_edge_cases_duplicates_unsorted_trans_ld():
+    cfg = Cfg(cm.F64, 500, 300, 2, 2, 64, 64, 1024)
+    rng = np.random.default_rng(41)
+    steps = []
+    # duplicates + unsorted indices must accumulate (Appendix A item 4)
+    ix = rng.integers(0, cfg.m, 70).astype(np.int64)
+    jx = rng.integers(0, cfg.n, 50).astype(np.int64)
+    ix[5] = ix[6] = ix[7]
+    jx[1] = jx[2]
+    steps.append(("slice", 0, rand_payload(rng, cfg.dtype, (50, 70)), 70, 50, 70, False, ix, jx))
+    # padded leading dimension
+    ix = sorted_unique(rng, cfg.m, 33)
+    jx = sorted_unique(rng, cfg.n, 21)
+    steps.append(("slice", 1, rand_payload(rng, cfg.dtype, (21, 40)), 33, 21, 40, False, ix, jx))
+    # transposed view (LocalMatrix::trans, include/local_matrix.hpp:58-72): storage 21 x 33, ld 25
+    steps.append(("slice", 2, rand_payload(rng, cfg.dtype, (33, 25)), 33, 21, 25, True, ix, jx))
+    # 1 x 1, single row, single column
+    one = np.array([3], dtype=np.int64)
+    steps.append(("slice", 3, rand_payload(rng, cfg.dtype, (1, 1)), 1, 1, 1, False, one, one))
+    steps.append(("slice", 3, rand_payload(rng, cfg.dtype, (21, 1)), 1, 21, 1, False, one, jx))
+    steps.append(("slice", 0, rand_payload(rng, cfg.dtype, (1, 33)), 33, 1, 33, False, ix, one))
+    steps.append(("commit",))
+    steps.append(("commit",))  # empty commit
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
+    got = run_cuda(cfg, steps, wire=True)
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+    # the same on one rank through the direct (no-pack) path
+    cfg1 = Cfg(cm.F64, 500, 300, 1, 1, 64, 64, 512)
+    steps1 = [s if s[0] != "slice" else (s[0], 0) + s[2:] for s in steps]
+    assert_blocks_match(cfg1, run_cuda(cfg1, steps1), run_checker(cfg1, steps1))
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_elemental_updates(P):
+    """randomElementUpdates (test/cm_test.cpp:44-101), seeded"""
+    cfg = Cfg(cm.F32, 2000, 1000, 2, 2, 64, 64, 1024) if P == 4 else Cfg(cm.F32, 2000, 1000, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(51)
+    steps = []
+    for it in range(3):
+        for r in range(cfg.P):
+            n = 5000
+            steps.append(("elems", r, rand_payload(rng, cfg.dtype, n), rng.integers(0, cfg.m, n), rng.integers(0, cfg.n, n)))
+        steps.append(("commit",))
+    want = run_checker(cfg, steps)
+    assert_blocks_match(cfg, run_cuda(cfg, steps), want)
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_symmetric_update_and_fill_lower(P):
+    """randomSliceUpdatesSymmetricFill (test/cm_test.cpp:220-282), seeded, non-unit payloads"""
+    cfg = Cfg(cm.F64, 2000, 2000, 2, 2, 64, 64, 1024) if P == 4 else Cfg(cm.F64, 2000, 2000, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(61)
+    steps = []
+    for it in range(3):
+        for r in range(cfg.P):
+            ix = sorted_unique(rng, cfg.m, 300)
+            steps.append(("sym", r, rand_payload(rng, cfg.dtype, (300, 300)), 300, 300, False, ix))
+        steps.append(("commit",))
+    steps += [("fill_lower",), ("commit",)]
+    want = run_checker(cfg, steps)
+    got = run_cuda(cfg, steps)
+    assert_blocks_match(cfg, got, want)
+
+
+def test_reset_and_multiple_rounds():
+    cfg = Cfg(cm.F64, 600, 600, 2, 2, 64, 64, 512)
+    rng = np.random.default_rng(71)
+    steps = slice_steps(cfg, rng, 4, 100, 100, commit_every=2)
+    steps.append(("reset",))
+    steps += slice_steps(cfg, rng, 2, 64, 64)
+    assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
+
+
+def test_deterministic_mode_bit_exact_run_to_run():
+    cfg = Cfg(cm.F64, 1024, 1024, 1, 1, 64, 64, 1024)
+    rng = np.random.default_rng(81)
+    steps = slice_steps(cfg, rng, 60, 256, 256)  # ~3.7 hits per element: order matters
+    a = run_cuda(cfg, steps, deterministic=True)
+    b = run_cuda(cfg, steps, deterministic=True)
+    assert a["local"][0].tobytes() == b["local"][0].tobytes()
+    assert_blocks_match(cfg, a, run_checker(cfg, steps))
