@@ -204,6 +204,7 @@ def bench_ours(args):
         M.set_sorted_sweep(False)
     if args.deterministic:
         M.set_deterministic(True)
+    M.set_apply_kernel({"auto": 0, "red": 1, "tile": 2}[args.apply_kernel])
     data, ix, jx = gen_inputs(spec, rank, torch, device)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(M.stream(), device=device)
@@ -300,7 +301,16 @@ def bench_ours(args):
         alg_bytes = 3 * esz * st["apply_elements"]  # 3*s per owned element
         achieved = alg_bytes / (st["apply_ms"] * 1e-3) / 1e9
         tag = f"{args.workload}_n{nranks}"
-        roof = {"bound": "hbm", "kernel": "k_apply_det" if args.deterministic else "k_apply", "achieved": achieved,
+        kname = "k_apply_tile" if st["tile_launches"] == st["apply_launches"] else (
+            "k_apply_red" if st["tile_launches"] == 0 else "k_apply_tile+k_apply_red")
+        # compulsory DRAM bytes if repeated hits combine on chip: s*E + 2*s*(distinct elements touched),
+        # bounded above by 2*s*(local block) per launch
+        local_bytes = spec["lld"] * (spec["n"] // spec["npcol"]) * esz
+        compulsory = esz * st["apply_elements"] + min(2 * esz * st["apply_elements"], 2 * local_bytes * st["apply_launches"])
+        roof = {"bound": "hbm", "kernel": kname, "achieved": achieved,
+                "compulsory_bound": {"bytes_per_launch": compulsory // max(1, st["apply_launches"]),
+                                     "achieved": compulsory / (st["apply_ms"] * 1e-3) / 1e9,
+                                     "frac": compulsory / (st["apply_ms"] * 1e-3) / 1e9 / peak},
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": known_traffic(tag),
                 "peak_source": peak_src, "algorithmic_bytes_per_element": 3 * esz,
                 "launches": st["apply_launches"], "avg_launch_ms": st["apply_ms"] / max(1, st["apply_launches"]),
@@ -325,7 +335,7 @@ def bench_ours(args):
             "config": {"workload": spec["name"], "updates_per_rank_per_step": spec["U"], "grid": [spec["nprow"], spec["npcol"]],
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
-                       "deterministic": bool(args.deterministic), "payload_bytes_per_rank_per_step": step_bytes},
+                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "payload_bytes_per_rank_per_step": step_bytes},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
             "commit_latency_us": {"empty": lat_empty, "one_update": lat_one},
@@ -419,6 +429,7 @@ def main():
     ap.add_argument("--flush-threshold", type=int, default=0, help="elements; 0 = library default")
     ap.add_argument("--unsorted", action="store_true", help="disable the column-sorted sweep")
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--apply-kernel", default="auto", choices=["auto", "red", "tile"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-updates", type=int, default=0, help="updates per rank per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -34,7 +34,7 @@ class Stats(C.Structure):
                                         "commits", "kernel_launches", "bytes_sent", "bytes_received",
                                         "h2d_bytes", "d2h_bytes")] + \
                [("apply_ms", C.c_double), ("pack_ms", C.c_double), ("exchange_ms", C.c_double),
-                ("apply_launches", C.c_long), ("apply_elements", C.c_long)]
+                ("apply_launches", C.c_long), ("apply_elements", C.c_long), ("tile_launches", C.c_long)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -85,6 +85,7 @@ SYMBOLS = {
     "cm_set_progress_interval": (_i, [_vp, _i]),
     "cm_set_deterministic": (_i, [_vp, _i]),
     "cm_set_sorted_sweep": (_i, [_vp, _i]),
+    "cm_set_apply_kernel": (_i, [_vp, _i, C.c_double]),
     "cm_descinit": (_i, [_vp, _i, C.POINTER(_i)]),
     "cm_get_stats": (_i, [_vp, C.POINTER(Stats)]),
     "cm_reset_stats": (_i, [_vp]),
@@ -305,6 +306,9 @@ class Matrix:
 
     def set_sorted_sweep(self, on):
         _check(self.L.cm_set_sorted_sweep(self.h, int(on)))
+
+    def set_apply_kernel(self, kernel, tile_density=0.0):
+        _check(self.L.cm_set_apply_kernel(self.h, kernel, tile_density))
 
     def set_profiling(self, on):
         _check(self.L.cm_set_profiling(self.h, int(on)))

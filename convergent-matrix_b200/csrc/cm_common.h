@@ -17,7 +17,7 @@
 namespace cmb {
 
 constexpr int kMaxGridDim = 64;     // max NPROW, NPCOL handled by the grouping kernel
-constexpr int kRowChunk = 1024;     // rows of one segment column covered by one item
+constexpr int kRowChunk = 256;      // rows of one segment column covered by one item (= block size)
 constexpr int kItemSegBits = 26;    // item encoding: seg | column | row chunk
 constexpr int kItemColBits = 22;
 constexpr int kItemChunkBits = 16;
@@ -56,6 +56,17 @@ struct Seg {
   int flags;  // kSegRowsMayRepeat
 };
 constexpr int kSegRowsMayRepeat = 1;  // row index set not strictly increasing (duplicates possible)
+
+// one item after the sort, with absolute pointers (what the scatter-add kernels read)
+struct ItemRec {
+  const void *v;    // first value of the item
+  const int *lrow;  // its local row indices
+  int n;            // rows in the item (<= kRowChunk)
+  int row_stride;   // elements between consecutive rows in v (1 unless a transposed direct payload)
+  int mask_flags;   // mask | flags << 8
+  int col;          // destination local column
+};
+static_assert(sizeof(ItemRec) == 32, "item record layout");
 
 // ---- wire format of one message (metadata part); all offsets relative to the message ----
 // Instead of the reference's 8-byte index per element (XBuff::inds, :131) a segment ships

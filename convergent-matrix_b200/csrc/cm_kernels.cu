@@ -4,13 +4,16 @@
 //   owner map + local index (:606-610)            k_map_group
 //   Bin::append per owner, column-major (:605-613) k_scan_dest + k_pack (per-owner segments)
 //   XBuff wire format (:128-133)                   WireHdr / WireSeg written by k_pack
-//   apply<T>: elts[inds[i]] += data[i] (:178-187)  k_apply (RED.ADD into the local block)
+//   apply<T>: elts[inds[i]] += data[i] (:178-187)  k_apply_tile (dense flushes: column tiles in
+//                                                  shared memory) / k_apply_red (sparse: RED.ADD)
 //
 // All of this is HBM-bound integer / gather-scatter work: no tensor cores. The design
 // levers are (a) O(m+n) index work per update instead of O(m*n) (owner and local index are
 // separable in i and j), (b) values-only wire format, (c) a column-sorted sweep of the local
 // block so that repeated hits on a sector meet in L2 instead of DRAM.
 #include <cub/cub.cuh>
+
+#include <algorithm>
 
 #include "cm_kernels.h"
 
@@ -411,10 +414,67 @@ void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint3
 }
 
 // ------------------------------------------------------------------------------------
-// (6) scatter-add: apply<T> of the reference (:178-187). One warp per item (one column
-// chunk of one segment). Values stream in coalesced; every destination element is a
-// RED.ADD at  local[lcol[b]*LLD + lrow[a]].  Items arrive sorted by destination column, so
-// the active window of the local block is a few columns wide and stays in L2.
+// (5b) after the sort: one ItemRec per item (absolute pointers, so the scatter-add has a
+// single dependent load instead of item -> Seg -> lists), the start of every destination
+// column's run in the sorted order.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_recs(const Seg *__restrict__ segs, const uint32_t *__restrict__ keys,
+                                                    const uint64_t *__restrict__ items, long nitems, int esz,
+                                                    ItemRec *__restrict__ recs) {
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nitems; t += (long)gridDim.x * blockDim.x) {
+    const uint64_t it = items[t];
+    const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
+    const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
+    const int ch = (int)(it & ((1u << kItemChunkBits) - 1u));
+    const Seg s = segs[sid];
+    const int a0 = ch * kRowChunk;
+    ItemRec r;
+    r.v = static_cast<const char *>(s.vals) + ((long)b * s.col_stride + (long)a0 * s.row_stride) * esz;
+    r.lrow = s.lrow + a0;
+    r.n = min(s.nr - a0, kRowChunk);
+    r.row_stride = (int)s.row_stride;
+    r.mask_flags = s.mask | (s.flags << 8);
+    r.col = (int)keys[t];
+    recs[t] = r;
+  }
+}
+
+// col_start[c] = first sorted position whose key >= c, for c in [0, ncols]
+__global__ void __launch_bounds__(256) k_col_starts(const uint32_t *__restrict__ keys, long nitems, long ncols,
+                                                    long *__restrict__ col_start) {
+  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c <= ncols; c += (long)gridDim.x * blockDim.x) {
+    long lo = 0, hi = nitems;
+    while (lo < hi) {
+      const long mid = (lo + hi) >> 1;
+      if (keys[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+    }
+    col_start[c] = lo;
+  }
+}
+
+int tile_count(int dtype, long m_local) {
+  const long tile_rows = 65536 / (long)dtype_size(dtype);
+  return (int)((m_local + tile_rows - 1) / tile_rows);
+}
+
+void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, const uint64_t *d_items, long nitems,
+                       ItemRec *d_recs, long n_local, long *d_col_start, cudaStream_t s) {
+  if (nitems <= 0) return;
+  const long cap = (long)kernel_sm_count() * 8;
+  long blocks = std::min((nitems + 255) / 256, cap);
+  k_build_recs<<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs);
+  if (d_col_start) {
+    blocks = std::min((n_local + 256) / 256, cap);
+    k_col_starts<<<(unsigned)blocks, 256, 0, s>>>(d_keys, nitems, n_local, d_col_start);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (6a) scatter-add with RED: apply<T> of the reference (:178-187). One warp per item (one
+// column chunk of one segment, <= 256 rows). Values stream in coalesced; every destination
+// element is a RED.ADD at local[col*LLD + lrow[a]]. Items arrive sorted by destination
+// column, so the active window of the local block is a few columns wide and stays in L2.
+// Best when the flush touches the local block sparsely (few hits per column).
 // ------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void red_add(T *p, T v) {
@@ -426,27 +486,21 @@ __device__ __forceinline__ bool mask_keep(int mask, long grow, long gcol) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_apply(const Seg *__restrict__ segs, const uint64_t *__restrict__ items,
-                                               long nitems, T *__restrict__ local, Geom g) {
+__global__ void __launch_bounds__(256) k_apply_red(const ItemRec *__restrict__ recs, long nitems, T *__restrict__ local,
+                                                   Geom g) {
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
   for (long t = warp; t < nitems; t += nwarps) {
-    const uint64_t it = items[t];
-    const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
-    const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
-    const int ch = (int)(it & ((1u << kItemChunkBits) - 1u));
-    const Seg s = segs[sid];
-    const int a0 = ch * kRowChunk;
-    const int a1 = min(s.nr, a0 + kRowChunk);
-    const int lc = s.lcol[b];
-    T *__restrict__ dcol = local + (long)lc * g.lld;
-    const T *__restrict__ v = static_cast<const T *>(s.vals) + (long)b * s.col_stride;
-    const int *__restrict__ lrow = s.lrow;
-    if (s.mask == 0 && s.row_stride == 1) {
-      int a = a0 + lane;
+    const ItemRec r = recs[t];
+    T *__restrict__ dcol = local + (long)r.col * g.lld;
+    const T *__restrict__ v = static_cast<const T *>(r.v);
+    const int *__restrict__ lrow = r.lrow;
+    const int mask = r.mask_flags & 0xff;
+    if (mask == 0 && r.row_stride == 1) {
+      int a = lane;
       // 4 independent value/index loads in flight per lane before the REDs
-      for (; a + 96 < a1; a += 128) {
+      for (; a + 96 < r.n; a += 128) {
         const T x0 = v[a], x1 = v[a + 32], x2 = v[a + 64], x3 = v[a + 96];
         const int r0 = lrow[a], r1 = lrow[a + 32], r2 = lrow[a + 64], r3 = lrow[a + 96];
         red_add(dcol + r0, x0);
@@ -454,110 +508,272 @@ __global__ void __launch_bounds__(256) k_apply(const Seg *__restrict__ segs, con
         red_add(dcol + r2, x2);
         red_add(dcol + r3, x3);
       }
-      for (; a < a1; a += 32) red_add(dcol + lrow[a], v[a]);
+      for (; a < r.n; a += 32) red_add(dcol + lrow[a], v[a]);
     } else {
-      const long gcol = global_index(lc, g.nb, g.npcol, g.mypcol);
-      for (int a = a0 + lane; a < a1; a += 32) {
-        const int r = lrow[a];
-        if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
-        red_add(dcol + r, v[(long)a * s.row_stride]);
+      const long gcol = global_index(r.col, g.nb, g.npcol, g.mypcol);
+      for (int a = lane; a < r.n; a += 32) {
+        const int row = lrow[a];
+        if (mask != 0 && !mask_keep(mask, global_index(row, g.mb, g.nprow, g.myprow), gcol)) continue;
+        red_add(dcol + row, v[(long)a * r.row_stride]);
       }
     }
   }
 }
 
-void launch_apply(int dtype, const Seg *d_segs, const uint64_t *d_items, long nitems, void *d_local, const Geom &g,
-                  cudaStream_t s) {
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return per_sm * kernel_sm_count();
+}
+
+template <typename T>
+static void launch_apply_red_t(const ItemRec *d_recs, long nitems, T *d_local, const Geom &g, cudaStream_t s) {
+  // exactly one resident wave: the strided item order is also the time order of the sweep
+  static const int resident = resident_blocks(k_apply_red<T>, 256, 0);
+  const long blocks = std::min((nitems + 7) / 8, (long)resident);
+  k_apply_red<T><<<(unsigned)blocks, 256, 0, s>>>(d_recs, nitems, d_local, g);
+}
+
+void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_local, const Geom &g, cudaStream_t s) {
   if (nitems <= 0) return;
-  const long warps_per_block = 8;
-  long blocks = (nitems + warps_per_block - 1) / warps_per_block;
-  const long cap = (long)kernel_sm_count() * 8;  // 8 blocks x 8 warps = 64 warps per SM
-  if (blocks > cap) blocks = cap;
   switch (dtype) {
-    case 0:
-      k_apply<double><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<double *>(d_local), g);
-      break;
-    case 1:
-      k_apply<float><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<float *>(d_local), g);
-      break;
-    default:
-      k_apply<int><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_items, nitems, static_cast<int *>(d_local), g);
-      break;
+    case 0: launch_apply_red_t(d_recs, nitems, static_cast<double *>(d_local), g, s); break;
+    case 1: launch_apply_red_t(d_recs, nitems, static_cast<float *>(d_local), g, s); break;
+    default: launch_apply_red_t(d_recs, nitems, static_cast<int *>(d_local), g, s); break;
   }
 }
 
+// ------------------------------------------------------------------------------------
+// (6b) column-tile scatter-add. One block owns one tile of the local block — one column x
+// kTileWarps row bands — in shared memory, and each WARP owns one band of it. The block walks
+// the column's run of items in sorted order; for every item a warp takes exactly the rows
+// that fall into its band (a contiguous sub-range, because an update's row indices are
+// strictly increasing; the sub-range bounds were precomputed once per segment chunk) and adds
+// them into its band with plain shared-memory read-modify-write. Warps never touch each
+// other's bands, so there is no atomic and no block barrier inside a run; values and row
+// indices are prefetched kValStages items ahead with cp.async into warp-private rings.
+// Finally the tile is added to HBM with coalesced loads/stores, skipping 32-byte sectors
+// nobody touched. A tile has one owner and a band's items are applied in a fixed order, so
+// the result is bit-exact run to run (this is also the deterministic-order mode). DRAM
+// traffic is the compulsory s*E + 2*s*(touched sectors) instead of one sector round trip
+// per element. Best when the flush hits the local block densely.
+// ------------------------------------------------------------------------------------
+constexpr int kRecChunk = 128;  // items of a run staged in shared memory at a time (multiple of 2*kTileBlk)
+constexpr int kTileBlk = 8;     // items whose values / row indices a thread keeps in flight in registers
 
-// ------------------------------------------------------------------------------------
-// (6') deterministic order: the items are stably sorted by destination column, so all the
-// contributions to one column form one run in a fixed order (source rank, update, column of
-// the update, row chunk). One warp owns one column: it walks the run item by item and does a
-// plain load-add-store per element (no atomics; lanes of one item hit distinct rows when the
-// update's row indices are strictly increasing, otherwise lane 0 applies the item serially).
-// Accumulation order per element is therefore fixed => bit-exact run to run.
-// ------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) k_apply_det(const Seg *__restrict__ segs, const uint32_t *__restrict__ keys,
-                                                   const uint64_t *__restrict__ items, long nitems, T *local, Geom g,
-                                                   long ncols) {
-  const int lane = threadIdx.x & 31;
-  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long c = warp; c < ncols; c += nwarps) {
-    long lo = 0, hi = nitems;  // lower_bound(keys, c)
-    while (lo < hi) {
-      const long mid = (lo + hi) >> 1;
-      if (keys[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
-    }
-    T *dcol = local + c * g.lld;
-    const long gcol = global_index(c, g.nb, g.npcol, g.mypcol);
-    for (long t = lo; t < nitems && keys[t] == (uint32_t)c; ++t) {
-      const uint64_t it = items[t];
-      const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
-      const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
-      const int ch = (int)(it & ((1u << kItemChunkBits) - 1u));
-      const Seg s = segs[sid];
-      const int a0 = ch * kRowChunk;
-      const int a1 = min(s.nr, a0 + kRowChunk);
-      const T *__restrict__ v = static_cast<const T *>(s.vals) + (long)b * s.col_stride;
-      const int *__restrict__ lrow = s.lrow;
-      if (s.flags & kSegRowsMayRepeat) {
-        if (lane == 0)
-          for (int a = a0; a < a1; ++a) {
-            const int r = lrow[a];
-            if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
-            __stcg(dcol + r, __ldcg(dcol + r) + v[(long)a * s.row_stride]);
+struct TileItem {  // one staged item, 32 bytes
+  const T *v;       // first value
+  const int *rows;  // row indices
+  int n;            // rows (0 for padding / serially applied items)
+  int stride;       // elements between rows in v
+  int mf;           // mask | flags << 8
+  int pad;
+};
+
+template <typename T>
+struct TileSmem {
+  static constexpr int kTileRows = 65536 / (int)sizeof(T);
+  T acc[kTileRows];             // 64 KiB: the tile (one column x kTileRows rows)
+  TileItem<T> item[kRecChunk];  // 4 KiB
+};
+
+// largest local row whose global row index is <= gcol (-1 if none): with it the triangular
+// masks of the symmetric update / fill_lower (:654, :701) become one integer compare per row
+__device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geom &g) {
+  long lo = 0, hi = m_local;  // first local row with global index > gcol
+  while (lo < hi) {
+    const long mid = (lo + hi) >> 1;
+    if (global_index(mid, g.mb, g.nprow, g.myprow) <= gcol) lo = mid + 1; else hi = mid;
+  }
+  return (int)lo - 1;
+}
+
+// fetch element `tid` of the kTileBlk items starting at staged index j0 (plain items: stride 1)
+template <typename T, bool kMulti>
+__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int r0, int h, int (&row)[kTileBlk],
+                                                T (&val)[kTileBlk]) {
+#pragma unroll
+  for (int i = 0; i < kTileBlk; ++i) {
+    const TileItem<T> t = it[i];
+    const bool ok = tid < t.n;
+    const int aa = ok ? tid : 0;  // idle threads re-read element 0 (always valid memory)
+    const int rr = __ldg(t.rows + aa) - r0;
+    row[i] = (ok && (unsigned)rr < (unsigned)h) ? rr : -1;
+    if (!kMulti) val[i] = __ldg(t.v + aa);
+  }
+  if (kMulti) {  // taller than one tile: fetch the value only if this tile owns the row
+#pragma unroll
+    for (int i = 0; i < kTileBlk; ++i) val[i] = __ldg(it[i].v + (row[i] >= 0 ? tid : 0));
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void tile_add_block(T *acc, const int (&row)[kTileBlk], const T (&val)[kTileBlk]) {
+#pragma unroll
+  for (int i = 0; i < kTileBlk; ++i) {
+    if (row[i] >= 0) acc[row[i]] += val[i];
+    __syncthreads();  // items strictly in order
+  }
+}
+
+// kMulti: the local block is taller than one tile, so a block only owns part of each item's rows.
+template <typename T, bool kMulti>
+__global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
+                                                       long ncols, int ntiles, long m_local, T *local, Geom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
+  constexpr int kTileRows = TileSmem<T>::kTileRows;
+  const int tid = threadIdx.x;
+  const long nunits = ncols * ntiles;
+  for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const long c = unit / ntiles;
+    const int tile = (int)(unit % ntiles);
+    const long lo = col_start[c], hi = col_start[c + 1];
+    if (lo == hi) continue;  // uniform: nothing for this column in this flush
+    const int r0 = tile * kTileRows;
+    const int h = (int)min((long)kTileRows, m_local - r0);
+    for (int i = tid; i < h; i += 256) sm.acc[i] = T(0);
+
+    for (long base = lo; base < hi; base += kRecChunk) {
+      const int cnt = (int)min((long)kRecChunk, hi - base);
+      __syncthreads();  // previous chunk fully consumed; acc zeroed
+      int special = 0;
+      if (tid < kRecChunk) {
+        // padding entries (tid >= cnt) alias item 0 with n = 0: loads stay in bounds, nothing is added
+        const ItemRec r = recs[base + (tid < cnt ? tid : 0)];
+        TileItem<T> t;
+        t.v = static_cast<const T *>(r.v);
+        t.rows = r.lrow;
+        t.n = tid < cnt ? r.n : 0;
+        t.stride = r.row_stride;
+        t.mf = tid < cnt ? r.mask_flags : 0;
+        t.pad = 0;
+        sm.item[tid] = t;
+        special = tid < cnt ? (r.mask_flags | (r.row_stride != 1)) : 0;
+      }
+      const bool plain = __syncthreads_or(special) == 0;  // no mask, no repeated rows, unit stride
+      if (plain) {
+        // thread t owns element t of every item; block b+1's elements are in flight while block b
+        // is added; one barrier per item keeps the items in order
+        int rowA[kTileBlk], rowB[kTileBlk];
+        T valA[kTileBlk], valB[kTileBlk];
+        const int nblk = (cnt + kTileBlk - 1) / kTileBlk;  // staged padding covers up to kRecChunk
+        tile_load_block<T, kMulti>(sm.item, tid, r0, h, rowA, valA);
+        for (int b = 0; b < nblk; b += 2) {
+          if (b + 1 < nblk) tile_load_block<T, kMulti>(sm.item + (b + 1) * kTileBlk, tid, r0, h, rowB, valB);
+          tile_add_block<T>(sm.acc, rowA, valA);
+          if (b + 1 < nblk) {
+            if (b + 2 < nblk) tile_load_block<T, kMulti>(sm.item + (b + 2) * kTileBlk, tid, r0, h, rowA, valA);
+            tile_add_block<T>(sm.acc, rowB, valB);
           }
+        }
       } else {
-        for (int a = a0 + lane; a < a1; a += 32) {
-          const int r = lrow[a];
-          if (s.mask != 0 && !mask_keep(s.mask, global_index(r, g.mb, g.nprow, g.myprow), gcol)) continue;
-          __stcg(dcol + r, __ldcg(dcol + r) + v[(long)a * s.row_stride]);
+        // masked (symmetric update / fill_lower), strided or repeated-row items: simple in-order loop
+        const int thr = mask_threshold(global_index(c, g.nb, g.npcol, g.mypcol), m_local, g);
+        for (int j = 0; j < cnt; ++j) {
+          const TileItem<T> t = sm.item[j];
+          const int mask = t.mf & 0xff;
+          if (t.mf >> 8) {
+            if (tid == 0) {  // rows may repeat: one thread applies the item serially
+              for (int a = 0; a < t.n; ++a) {
+                const int rr = t.rows[a] - r0;
+                if ((unsigned)rr >= (unsigned)h) continue;
+                if (mask != 0 && (mask == 1) != (rr + r0 <= thr)) continue;
+                sm.acc[rr] += t.v[(long)a * t.stride];
+              }
+            }
+          } else if (tid < t.n) {
+            const int rr = __ldg(t.rows + tid) - r0;
+            if ((unsigned)rr < (unsigned)h && (mask == 0 || (mask == 1) == (rr + r0 <= thr)))
+              sm.acc[rr] += __ldg(t.v + (long)tid * t.stride);
+          }
+          __syncthreads();
         }
       }
-      __syncwarp();
     }
+    __syncthreads();
+
+    // write-back: local[c, r0 + i] += acc[i]; 32-byte sectors, untouched sectors skipped
+    T *dcol = local + c * g.lld + r0;
+    constexpr int kPer = 32 / (int)sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(dcol) & 31) == 0) {
+      const int hv = h / kPer;
+      for (int i0 = 0; i0 < hv; i0 += 2 * 256) {
+        T a[2][kPer];
+        bool any[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * 256 + tid;
+          any[u] = false;
+          if (i < hv) {
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+              a[u][k] = sm.acc[i * kPer + k];
+              any[u] |= a[u][k] != T(0);
+            }
+          }
+        }
+        T p[2][kPer];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (any[u]) {
+            const T *src = dcol + (long)(i0 + u * 256 + tid) * kPer;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) p[u][k] = src[k];
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (any[u]) {
+            T *dst = dcol + (long)(i0 + u * 256 + tid) * kPer;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) dst[k] = p[u][k] + a[u][k];
+          }
+      }
+      for (int i = hv * kPer + tid; i < h; i += 256)
+        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
+    } else {
+      for (int i = tid; i < h; i += 256)
+        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
+    }
+    __syncthreads();  // the next unit re-zeroes acc
   }
 }
 
-void launch_apply_det(int dtype, const Seg *d_segs, const uint32_t *d_sorted_keys, const uint64_t *d_sorted_items,
-                      long nitems, void *d_local, long n_local, const Geom &g, cudaStream_t s) {
+template <typename T>
+static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
+                                const Geom &g, cudaStream_t s) {
+  const size_t smem = sizeof(TileSmem<T>);
+  static bool attr_set = false;
+  static int resident1 = 0, residentM = 0;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_apply_tile<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_apply_tile<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident1 = resident_blocks(k_apply_tile<T, false>, 256, smem);
+    residentM = resident_blocks(k_apply_tile<T, true>, 256, smem);
+    attr_set = true;
+  }
+  const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
+  const long nunits = n_local * ntiles;
+  if (ntiles == 1)
+    k_apply_tile<T, false><<<(unsigned)std::min(nunits, (long)resident1), 256, smem, s>>>(d_recs, d_col_start, n_local, ntiles,
+                                                                                     m_local, d_local, g);
+  else
+    k_apply_tile<T, true><<<(unsigned)std::min(nunits, (long)residentM), 256, smem, s>>>(d_recs, d_col_start, n_local, ntiles,
+                                                                                    m_local, d_local, g);
+}
+
+void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
+                       long n_local, long m_local, const Geom &g, cudaStream_t s) {
   if (nitems <= 0) return;
-  long blocks = (n_local + 7) / 8;
-  const long cap = (long)kernel_sm_count() * 8;
-  if (blocks > cap) blocks = cap;
   switch (dtype) {
-    case 0:
-      k_apply_det<double><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
-                                                          static_cast<double *>(d_local), g, n_local);
-      break;
-    case 1:
-      k_apply_det<float><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
-                                                         static_cast<float *>(d_local), g, n_local);
-      break;
-    default:
-      k_apply_det<int><<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_sorted_keys, d_sorted_items, nitems,
-                                                       static_cast<int *>(d_local), g, n_local);
-      break;
+    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, s); break;
+    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, s); break;
+    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, s); break;
   }
 }
 

@@ -62,14 +62,16 @@ size_t sort_temp_bytes(long nitems, int end_bit);
 void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint32_t *keys_out,
                  const uint64_t *items_in, uint64_t *items_out, long nitems, int end_bit,
                  cudaStream_t s);
-// (6) scatter-add (apply<T>, reference :178-187)
-void launch_apply(int dtype, const Seg *d_segs, const uint64_t *d_items, long nitems,
-                  void *d_local, const Geom &g, cudaStream_t s);
-// (6') deterministic-order scatter-add: one warp owns one destination column and applies its
-// items in sorted (stable) order with plain read-modify-write — bit-exact run to run
-void launch_apply_det(int dtype, const Seg *d_segs, const uint32_t *d_sorted_keys,
-                      const uint64_t *d_sorted_items, long nitems, void *d_local, long n_local,
-                      const Geom &g, cudaStream_t s);
+// (5b) sorted items -> ItemRec (absolute pointers) + start of every destination column's run
+int tile_count(int dtype, long m_local);  // column tiles stacked over the local rows
+void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, const uint64_t *d_items,
+                       long nitems, ItemRec *d_recs, long n_local, long *d_col_start, cudaStream_t s);
+// (6a) scatter-add with RED.ADD, one warp per item (apply<T>, reference :178-187)
+void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_local, const Geom &g,
+                      cudaStream_t s);
+// (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
+void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
+                       void *d_local, long n_local, long m_local, const Geom &g, cudaStream_t s);
 // COO path for elemental updates: local[inds[k]] += vals[k]
 void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local,
                       cudaStream_t s);

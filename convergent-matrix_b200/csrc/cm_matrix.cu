@@ -253,6 +253,8 @@ struct cm_matrix {
   int sorted_sweep = 1;
   int profiling = 0;
   int keep_wire = 0;
+  int apply_kernel = 0;        // 0 auto, 1 RED, 2 column tiles
+  double tile_density = 0.25;  // auto: tile when (elements / local block elements) >= this
 
   // staged updates
   std::vector<UpdDesc> descs;
@@ -271,7 +273,7 @@ struct cm_matrix {
   DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_coo_tmp;
   DevBuf d_valoff, d_idxoff, d_itemoff, d_totals, d_val_base, d_meta_base;
   DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
-  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp;
+  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp, d_recs, d_col_start, d_pairs, d_tile_tmp;
   PinBuf h_counts;
 
   cm_stats stats{};
@@ -396,10 +398,17 @@ MapArenas map_arenas(cm_matrix *M) {
 }
 
 // sort (optional) + scatter-add over nitems (key,item) pairs sitting in keys0/items0
-int sort_and_apply(cm_matrix *M, long nitems, long elements) {
+int sort_and_apply(cm_matrix *M, long nseg, long nitems, long elements) {
   if (nitems <= 0) return CM_OK;
   const uint64_t *items = M->d_items0.as<uint64_t>();
-  if (M->sorted_sweep || M->deterministic) {
+  const uint32_t *keys = M->d_keys0.as<uint32_t>();
+  // which scatter-add: the column-tile kernel pays 2*s bytes per touched sector of a touched
+  // column and no atomics; RED pays one sector round trip per element. Dense flushes -> tile.
+  const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
+  bool tile = M->apply_kernel == 2 || (M->apply_kernel == 0 && density >= M->tile_density);
+  if (M->deterministic) tile = true;
+  const bool sorted = M->sorted_sweep || tile;
+  if (sorted) {
     const int end_bit = std::max(1, ceil_log2(std::max(M->n_local, 2L)));
     const size_t tmp = sort_temp_bytes(nitems, end_bit);
     CM_TRY(M->d_sort_tmp.ensure(tmp));
@@ -409,15 +418,22 @@ int sort_and_apply(cm_matrix *M, long nitems, long elements) {
                 M->d_items1.as<uint64_t>(), nitems, end_bit, M->stream);
     M->stats.kernel_launches += 3;  // CUB radix sort passes (library metadata sort, not the hot op)
     items = M->d_items1.as<uint64_t>();
+    keys = M->d_keys1.as<uint32_t>();
   }
+  CM_TRY(M->d_recs.ensure(sizeof(ItemRec) * (size_t)nitems));
+  if (tile) CM_TRY(M->d_col_start.ensure(8 * (size_t)(M->n_local + 1)));
+  launch_build_recs(M->dtype, M->d_segs.as<Seg>(), keys, items, nitems, M->d_recs.as<ItemRec>(), M->n_local,
+                    tile ? M->d_col_start.as<long>() : nullptr, M->stream);
+  M->stats.kernel_launches += tile ? 2 : 1;
   {
     ScopedTimer t(M, 0, elements);
-    if (M->deterministic)
-      launch_apply_det(M->dtype, M->d_segs.as<Seg>(), M->d_keys1.as<uint32_t>(), items, nitems, M->d_local, M->n_local,
-                       M->g, M->stream);
+    if (tile)
+      launch_apply_tile(M->dtype, M->d_recs.as<ItemRec>(), M->d_col_start.as<long>(), nitems, M->d_local, M->n_local,
+                        M->m_local, M->g, M->stream);
     else
-      launch_apply(M->dtype, M->d_segs.as<Seg>(), items, nitems, M->d_local, M->g, M->stream);
+      launch_apply_red(M->dtype, M->d_recs.as<ItemRec>(), nitems, M->d_local, M->g, M->stream);
     M->stats.kernel_launches += 1;
+    if (tile) M->stats.tile_launches += 1;
   }
   CM_CUDA_TRY(cudaGetLastError());
   return CM_OK;
@@ -471,7 +487,7 @@ int flush_direct(cm_matrix *M) {
                           M->d_segs.as<Seg>(), M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
     }
-    CM_TRY(sort_and_apply(M, nitems, M->staged_elems));
+    CM_TRY(sort_and_apply(M, nupd, nitems, M->staged_elems));
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
@@ -653,7 +669,7 @@ int commit_exchange(cm_matrix *M) {
     launch_build_recv(M->dtype, M->d_msgs.as<MsgRef>(), (int)msgs.size(), max_seg, M->d_segs.as<Seg>(),
                       M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
     M->stats.kernel_launches += 1;
-    CM_TRY(sort_and_apply(M, item_total, elem_total));
+    CM_TRY(sort_and_apply(M, seg_total, item_total, elem_total));
     M->stats.elements_applied += elem_total;
   }
   for (int s = 0; s < P; ++s) {
@@ -906,7 +922,7 @@ int cm_destroy(cm_matrix *M) {
                     &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
                     &M->d_val_base, &M->d_meta_base, &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
                     &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_msgs, &M->d_segs,
-                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp};
+                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp, &M->d_recs, &M->d_col_start, &M->d_pairs, &M->d_tile_tmp};
   for (DevBuf *b : bufs) b->release();
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
@@ -1093,6 +1109,13 @@ int cm_set_deterministic(cm_matrix *M, int on) {
 int cm_set_sorted_sweep(cm_matrix *M, int on) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   M->sorted_sweep = on ? 1 : 0;
+  return CM_OK;
+}
+int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (kernel < 0 || kernel > 2) return fail(CM_ERR_INVALID, "apply kernel must be 0 (auto), 1 (RED) or 2 (tile)");
+  M->apply_kernel = kernel;
+  if (tile_density > 0) M->tile_density = tile_density;
   return CM_OK;
 }
 int cm_set_profiling(cm_matrix *M, int on) {

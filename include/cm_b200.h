@@ -174,6 +174,12 @@ int cm_set_deterministic(cm_matrix *M, int on);
  * default; exposed so benches can show its effect. */
 int cm_set_sorted_sweep(cm_matrix *M, int on);
 
+/* which scatter-add kernel a flush uses: 0 = auto (column tiles in shared memory when the
+ * flush holds >= tile_density update elements per element of the local block, RED.ADD
+ * otherwise), 1 = always RED.ADD, 2 = always column tiles. tile_density <= 0 keeps the
+ * current value (default 0.25). Deterministic mode always uses column tiles. */
+int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
+
 /* PBLAS array descriptor of the local block: {1, ictxt, M, N, MB, NB, 0, 0, LLD}. The
  * reference exposes only the accessors (:550-576); this is the descinit a user writes. */
 int cm_descinit(const cm_matrix *M, int ictxt, int desc[9]);
@@ -195,6 +201,7 @@ typedef struct cm_stats {
   double exchange_ms;      /* NCCL / loopback exchange                                  */
   long apply_launches;
   long apply_elements;     /* elements covered by the timed scatter-add launches        */
+  long tile_launches;      /* scatter-add launches that used the column-tile kernel     */
 } cm_stats;
 int cm_get_stats(cm_matrix *M, cm_stats *out);
 int cm_reset_stats(cm_matrix *M);

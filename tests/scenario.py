@@ -66,7 +66,8 @@ def run_checker(cfg, steps, kind="oracle", wire=False, threshold=None):
     return out
 
 
-def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, deterministic=False, device_api=False):
+def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, deterministic=False, device_api=False,
+             apply_kernel=0):
     """Execute on the GPU. P == 1 uses the process runtime, P > 1 the loopback transport
     (threads-as-ranks on one device). device_api=True feeds slices through
     cm_update_slice_device from torch tensors already resident in HBM."""
@@ -91,6 +92,7 @@ def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, determin
                 M.set_flush_threshold(threshold)
             M.set_sorted_sweep(sorted_sweep)
             M.set_deterministic(deterministic)
+            M.set_apply_kernel(apply_kernel)
         run(setup)
         wires = {}
         for st in steps:

@@ -17,6 +17,20 @@ def test_single_rank_slices(dtype):
     assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("geom", [(1, 1, 2048, 2048, 2048), (2, 2, 2000, 1000, 1024), (1, 1, 20000, 300, 20000)])
+def test_both_scatter_add_kernels(kernel, geom):
+    """RED.ADD kernel (1) and column-tile kernel (2) forced, incl. a local block taller than one
+    shared-memory band (20000 rows of fp64 > 8192)"""
+    nprow, npcol, m, n, lld = geom
+    cfg = Cfg(cm.F64, m, n, nprow, npcol, 64, 64, lld)
+    rng = np.random.default_rng(14)
+    steps = slice_steps(cfg, rng, 6, min(m, 700), min(n, 90), commit_every=3)
+    got = run_cuda(cfg, steps, apply_kernel=kernel)
+    assert all((st["tile_launches"] > 0) == (kernel == 2) for st in got["stats"])
+    assert_blocks_match(cfg, got, run_checker(cfg, steps))
+
+
 def test_single_rank_threshold_flush_and_unsorted_sweep():
     cfg = Cfg(cm.F64, 2048, 2048, 1, 1, 64, 64, 2048)
     rng = np.random.default_rng(12)
@@ -25,7 +39,7 @@ def test_single_rank_threshold_flush_and_unsorted_sweep():
     got = run_cuda(cfg, steps, threshold=50000)
     assert got["stats"][0]["flushes"] > 5
     assert_blocks_match(cfg, got, want)
-    assert_blocks_match(cfg, run_cuda(cfg, steps, sorted_sweep=False), want)
+    assert_blocks_match(cfg, run_cuda(cfg, steps, sorted_sweep=False, apply_kernel=1), want)
 
 
 def test_single_rank_device_api():
