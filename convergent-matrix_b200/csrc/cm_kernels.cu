@@ -562,8 +562,8 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_loc
 // traffic is the compulsory s*E + 2*s*(touched sectors) instead of one sector round trip
 // per element. Best when the flush hits the local block densely.
 // ------------------------------------------------------------------------------------
-constexpr int kRecChunk = 128;  // items of a run staged in shared memory at a time (multiple of 2*kTileBlk)
-constexpr int kTileBlk = 8;     // items whose values / row indices a thread keeps in flight in registers
+constexpr int kRecChunk = 132;  // items of a run staged in shared memory at a time (multiple of 2*kTileBlk)
+constexpr int kTileBlk = 6;     // items whose values / row indices a thread keeps in flight in registers
 
 template <typename T>
 struct TileItem {  // one staged item, 32 bytes
@@ -698,41 +698,28 @@ __global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict
     }
     __syncthreads();
 
-    // write-back: local[c, r0 + i] += acc[i]; 32-byte sectors, untouched sectors skipped
+    // write-back: local[c, r0 + i] += acc[i], 16 bytes per thread step, untouched pieces skipped
     T *dcol = local + c * g.lld + r0;
-    constexpr int kPer = 32 / (int)sizeof(T);
-    if ((reinterpret_cast<uintptr_t>(dcol) & 31) == 0) {
+    constexpr int kPer = 16 / (int)sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) {
       const int hv = h / kPer;
-      for (int i0 = 0; i0 < hv; i0 += 2 * 256) {
-        T a[2][kPer];
-        bool any[2];
+#pragma unroll 4
+      for (int i = tid; i < hv; i += 256) {
+        T a[kPer];
+        bool any = false;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int i = i0 + u * 256 + tid;
-          any[u] = false;
-          if (i < hv) {
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-              a[u][k] = sm.acc[i * kPer + k];
-              any[u] |= a[u][k] != T(0);
-            }
-          }
+        for (int k = 0; k < kPer; ++k) {
+          a[k] = sm.acc[i * kPer + k];
+          any |= a[k] != T(0);
         }
-        T p[2][kPer];
+        if (any) {
+          T *p = dcol + (long)i * kPer;
+          T q[kPer];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (any[u]) {
-            const T *src = dcol + (long)(i0 + u * 256 + tid) * kPer;
+          for (int k = 0; k < kPer; ++k) q[k] = p[k];
 #pragma unroll
-            for (int k = 0; k < kPer; ++k) p[u][k] = src[k];
-          }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (any[u]) {
-            T *dst = dcol + (long)(i0 + u * 256 + tid) * kPer;
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) dst[k] = p[u][k] + a[u][k];
-          }
+          for (int k = 0; k < kPer; ++k) p[k] = q[k] + a[k];
+        }
       }
       for (int i = hv * kPer + tid; i < h; i += 256)
         if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
