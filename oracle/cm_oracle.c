@@ -73,6 +73,11 @@ cmo_matrix *cmo_create(int dtype, long m, long n, long nprow, long npcol, long m
     long myrow = r / npcol, mycol = r % npcol; /* row-major grid (see header) */
     M->m_local[r] = cmo_roc(m, nprow, myrow, mb); /* :412 */
     M->n_local[r] = cmo_roc(n, npcol, mycol, nb); /* :413 */
+    /* the reference asserts these (:417-428); a checker must not scribble instead */
+    if (m <= 0 || n <= 0 || M->m_local[r] <= 0 || M->n_local[r] <= 0 || M->m_local[r] > lld) {
+      cmo_destroy(M);
+      return NULL;
+    }
     M->local[r] = (unsigned char *)calloc((size_t)(lld * M->n_local[r]) + 1, M->esz); /* :415,:432 */
   }
   return M;

@@ -87,6 +87,8 @@ class Oracle:
         self.lld = lld
         self.P = nprow * npcol
         self.h = self.L.cmo_create(dtype, m, n, nprow, npcol, mb, nb, lld)
+        if not self.h:
+            raise ValueError(f"invalid distribution (reference asserts :417-428): {self.geom}")
         if record_wire:
             self.L.cmo_wire_enable(self.h, 1)
 
