@@ -205,6 +205,8 @@ def bench_ours(args):
     if args.deterministic:
         M.set_deterministic(True)
     M.set_apply_kernel({"auto": 0, "red": 1, "tile": 2}[args.apply_kernel])
+    if nranks > 1:
+        M.set_exchange_mode({"auto": 0, "nccl": 1, "p2p": 2}[args.exchange])
     data, ix, jx = gen_inputs(spec, rank, torch, device)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(M.stream(), device=device)
@@ -316,11 +318,16 @@ def bench_ours(args):
                 "launches": st["apply_launches"], "avg_launch_ms": st["apply_ms"] / max(1, st["apply_launches"]),
                 "elements_per_launch": st["apply_elements"] // max(1, st["apply_launches"]),
                 "kernel_share_of_step": st["apply_ms"] / ms}
-        if nranks > 1 and st["exchange_ms"] > 0:
-            roof["exchange"] = {"bytes_sent_per_rank_per_step": st["bytes_sent"] // args.steps,
-                                "exchange_ms_per_step": st["exchange_ms"] / args.steps,
-                                "achieved_GBps_per_direction": st["bytes_sent"] / (st["exchange_ms"] * 1e-3) / 1e9,
-                                "peak_GBps_per_direction": 770.0}
+        if nranks > 1:
+            p2p = M.exchange_mode() == 2
+            # p2p: the exchange IS the pack kernel (its stores cross NVLink); nccl: the all-to-all-v
+            xms = st["pack_ms"] if p2p else st["exchange_ms"]
+            if xms > 0:
+                roof["exchange"] = {"mode": "p2p (pack kernel stores over NVLink)" if p2p else "nccl all-to-all-v",
+                                    "bytes_sent_per_rank_per_step": st["bytes_sent"] // args.steps,
+                                    "exchange_ms_per_step": xms / args.steps,
+                                    "achieved_GBps_per_direction": st["bytes_sent"] / (xms * 1e-3) / 1e9,
+                                    "peak_GBps_per_direction": 770.0}
 
     # ---- CPU baseline (rank 0, N = 1 only): reference header over the in-repo SMP shim -------
     cpu = None
@@ -335,7 +342,7 @@ def bench_ours(args):
             "config": {"workload": spec["name"], "updates_per_rank_per_step": spec["U"], "grid": [spec["nprow"], spec["npcol"]],
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
-                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "payload_bytes_per_rank_per_step": step_bytes},
+                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": ("p2p" if M.exchange_mode() == 2 else "nccl") if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
             "commit_latency_us": {"empty": lat_empty, "one_update": lat_one},
@@ -430,6 +437,8 @@ def main():
     ap.add_argument("--unsorted", action="store_true", help="disable the column-sorted sweep")
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--apply-kernel", default="auto", choices=["auto", "red", "tile"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="auto/p2p: the pack kernel stores into the owners' arenas over NVLink; nccl: grouped send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-updates", type=int, default=0, help="updates per rank per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -86,6 +86,8 @@ SYMBOLS = {
     "cm_set_deterministic": (_i, [_vp, _i]),
     "cm_set_sorted_sweep": (_i, [_vp, _i]),
     "cm_set_apply_kernel": (_i, [_vp, _i, C.c_double]),
+    "cm_set_exchange_mode": (_i, [_vp, _i]),
+    "cm_get_exchange_mode": (_i, [_vp]),
     "cm_descinit": (_i, [_vp, _i, C.POINTER(_i)]),
     "cm_get_stats": (_i, [_vp, C.POINTER(Stats)]),
     "cm_reset_stats": (_i, [_vp]),
@@ -309,6 +311,12 @@ class Matrix:
 
     def set_apply_kernel(self, kernel, tile_density=0.0):
         _check(self.L.cm_set_apply_kernel(self.h, kernel, tile_density))
+
+    def set_exchange_mode(self, mode):
+        _check(self.L.cm_set_exchange_mode(self.h, mode))
+
+    def exchange_mode(self):
+        return self.L.cm_get_exchange_mode(self.h)
 
     def set_profiling(self, on):
         _check(self.L.cm_set_profiling(self.h, int(on)))

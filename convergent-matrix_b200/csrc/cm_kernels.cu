@@ -182,30 +182,9 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas m
   if (threadIdx.x == 0) sa.totals[dst] = MsgCounts{running.a, running.b, (long)nupd, running.c};
 }
 
-__global__ void k_finalize_msgs(int P, ScanArenas sa, char *send_meta) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  long vb = 0, mbs = 0;
-  for (int d = 0; d < P; ++d) {
-    const MsgCounts c = sa.totals[d];
-    sa.val_base[d] = vb;
-    sa.meta_base[d] = mbs;
-    WireHdr *h = reinterpret_cast<WireHdr *>(send_meta + mbs);
-    h->nseg = c.nseg;
-    h->nvals = c.nvals;
-    h->nidx = c.nidx;
-    h->nitems = c.nitems;
-    vb += c.nvals;
-    mbs += meta_bytes(c.nseg, c.nidx);
-  }
-  sa.val_base[P] = vb;
-  sa.meta_base[P] = mbs;
-}
-
-void launch_scan(const UpdDesc *, int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
-                 char *d_send_meta, cudaStream_t s) {
+void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
   const int P = (int)(g.nprow * g.npcol);
   k_scan_dest<<<P, 256, 0, s>>>(nupd, g, ma, sa);
-  k_finalize_msgs<<<1, 32, 0, s>>>(P, sa, d_send_meta);
 }
 
 // ------------------------------------------------------------------------------------
@@ -216,7 +195,7 @@ void launch_scan(const UpdDesc *, int nupd, const Geom &g, const MapArenas &ma, 
 // ------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs, int nupd, Geom g, MapArenas ma,
-                                              ScanArenas sa, T *__restrict__ send_vals, char *__restrict__ send_meta) {
+                                              ScanArenas sa) {
   const int u = blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol;
@@ -239,7 +218,7 @@ __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs,
       const int nr = roff[p + 1] - roff[p];
       if (nr == 0) continue;
       const int dst = p * npcol + q;
-      T *__restrict__ out = send_vals + sa.val_base[dst] + sa.valoff[(long)dst * nupd + u] + (long)b * nr;
+      T *__restrict__ out = static_cast<T *>(sa.dst_vals[dst]) + sa.valoff[(long)dst * nupd + u] + (long)b * nr;
       const int *__restrict__ rp = rpos + roff[p];
       if (!d.trans) {
         const T *__restrict__ col = data + d.ld * j;
@@ -257,7 +236,15 @@ __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs,
     for (int dst = 0; dst < nprow * npcol; ++dst) {
       const int p = dst / npcol, q = dst % npcol;
       const int nr = roff[p + 1] - roff[p], nc = coff[q + 1] - coff[q];
-      char *mb = send_meta + sa.meta_base[dst];
+      char *mb = sa.dst_meta[dst];
+      if (u == 0 && tid == 0) {  // message header
+        const MsgCounts c = sa.totals[dst];
+        WireHdr *h = reinterpret_cast<WireHdr *>(mb);
+        h->nseg = c.nseg;
+        h->nvals = c.nvals;
+        h->nidx = c.nidx;
+        h->nitems = c.nitems;
+      }
       WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
       const bool empty = (long)nr * nc == 0;
       const long ioff = sa.idxoff[(long)dst * nupd + u];
@@ -290,19 +277,13 @@ static int pick_ytiles(int nupd, long max_cols) {
 }
 
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
-                 const ScanArenas &sa, void *d_send_vals, char *d_send_meta, cudaStream_t s) {
+                 const ScanArenas &sa, cudaStream_t s) {
   if (nupd <= 0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
   switch (dtype) {
-    case 0:
-      k_pack<double><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<double *>(d_send_vals), d_send_meta);
-      break;
-    case 1:
-      k_pack<float><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<float *>(d_send_vals), d_send_meta);
-      break;
-    default:
-      k_pack<int><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa, static_cast<int *>(d_send_vals), d_send_meta);
-      break;
+    case 0: k_pack<double><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    case 1: k_pack<float><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    default: k_pack<int><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
   }
 }
 

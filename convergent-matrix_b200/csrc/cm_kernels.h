@@ -34,8 +34,8 @@ struct ScanArenas {
   long *idxoff;    // [P * nupd]
   long *itemoff;   // [P * nupd]
   MsgCounts *totals;  // [P]
-  long *val_base;  // [P+1] start of each owner's values in the send arena (elements)
-  long *meta_base; // [P+1] start of each owner's metadata in the send-meta arena (bytes)
+  void **dst_vals;    // [P] where this rank's message to owner d starts: values ...
+  char **dst_meta;    // [P] ... and metadata. May point into a PEER's receive arena (NVLink stores).
 };
 
 size_t dtype_size(int dtype);
@@ -43,13 +43,12 @@ size_t dtype_size(int dtype);
 // (1) owner map + stable grouping by owner row / column (warp match + prefix sums)
 void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
                       cudaStream_t s);
-// (2) per-owner scans over the staged updates, then message bases + wire headers
-void launch_scan(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
-                 const ScanArenas &sa, char *d_send_meta, cudaStream_t s);
-// (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata
+// (2) per-owner scans over the staged updates (sizes of every message)
+void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
+// (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
+// to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g,
-                 const MapArenas &ma, const ScanArenas &sa, void *d_send_vals,
-                 char *d_send_meta, cudaStream_t s);
+                 const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,
                          const Geom &g, const MapArenas &ma, Seg *d_segs, uint32_t *d_keys,

@@ -245,6 +245,13 @@ struct cm_matrix {
   bool mirror_valid = false;
   std::vector<void *> peer_local;  // remote read (operator(), :585-596): IPC / same-process
   std::vector<bool> peer_ipc_open;
+  // receive arenas of every rank (mine included), see ensure_recv_arenas()
+  bool p2p_possible = false;
+  bool p2p = false;         // sources store straight into the owners' arenas (pack == exchange)
+  int exchange_mode = 0;    // 0 auto, 1 transport all-to-all-v, 2 peer-to-peer stores
+  std::vector<void *> peer_vals, peer_meta;
+  std::vector<size_t> cap_vals, cap_meta;
+  std::vector<bool> peer_arena_open;
 
   cudaStream_t stream = nullptr;
   long flush_threshold = CM_DEFAULT_FLUSH_THRESHOLD;
@@ -271,9 +278,9 @@ struct cm_matrix {
 
   // device work buffers
   DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_coo_tmp;
-  DevBuf d_valoff, d_idxoff, d_itemoff, d_totals, d_val_base, d_meta_base;
+  DevBuf d_valoff, d_idxoff, d_itemoff, d_totals;
   DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
-  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp, d_recs, d_col_start, d_pairs, d_tile_tmp;
+  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp, d_recs, d_col_start, d_dst_ptrs;
   PinBuf h_counts;
 
   cm_stats stats{};
@@ -500,46 +507,115 @@ int flush_direct(cm_matrix *M) {
   return CM_OK;
 }
 
-// ---- general commit path: pack -> exchange -> scatter-add (also used for P == 1 when the
-// wire is being captured, so the pack kernels are testable on one rank) ----
+// ---- receive arenas ---------------------------------------------------------------------
+// Every rank owns a values arena and a metadata arena that hold the messages of ONE commit from
+// all sources (its own included). With peer-to-peer exchange the sources' pack kernels store
+// straight into them over NVLink, so every rank keeps them mapped (CUDA IPC; plain pointers when
+// the ranks share a process). Capacities only grow; because every rank sees the full counts
+// matrix, every rank takes the same growth decision for every arena without extra messages.
+struct ArenaHandles {
+  cudaIpcMemHandle_t vals, meta;
+  void *pvals, *pmeta;  // same-process transports
+};
+
+size_t grown(size_t need) { return need + need / 4 + (1u << 20); }
+
+int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const std::vector<size_t> &need_meta) {
+  const int P = M->P, me = M->me;
+  Transport *tp = M->ctx->tp;
+  if (!M->p2p) {  // only my own arenas matter
+    CM_TRY(M->d_recv_vals.ensure(std::max(need_vals[me], (size_t)256)));
+    CM_TRY(M->d_recv_meta.ensure(std::max(need_meta[me], (size_t)256)));
+    M->peer_vals[me] = M->d_recv_vals.p;
+    M->peer_meta[me] = M->d_recv_meta.p;
+    return CM_OK;
+  }
+  bool any = false;
+  std::vector<char> grow(P, 0);
+  for (int d = 0; d < P; ++d)
+    if (need_vals[d] > M->cap_vals[d] || need_meta[d] > M->cap_meta[d]) grow[d] = 1, any = true;
+  if (!any) return CM_OK;
+  // 1. nobody keeps a mapping of an arena that is about to be freed
+  for (int d = 0; d < P; ++d)
+    if (grow[d] && d != me && M->peer_arena_open[d]) {
+      cudaIpcCloseMemHandle(M->peer_vals[d]);
+      cudaIpcCloseMemHandle(M->peer_meta[d]);
+      M->peer_arena_open[d] = false;
+    }
+  CM_TRY(tp->barrier(M->stream));
+  // 2. owners reallocate
+  if (grow[me]) {
+    M->d_recv_vals.release();
+    M->d_recv_meta.release();
+    CM_TRY(M->d_recv_vals.ensure(grown(need_vals[me])));
+    CM_TRY(M->d_recv_meta.ensure(grown(need_meta[me])));
+  }
+  // 3. publish + map
+  ArenaHandles mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.pvals = M->d_recv_vals.p;
+  mine.pmeta = M->d_recv_meta.p;
+  if (!tp->same_process()) {
+    CM_CUDA_TRY(cudaIpcGetMemHandle(&mine.vals, M->d_recv_vals.p));
+    CM_CUDA_TRY(cudaIpcGetMemHandle(&mine.meta, M->d_recv_meta.p));
+  }
+  std::vector<ArenaHandles> all(P);
+  CM_TRY(tp->host_allgather(&mine, all.data(), sizeof(mine), M->stream));
+  for (int d = 0; d < P; ++d) {
+    if (!grow[d]) continue;
+    if (d == me || tp->same_process()) {
+      M->peer_vals[d] = all[d].pvals;
+      M->peer_meta[d] = all[d].pmeta;
+    } else {
+      CM_CUDA_TRY(cudaIpcOpenMemHandle(&M->peer_vals[d], all[d].vals, cudaIpcMemLazyEnablePeerAccess));
+      CM_CUDA_TRY(cudaIpcOpenMemHandle(&M->peer_meta[d], all[d].meta, cudaIpcMemLazyEnablePeerAccess));
+      M->peer_arena_open[d] = true;
+    }
+    // every rank records the same capacity the owner allocated at least
+    M->cap_vals[d] = grown(need_vals[d]);
+    M->cap_meta[d] = grown(need_meta[d]);
+  }
+  return CM_OK;
+}
+
+// ---- general commit path (also used for P == 1 when the wire is being captured, so the pack
+// kernels are testable on one rank):
+//   map -> scan -> counts all-gather (the one host sync) -> pack -> [all-to-all-v] -> barrier ->
+//   build -> sort -> scatter-add -> barrier
+// The pack kernel writes every message where the owner will read it: with peer-to-peer exchange
+// that is the owner's receive arena itself (pack and exchange are ONE kernel whose stores cross
+// NVLink); otherwise a local send arena that a grouped ncclSend/ncclRecv all-to-all-v moves.
 int commit_exchange(cm_matrix *M) {
   const int P = M->P, me = M->me;
   const int nupd = (int)M->descs.size();
   Transport *tp = M->ctx->tp;
   const size_t esz = M->esz;
 
-  // -- source side: map, scan, pack ----------------------------------------------------
+  // -- source side: owner map + per-owner sizes -------------------------------------------
   CM_TRY(upload_staged(M));
   const size_t pu = (size_t)P * std::max(nupd, 1);
   CM_TRY(M->d_valoff.ensure(8 * pu));
   CM_TRY(M->d_idxoff.ensure(8 * pu));
   CM_TRY(M->d_itemoff.ensure(8 * pu));
   CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P));
-  CM_TRY(M->d_val_base.ensure(8 * (size_t)(P + 1)));
-  CM_TRY(M->d_meta_base.ensure(8 * (size_t)(P + 1)));
-  // exact sizes are known on the host: every element goes to exactly one owner, and an
-  // update contributes (npcol*m_u + nprow*n_u) index words at most
-  const size_t send_val_bytes = (size_t)M->staged_elems * esz;
-  const size_t send_meta_cap = (size_t)P * (sizeof(WireHdr) + 16) + (size_t)P * nupd * sizeof(WireSeg) +
-                               4 * ((size_t)M->g.npcol * M->staged_rows + (size_t)M->g.nprow * M->staged_cols);
-  CM_TRY(M->d_send_vals.ensure(std::max(send_val_bytes, (size_t)256)));
-  CM_TRY(M->d_send_meta.ensure(send_meta_cap));
+  CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P));
   const MapArenas ma = map_arenas(M);
   ScanArenas sa;
   sa.valoff = M->d_valoff.as<long>();
   sa.idxoff = M->d_idxoff.as<long>();
   sa.itemoff = M->d_itemoff.as<long>();
   sa.totals = M->d_totals.as<MsgCounts>();
-  sa.val_base = M->d_val_base.as<long>();
-  sa.meta_base = M->d_meta_base.as<long>();
-  {
-    ScopedTimer t(M, 1, 0);
-    launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
-    launch_scan(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->d_send_meta.as<char>(), M->stream);
-    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->d_send_vals.p, M->d_send_meta.as<char>(),
-                M->stream);
-    M->stats.kernel_launches += (nupd ? 2 : 0) + 2;
+  sa.dst_vals = M->d_dst_ptrs.as<void *>();
+  sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + P);
+  cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
+  if (M->profiling) {
+    ev_pack0 = get_event(M);
+    ev_pack1 = get_event(M);
+    cudaEventRecord(ev_pack0, M->stream);
   }
+  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
+  launch_scan(nupd, M->g, ma, sa, M->stream);
+  M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
   CM_CUDA_TRY(cudaGetLastError());
 
   // -- counts: all-gather the per-owner totals, read them back (the one host sync) --------
@@ -558,31 +634,66 @@ int commit_exchange(cm_matrix *M) {
     CM_TRY(tp->host_allgather(mine.data(), coo_counts, 8 * (size_t)P, M->stream));
   }
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-  // the borrowed device payloads and index arrays are no longer needed: pack has finished
 
-  // -- lay out send / receive regions ---------------------------------------------------
+  // -- layout of every rank's receive arenas (identical computation on every rank) ----------
+  // rbase_v[d*(P+1) + s]: element offset of source s's values inside owner d's arena
+  std::vector<long> rbase_v((size_t)P * (P + 1), 0), rbase_m((size_t)P * (P + 1), 0);
+  std::vector<size_t> need_vals(P), need_meta(P);
+  for (int d = 0; d < P; ++d) {
+    long *bv = &rbase_v[(size_t)d * (P + 1)], *bm = &rbase_m[(size_t)d * (P + 1)];
+    for (int s = 0; s < P; ++s) {
+      const MsgCounts &c = counts[(size_t)s * P + d];
+      bv[s + 1] = bv[s] + ((c.nvals + 1) & ~1L);  // keep every message 16-byte aligned
+      bm[s + 1] = bm[s] + meta_bytes(c.nseg, c.nidx);
+    }
+    need_vals[d] = (size_t)bv[P] * esz;
+    need_meta[d] = (size_t)bm[P];
+  }
+  CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
+
+  // -- where my messages go ------------------------------------------------------------------
+  // p2p: straight into the owners' arenas. Otherwise: my own message into my arena, the others
+  // into a local send arena laid out owner after owner.
   std::vector<long> s_val_base(P + 1, 0), s_meta_base(P + 1, 0);
   for (int d = 0; d < P; ++d) {
     const MsgCounts &c = counts[(size_t)me * P + d];
-    s_val_base[d + 1] = s_val_base[d] + c.nvals;
-    s_meta_base[d + 1] = s_meta_base[d] + meta_bytes(c.nseg, c.nidx);
+    const bool staged = !M->p2p && d != me;
+    s_val_base[d + 1] = s_val_base[d] + (staged ? ((c.nvals + 1) & ~1L) : 0);
+    s_meta_base[d + 1] = s_meta_base[d] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
   }
-  // COO blob of n elements: [inds x n (8 B)][vals x n], padded so every blob stays 8-aligned
+  if (!M->p2p) {
+    CM_TRY(M->d_send_vals.ensure(std::max((size_t)s_val_base[P] * esz, (size_t)256)));
+    CM_TRY(M->d_send_meta.ensure(std::max((size_t)s_meta_base[P], (size_t)256)));
+  }
+  std::vector<void *> dst_ptrs(2 * (size_t)P);
+  for (int d = 0; d < P; ++d) {
+    if (M->p2p || d == me) {
+      dst_ptrs[d] = static_cast<char *>(M->peer_vals[d]) + (size_t)rbase_v[(size_t)d * (P + 1) + me] * esz;
+      dst_ptrs[P + d] = static_cast<char *>(M->peer_meta[d]) + rbase_m[(size_t)d * (P + 1) + me];
+    } else {
+      dst_ptrs[d] = M->d_send_vals.as<char>() + (size_t)s_val_base[d] * esz;
+      dst_ptrs[P + d] = M->d_send_meta.as<char>() + s_meta_base[d];
+    }
+  }
+  CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                              M->stream));
+  launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->stream);
+  M->stats.kernel_launches += nupd ? 1 : 0;
+  if (M->profiling) {
+    cudaEventRecord(ev_pack1, M->stream);
+    M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+  }
+  CM_CUDA_TRY(cudaGetLastError());
+
+  // -- COO blobs (elemental updates): [inds x n][vals x n] per owner, always via the transport --
   auto coo_blob = [esz](long n) { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); };
-  std::vector<long> r_val_base(P + 1, 0), r_meta_base(P + 1, 0), r_coo_base(P + 1, 0), s_coo_base(P + 1, 0);
+  std::vector<long> r_coo_base(P + 1, 0), s_coo_base(P + 1, 0);
   for (int s = 0; s < P; ++s) {
-    const MsgCounts &c = counts[(size_t)s * P + me];
-    const bool remote = s != me;
-    r_val_base[s + 1] = r_val_base[s] + (remote ? c.nvals : 0);
-    r_meta_base[s + 1] = r_meta_base[s] + (remote ? meta_bytes(c.nseg, c.nidx) : 0);
-    r_coo_base[s + 1] = r_coo_base[s] + (remote ? coo_blob(coo_counts[(size_t)s * P + me]) : 0);
+    r_coo_base[s + 1] = r_coo_base[s] + (s != me ? coo_blob(coo_counts[(size_t)s * P + me]) : 0);
     s_coo_base[s + 1] = s_coo_base[s] + coo_blob((long)M->coo[s].inds.size());
   }
-  CM_TRY(M->d_recv_vals.ensure(std::max((size_t)r_val_base[P] * esz, (size_t)256)));
-  CM_TRY(M->d_recv_meta.ensure(std::max((size_t)r_meta_base[P], (size_t)256)));
   CM_TRY(M->d_recv_coo.ensure(std::max((size_t)r_coo_base[P], (size_t)256)));
   CM_TRY(M->d_send_coo.ensure(std::max((size_t)s_coo_base[P], (size_t)256)));
-  // COO blobs: per owner [inds x n][vals x n]
   for (int d = 0; d < P; ++d) {
     const long n = (long)M->coo[d].inds.size();
     if (!n) continue;
@@ -593,48 +704,72 @@ int commit_exchange(cm_matrix *M) {
     M->stats.h2d_bytes += n * (long)(8 + esz);
   }
 
-  if (M->keep_wire) {
-    M->dbg_meta.resize((size_t)s_meta_base[P]);
-    M->dbg_vals.resize((size_t)s_val_base[P] * esz);
-    if (!M->dbg_meta.empty())
-      CM_CUDA_TRY(cudaMemcpy(M->dbg_meta.data(), M->d_send_meta.p, M->dbg_meta.size(), cudaMemcpyDeviceToHost));
-    if (!M->dbg_vals.empty())
-      CM_CUDA_TRY(cudaMemcpy(M->dbg_vals.data(), M->d_send_vals.p, M->dbg_vals.size(), cudaMemcpyDeviceToHost));
-    M->dbg_meta_base = s_meta_base;
-    M->dbg_val_base = s_val_base;
-    M->dbg_coo = M->coo;
-    M->dbg_valid = true;
-  }
-
-  // -- exchange: one grouped all-to-all-v with three lanes (values, metadata, coo) ---------
-  std::vector<std::vector<XferSpec>> sends(3, std::vector<XferSpec>(P)), recvs(3, std::vector<XferSpec>(P));
+  // -- exchange --------------------------------------------------------------------------------
+  std::vector<std::vector<XferSpec>> sends(3, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
+  std::vector<std::vector<XferSpec>> recvs(3, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
   long sent = 0, received = 0;
+  bool any_lane = false;
   for (int r = 0; r < P; ++r) {
+    if (r == me) continue;
     const MsgCounts &cs = counts[(size_t)me * P + r];
     const MsgCounts &cr = counts[(size_t)r * P + me];
-    const bool remote = r != me;
-    // an all-empty message (no values) still ships its header so the owner can parse it
-    sends[0][r] = XferSpec{M->d_send_vals.as<char>() + (size_t)s_val_base[r] * esz, remote ? (size_t)cs.nvals * esz : 0};
-    sends[1][r] = XferSpec{M->d_send_meta.as<char>() + s_meta_base[r],
-                           remote && cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
-    sends[2][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r],
-                           remote ? (size_t)coo_blob((long)M->coo[r].inds.size()) : 0};
-    recvs[0][r] = XferSpec{M->d_recv_vals.as<char>() + (size_t)r_val_base[r] * esz, remote ? (size_t)cr.nvals * esz : 0};
-    recvs[1][r] = XferSpec{M->d_recv_meta.as<char>() + r_meta_base[r],
-                           remote && cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
-    recvs[2][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r],
-                           remote ? (size_t)coo_blob(coo_counts[(size_t)r * P + me]) : 0};
-    for (int lane = 0; lane < 3; ++lane) {
-      sent += (long)sends[lane][r].bytes;
-      received += (long)recvs[lane][r].bytes;
+    if (!M->p2p) {
+      sends[0][r] = XferSpec{dst_ptrs[r], (size_t)cs.nvals * esz};
+      sends[1][r] = XferSpec{dst_ptrs[P + r], cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
+      recvs[0][r] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[(size_t)me * (P + 1) + r] * esz,
+                             (size_t)cr.nvals * esz};
+      recvs[1][r] = XferSpec{static_cast<char *>(M->peer_meta[me]) + rbase_m[(size_t)me * (P + 1) + r],
+                             cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
     }
+    sends[2][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r], (size_t)coo_blob((long)M->coo[r].inds.size())};
+    recvs[2][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r], (size_t)coo_blob(coo_counts[(size_t)r * P + me])};
+    if (!M->coo[r].inds.size()) sends[2][r].bytes = 0;
+    if (!coo_counts[(size_t)r * P + me]) recvs[2][r].bytes = 0;
+    sent += (long)(cs.nvals * esz + (cs.nvals ? meta_bytes(cs.nseg, cs.nidx) : 0)) + (long)sends[2][r].bytes;
+    received += (long)(cr.nvals * esz + (cr.nvals ? meta_bytes(cr.nseg, cr.nidx) : 0)) + (long)recvs[2][r].bytes;
   }
-  {
+  for (int lane = 0; lane < 3; ++lane)
+    for (int r = 0; r < P; ++r) any_lane |= sends[lane][r].bytes || recvs[lane][r].bytes;
+  // every rank must take the same branch: a rank with nothing to move still joins the group when
+  // any pair moves something. The counts matrix is global knowledge, so decide from it.
+  bool global_lane = false;
+  for (int s = 0; s < P && !global_lane; ++s)
+    for (int d = 0; d < P; ++d)
+      if (s != d && ((!M->p2p && counts[(size_t)s * P + d].nvals) || coo_counts[(size_t)s * P + d])) global_lane = true;
+  (void)any_lane;
+  if (global_lane) {
     ScopedTimer t(M, 2, 0);
     CM_TRY(tp->alltoallv(sends, recvs, M->stream));
   }
   M->stats.bytes_sent += sent;
   M->stats.bytes_received += received;
+  // every source has finished writing into my arenas (p2p: their pack kernels; the transports'
+  // all-to-all-v completes on the stream by itself)
+  if (M->p2p && P > 1) CM_TRY(tp->stream_barrier(M->stream));
+
+  if (M->keep_wire) {
+    // what THIS rank sent to every owner, read back from wherever pack put it
+    CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+    M->dbg_meta_base.assign(P + 1, 0);
+    M->dbg_val_base.assign(P + 1, 0);
+    for (int d = 0; d < P; ++d) {
+      const MsgCounts &c = counts[(size_t)me * P + d];
+      M->dbg_meta_base[d + 1] = M->dbg_meta_base[d] + (c.nvals ? meta_bytes(c.nseg, c.nidx) : 0);
+      M->dbg_val_base[d + 1] = M->dbg_val_base[d] + c.nvals;
+    }
+    M->dbg_meta.resize((size_t)M->dbg_meta_base[P]);
+    M->dbg_vals.resize((size_t)M->dbg_val_base[P] * esz);
+    for (int d = 0; d < P; ++d) {
+      const MsgCounts &c = counts[(size_t)me * P + d];
+      if (!c.nvals) continue;
+      CM_CUDA_TRY(cudaMemcpy(M->dbg_meta.data() + M->dbg_meta_base[d], dst_ptrs[P + d], (size_t)meta_bytes(c.nseg, c.nidx),
+                             cudaMemcpyDefault));
+      CM_CUDA_TRY(cudaMemcpy(M->dbg_vals.data() + (size_t)M->dbg_val_base[d] * esz, dst_ptrs[d], (size_t)c.nvals * esz,
+                             cudaMemcpyDefault));
+    }
+    M->dbg_coo = M->coo;
+    M->dbg_valid = true;
+  }
 
   // -- owner side: message table -> Seg table + items -> sort -> scatter-add ---------------
   std::vector<MsgRef> msgs;
@@ -643,13 +778,8 @@ int commit_exchange(cm_matrix *M) {
     const MsgCounts &c = counts[(size_t)s * P + me];
     if (c.nvals == 0) continue;
     MsgRef m;
-    if (s == me) {
-      m.meta = M->d_send_meta.as<char>() + s_meta_base[me];
-      m.vals = M->d_send_vals.as<char>() + (size_t)s_val_base[me] * esz;
-    } else {
-      m.meta = M->d_recv_meta.as<char>() + r_meta_base[s];
-      m.vals = M->d_recv_vals.as<char>() + (size_t)r_val_base[s] * esz;
-    }
+    m.meta = static_cast<char *>(M->peer_meta[me]) + rbase_m[(size_t)me * (P + 1) + s];
+    m.vals = static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[(size_t)me * (P + 1) + s] * esz;
     m.seg_base = seg_total;
     m.item_base = item_total;
     seg_total += c.nseg;
@@ -901,6 +1031,25 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
       }
     }
   }
+  M->peer_vals.assign(M->P, nullptr);
+  M->peer_meta.assign(M->P, nullptr);
+  M->cap_vals.assign(M->P, 0);
+  M->cap_meta.assign(M->P, 0);
+  M->peer_arena_open.assign(M->P, false);
+  {
+    // peer-to-peer stores need every rank to be able to map every other rank's memory
+    int mine_ok = 1;
+    for (int r = 0; r < M->P; ++r) mine_ok &= M->peer_local[r] != nullptr;
+    std::vector<int> all_ok(M->P, 0);
+    int rc0 = ctx->tp->host_allgather(&mine_ok, all_ok.data(), sizeof(int), M->stream);
+    if (rc0 != CM_OK) return rc0;
+    M->p2p_possible = true;
+    for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
+    const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" override, must agree on all ranks
+    if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
+    if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;
+    M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
+  }
   int rc = ctx->tp->barrier(M->stream);
   if (rc != CM_OK) return rc;
   *out = M;
@@ -911,8 +1060,13 @@ int cm_destroy(cm_matrix *M) {
   if (!M) return CM_OK;
   int rc = do_commit(M);  // :458
   cudaStreamSynchronize(M->stream);
-  for (int r = 0; r < M->P; ++r)
+  for (int r = 0; r < M->P; ++r) {
     if (M->peer_ipc_open[r]) cudaIpcCloseMemHandle(M->peer_local[r]);
+    if (M->peer_arena_open[r]) {
+      cudaIpcCloseMemHandle(M->peer_vals[r]);
+      cudaIpcCloseMemHandle(M->peer_meta[r]);
+    }
+  }
   M->ctx->tp->barrier(M->stream);  // nobody still reads my block
   cudaFree(M->d_local);
   free(M->h_mirror);
@@ -920,9 +1074,9 @@ int cm_destroy(cm_matrix *M) {
   M->index_arena.release();
   DevBuf *bufs[] = {&M->d_fill_ix, &M->d_fill_jx, &M->d_descs, &M->d_item_base, &M->d_rl, &M->d_rpos, &M->d_roff,
                     &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
-                    &M->d_val_base, &M->d_meta_base, &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
+                    &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
                     &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_msgs, &M->d_segs,
-                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp, &M->d_recs, &M->d_col_start, &M->d_pairs, &M->d_tile_tmp};
+                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp, &M->d_recs, &M->d_col_start, &M->d_dst_ptrs};
   for (DevBuf *b : bufs) b->release();
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
@@ -1118,6 +1272,30 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density) {
   if (tile_density > 0) M->tile_density = tile_density;
   return CM_OK;
 }
+int cm_set_exchange_mode(cm_matrix *M, int mode) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (mode < 0 || mode > 2) return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v) or 2 (peer-to-peer)");
+  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the exchange mode only with nothing staged");
+  if (mode == 2 && M->P > 1 && !M->p2p_possible)
+    return fail(CM_ERR_STATE, "peer-to-peer exchange needs every rank's memory mapped (CUDA IPC unavailable)");
+  M->exchange_mode = mode;
+  M->p2p = M->P > 1 && M->p2p_possible && mode != 1;
+  // arenas allocated under the other mode are not mapped by the peers: start over
+  for (int r = 0; r < M->P; ++r) {
+    if (M->peer_arena_open[r]) {
+      cudaIpcCloseMemHandle(M->peer_vals[r]);
+      cudaIpcCloseMemHandle(M->peer_meta[r]);
+      M->peer_arena_open[r] = false;
+    }
+    M->peer_vals[r] = M->peer_meta[r] = nullptr;
+    M->cap_vals[r] = M->cap_meta[r] = 0;
+  }
+  CM_TRY(M->ctx->tp->barrier(M->stream));
+  M->d_recv_vals.release();
+  M->d_recv_meta.release();
+  return CM_OK;
+}
+int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->p2p ? 2 : 1) : -1; }
 int cm_set_profiling(cm_matrix *M, int on) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   M->profiling = on ? 1 : 0;

@@ -143,9 +143,13 @@ class NcclTransport final : public Transport {
     CM_NCCL_TRY(g_nccl.GroupEnd());
     return CM_OK;
   }
-  int barrier(cudaStream_t s) override {
+  int stream_barrier(cudaStream_t s) override {
     CM_TRY(ensure_scratch(256));
     CM_NCCL_TRY(g_nccl.AllReduce(d_scratch, d_scratch, 1, ncclInt32, ncclSum, comm, s));
+    return CM_OK;
+  }
+  int barrier(cudaStream_t s) override {
+    CM_TRY(stream_barrier(s));
     CM_CUDA_TRY(cudaStreamSynchronize(s));
     return CM_OK;
   }
@@ -224,6 +228,7 @@ class LoopbackTransport final : public Transport {
     w->barrier();
     return CM_OK;
   }
+  int stream_barrier(cudaStream_t s) override { return barrier(s); }
   int host_allgather(const void *send, void *recv, size_t bytes, cudaStream_t) override {
     w->board[rank] = send;
     w->barrier();
@@ -249,6 +254,7 @@ class SingleTransport final : public Transport {
     CM_CUDA_TRY(cudaStreamSynchronize(s));
     return CM_OK;
   }
+  int stream_barrier(cudaStream_t) override { return CM_OK; }
   int host_allgather(const void *send, void *recv, size_t bytes, cudaStream_t) override {
     memcpy(recv, send, bytes);
     return CM_OK;

@@ -51,6 +51,9 @@ class Transport {
                         const std::vector<std::vector<XferSpec>> &recvs, cudaStream_t s) = 0;
   // returns when every rank's stream work up to this call is complete
   virtual int barrier(cudaStream_t s) = 0;
+  // stream-ordered barrier: work enqueued on s after this call starts only when every rank's
+  // stream has reached its own stream_barrier (no host synchronisation where the transport allows)
+  virtual int stream_barrier(cudaStream_t s) = 0;
   // small host-side all-gather (IPC handles, pointers)
   virtual int host_allgather(const void *send, void *recv, size_t bytes, cudaStream_t s) = 0;
   // true if all ranks share this process's address space (peer pointers usable directly)

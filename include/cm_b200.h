@@ -180,6 +180,15 @@ int cm_set_sorted_sweep(cm_matrix *M, int on);
  * current value (default 0.25). Deterministic mode always uses column tiles. */
 int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
 
+/* How commit() moves the per-owner messages (COLLECTIVE: same call on every rank, nothing staged):
+ * 0 = auto, 1 = grouped ncclSend/ncclRecv all-to-all-v from a local send arena, 2 = peer-to-peer:
+ * the pack kernel stores each message straight into the owner's receive arena over NVLink (arenas
+ * mapped with CUDA IPC), so packing and exchange are one kernel. Auto picks 2 when every rank can
+ * map every other rank's memory. The environment variable CM_B200_EXCHANGE=nccl|p2p sets the
+ * default. cm_get_exchange_mode returns the mode in effect (1 or 2). */
+int cm_set_exchange_mode(cm_matrix *M, int mode);
+int cm_get_exchange_mode(const cm_matrix *M);
+
 /* PBLAS array descriptor of the local block: {1, ictxt, M, N, MB, NB, 0, 0, LLD}. The
  * reference exposes only the accessors (:550-576); this is the descinit a user writes. */
 int cm_descinit(const cm_matrix *M, int ictxt, int desc[9]);

@@ -53,6 +53,8 @@ def main():
             steps += [("commit",), ("fill_lower",), ("commit",)]
         want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
         M = cm.Matrix(*cfg.args())
+        if os.environ.get("CM_TEST_EXCHANGE_MODE"):
+            M.set_exchange_mode(int(os.environ["CM_TEST_EXCHANGE_MODE"]))
         M.keep_wire(True)
         wires = {}
         for st in steps:
@@ -91,7 +93,7 @@ def main():
             owner, ij = cm.owner_of(i, j, nprow, npcol, 64, 64, lld)
             read_ok &= bool(np.isclose(M.get(i, j), want["local"][owner][ij], rtol=1e-5 if dtype == cm.F32 else 1e-12, atol=1e-6 if dtype == cm.F32 else 1e-12))
         print(f"[rank {rank}] {cfg}: normwise rel err {err:.2e} ok={ok} wire_ok={wire_ok} remote_read_ok={read_ok} "
-              f"stats={ {k: v for k, v in M.stats().items() if k in ('bytes_sent', 'bytes_received', 'kernel_launches')} }", flush=True)
+              f"exchange_mode={M.exchange_mode()} stats={ {k: v for k, v in M.stats().items() if k in ('bytes_sent', 'bytes_received', 'kernel_launches')} }", flush=True)
         failures += (not ok) + (not wire_ok) + (not read_ok)
         M.destroy()
     cm.finalize()

@@ -60,6 +60,22 @@ def test_k0_grid_2x2_slices(dtype):
     assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_exchange_modes(mode):
+    """1 = all-to-all-v through the transport from a send arena, 2 = pack kernel stores straight into
+    the owners' receive arenas (peer-to-peer); same messages, same result"""
+    cfg = Cfg(cm.F64, 2000, 1000, 2, 2, 64, 64, 1024)
+    rng = np.random.default_rng(22)
+    steps = slice_steps(cfg, rng, 4, 500, 300, commit_every=1)  # growing then steady arenas
+    for r in range(cfg.P):
+        steps.append(("elems", r, rand_payload(rng, cfg.dtype, 300), rng.integers(0, cfg.m, 300), rng.integers(0, cfg.n, 300)))
+    steps.append(("commit",))
+    want = run_checker(cfg, steps)
+    got = run_cuda(cfg, steps, exchange_mode=mode)
+    assert_blocks_match(cfg, got, want)
+    assert all(st["bytes_sent"] > 0 for st in got["stats"])
+
+
 @pytest.mark.parametrize("grid", [(2, 3, 4, 8, 64, 100, 190), (3, 2, 8, 4, 96, 250, 150), (2, 4, 64, 64, 1024, 2000, 3000),
                                   (1, 2, 64, 64, 1024, 1000, 2000), (2, 1, 64, 64, 1024, 2000, 1000)])
 def test_nonsquare_grids_wire_bit_exact(grid):
