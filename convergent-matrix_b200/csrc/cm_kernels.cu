@@ -198,42 +198,62 @@ __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs,
                                               ScanArenas sa) {
   const int u = blockIdx.x;
   const UpdDesc d = descs[u];
-  const int nprow = (int)g.nprow, npcol = (int)g.npcol;
+  const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
   __shared__ int roff[kMaxGridDim + 1];
   __shared__ int coff[kMaxGridDim + 1];
+  __shared__ T *base[kMaxGridDim * kMaxGridDim > 1024 ? 1024 : kMaxGridDim * kMaxGridDim];  // per owner: my segment
   const int tid = threadIdx.x;
   if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
   if (tid <= npcol) coff[tid] = ma.coff[(long)u * (npcol + 1) + tid];
+  for (int dst = tid; dst < P && dst < 1024; dst += blockDim.x)
+    base[dst] = static_cast<T *>(sa.dst_vals[dst]) + sa.valoff[(long)dst * nupd + u];
   __syncthreads();
   const T *__restrict__ data = static_cast<const T *>(d.data);
   const int *__restrict__ rpos = ma.rpos + d.rbase;
   const int *__restrict__ cpos = ma.cpos + d.cbase;
+  const long src_rs = d.trans ? d.ld : 1, src_cs = d.trans ? 1 : d.ld;
 
-  for (int kc = blockIdx.y; kc < d.n; kc += gridDim.y) {
-    int q = 0;
-    while (kc >= coff[q + 1]) ++q;
-    const int b = kc - coff[q];
-    const long j = cpos[kc];
-    for (int p = 0; p < nprow; ++p) {
-      const int nr = roff[p + 1] - roff[p];
-      if (nr == 0) continue;
-      const int dst = p * npcol + q;
-      T *__restrict__ out = static_cast<T *>(sa.dst_vals[dst]) + sa.valoff[(long)dst * nupd + u] + (long)b * nr;
-      const int *__restrict__ rp = rpos + roff[p];
-      if (!d.trans) {
-        const T *__restrict__ col = data + d.ld * j;
-        for (int a = tid; a < nr; a += blockDim.x) out[a] = col[rp[a]];
-      } else {
-        const T *__restrict__ col = data + j;
-        for (int a = tid; a < nr; a += blockDim.x) out[a] = col[(long)rp[a] * d.ld];
+  // thread t owns grouped row k = t (+256, ...): its source row, its owner row p, its slot a in
+  // that owner's segment rows. All rows of a column are gathered in one pass by the whole block.
+  for (int k0 = 0; k0 < d.m; k0 += blockDim.x) {
+    const int k = k0 + tid;
+    const bool live = k < d.m;
+    int p = 0;
+    if (live)
+      while (k >= roff[p + 1]) ++p;
+    const int a = live ? k - roff[p] : 0;
+    const int nr = roff[p + 1] - roff[p];
+    const long srow = live ? (long)rpos[k] * src_rs : 0;
+    T *const *brow = base + p * npcol;
+    int kc = blockIdx.y;
+    // four columns in flight per thread
+    for (; kc + 3 * (int)gridDim.y < d.n; kc += 4 * gridDim.y) {
+      T x[4];
+      T *out[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = kc + i * gridDim.y;
+        int q = 0;
+        while (c >= coff[q + 1]) ++q;
+        out[i] = brow[q] + (long)(c - coff[q]) * nr + a;
+        x[i] = live ? data[srow + (long)cpos[c] * src_cs] : T(0);
       }
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *out[i] = x[i];
+      }
+    }
+    for (; kc < d.n; kc += gridDim.y) {
+      int q = 0;
+      while (kc >= coff[q + 1]) ++q;
+      if (live) brow[q][(long)(kc - coff[q]) * nr + a] = data[srow + (long)cpos[kc] * src_cs];
     }
   }
 
   if (blockIdx.y == 0) {
     const int *__restrict__ rl = ma.rl + d.rbase;
     const int *__restrict__ cl = ma.cl + d.cbase;
-    for (int dst = 0; dst < nprow * npcol; ++dst) {
+    for (int dst = 0; dst < P; ++dst) {
       const int p = dst / npcol, q = dst % npcol;
       const int nr = roff[p + 1] - roff[p], nc = coff[q + 1] - coff[q];
       char *mb = sa.dst_meta[dst];

@@ -959,7 +959,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   if (mb <= 0 || nb <= 0 || nprow <= 0 || npcol <= 0 || lld <= 0) return fail(CM_ERR_INVALID, "bad distribution parameters");
   if (nprow * npcol != ctx->nranks)
     return fail(CM_ERR_INVALID, "NPROW*NPCOL = %ld but rank_n() = %d", nprow * npcol, ctx->nranks);
-  if (nprow > kMaxGridDim || npcol > kMaxGridDim) return fail(CM_ERR_INVALID, "grid dims above %d unsupported", kMaxGridDim);
+  if (nprow > kMaxGridDim || npcol > kMaxGridDim || nprow * npcol > 1024)
+    return fail(CM_ERR_INVALID, "grid dims above %d (or more than 1024 ranks) unsupported", kMaxGridDim);
   cm_matrix *M = new cm_matrix();
   M->ctx = ctx;
   M->dtype = dtype;
