@@ -39,6 +39,9 @@ METRIC = "assembled_update_GBps"
 def workload_spec(name, nranks):
     """-> dict(dtype, m, n, nprow, npcol, mb, nb, lld, m_u, n_u, U (per rank), commit_every)."""
     nprow, npcol = GRIDS[nranks]
+    if os.environ.get("CM_BENCH_GRID"):  # experiments only, e.g. CM_BENCH_GRID=2x1
+        nprow, npcol = (int(x) for x in os.environ["CM_BENCH_GRID"].split("x"))
+        assert nprow * npcol == nranks
     if name == "K1":  # BASELINE.json configs[1]; for N > 1 its weak-scaling family (local block fixed)
         return dict(name=f"K1{'' if nranks == 1 else '-weak'}: N={8192 * nprow}x{8192 * npcol} f64 MB=NB=64 grid {nprow}x{npcol}, "
                          f"10000 updates/rank of 256x256, sorted unique random index sets, one commit",

@@ -145,8 +145,8 @@ void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const Map
 // (2) per-owner exclusive scans over the staged updates. grid = P blocks (one per owner).
 // ------------------------------------------------------------------------------------
 struct Long3 {
-  long a, b, c;
-  __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c}; }
+  long a, b, c, e;
+  __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e}; }
 };
 
 __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas ma, ScanArenas sa) {
@@ -155,22 +155,23 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas m
   const int dst = blockIdx.x;
   const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
   const int npr = (int)g.nprow + 1, npc = (int)g.npcol + 1;
-  Long3 running{0, 0, 0};
+  Long3 running{0, 0, 0, 0};
   for (int c0 = 0; c0 < nupd; c0 += 256) {
     const int u = c0 + threadIdx.x;
-    Long3 v{0, 0, 0};
+    Long3 v{0, 0, 0, 0};
     if (u < nupd) {
       const int nr = ma.roff[(long)u * npr + p + 1] - ma.roff[(long)u * npr + p];
       const int nc = ma.coff[(long)u * npc + q + 1] - ma.coff[(long)u * npc + q];
       const long nv = (long)nr * nc;
       if (nv > 0) {
-        v.a = nv;
+        v.a = seg_slots(nr, nc);
         v.b = nr + nc;
         v.c = (long)nc * ((nr + kRowChunk - 1) / kRowChunk);
+        v.e = nv;
       }
     }
     Long3 excl, total;
-    BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0}, cub::Sum(), total);
+    BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0, 0}, cub::Sum(), total);
     if (u < nupd) {
       sa.valoff[(long)dst * nupd + u] = running.a + excl.a;
       sa.idxoff[(long)dst * nupd + u] = running.b + excl.b;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas m
     running = running + total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) sa.totals[dst] = MsgCounts{running.a, running.b, (long)nupd, running.c};
+  if (threadIdx.x == 0) sa.totals[dst] = MsgCounts{running.a, running.b, (long)nupd, running.c, running.e, 0};
 }
 
 void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
@@ -193,37 +194,49 @@ void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas 
 // (p,q) segment — contiguous, coalesced stores; gathers hit every sector of the source
 // column exactly once per block. Block y == 0 also writes the update's wire metadata.
 // ------------------------------------------------------------------------------------
+constexpr int kPackThreads = 384;
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs, int nupd, Geom g, MapArenas ma,
-                                              ScanArenas sa) {
+__global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, Geom g, MapArenas ma,
+                                                       ScanArenas sa) {
   const int u = blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
   __shared__ int roff[kMaxGridDim + 1];
   __shared__ int coff[kMaxGridDim + 1];
-  __shared__ T *base[kMaxGridDim * kMaxGridDim > 1024 ? 1024 : kMaxGridDim * kMaxGridDim];  // per owner: my segment
+  __shared__ int tstart[kMaxGridDim + 1];  // first thread slot of each owner row's rows (16-aligned)
+  __shared__ T *base[1024];                // per owner: where this update's segment starts
   const int tid = threadIdx.x;
   if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
   if (tid <= npcol) coff[tid] = ma.coff[(long)u * (npcol + 1) + tid];
-  for (int dst = tid; dst < P && dst < 1024; dst += blockDim.x)
+  for (int dst = tid; dst < P; dst += blockDim.x)
     base[dst] = static_cast<T *>(sa.dst_vals[dst]) + sa.valoff[(long)dst * nupd + u];
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int p = 0; p < nprow; ++p) {
+      tstart[p] = acc;
+      acc += (roff[p + 1] - roff[p] + kSegAlign - 1) & ~(kSegAlign - 1);
+    }
+    tstart[nprow] = acc;
+  }
   __syncthreads();
   const T *__restrict__ data = static_cast<const T *>(d.data);
   const int *__restrict__ rpos = ma.rpos + d.rbase;
   const int *__restrict__ cpos = ma.cpos + d.cbase;
   const long src_rs = d.trans ? d.ld : 1, src_cs = d.trans ? 1 : d.ld;
 
-  // thread t owns grouped row k = t (+256, ...): its source row, its owner row p, its slot a in
-  // that owner's segment rows. All rows of a column are gathered in one pass by the whole block.
-  for (int k0 = 0; k0 < d.m; k0 += blockDim.x) {
-    const int k = k0 + tid;
-    const bool live = k < d.m;
+  // Thread slot t -> (owner row p, slot a of that owner's segment rows). Slots of one owner row
+  // start on a multiple of 16, and a tall segment's columns are 16-slot aligned in the message, so
+  // every half-warp stores one whole 128-byte line (fp64) — locally or across NVLink.
+  for (int t = tid; t < tstart[nprow]; t += blockDim.x) {
     int p = 0;
-    if (live)
-      while (k >= roff[p + 1]) ++p;
-    const int a = live ? k - roff[p] : 0;
+    while (t >= tstart[p + 1]) ++p;
+    const int a = t - tstart[p];
     const int nr = roff[p + 1] - roff[p];
-    const long srow = live ? (long)rpos[k] * src_rs : 0;
+    const bool live = a < nr;
+    const int stride = seg_col_stride(nr);
+    const long srow = live ? (long)rpos[roff[p] + a] * src_rs : 0;
     T *const *brow = base + p * npcol;
     int kc = blockIdx.y;
     // four columns in flight per thread
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs,
         const int c = kc + i * gridDim.y;
         int q = 0;
         while (c >= coff[q + 1]) ++q;
-        out[i] = brow[q] + (long)(c - coff[q]) * nr + a;
+        out[i] = brow[q] + (long)(c - coff[q]) * stride + a;
         x[i] = live ? data[srow + (long)cpos[c] * src_cs] : T(0);
       }
       if (live) {
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(256) k_pack(const UpdDesc *__restrict__ descs,
     for (; kc < d.n; kc += gridDim.y) {
       int q = 0;
       while (kc >= coff[q + 1]) ++q;
-      if (live) brow[q][(long)(kc - coff[q]) * nr + a] = data[srow + (long)cpos[kc] * src_cs];
+      if (live) brow[q][(long)(kc - coff[q]) * stride + a] = data[srow + (long)cpos[kc] * src_cs];
     }
   }
 
@@ -301,9 +314,9 @@ void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g, con
   if (nupd <= 0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
   switch (dtype) {
-    case 0: k_pack<double><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
-    case 1: k_pack<float><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
-    default: k_pack<int><<<grid, 256, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    case 0: k_pack<double><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    case 1: k_pack<float><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    default: k_pack<int><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
   }
 }
 
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(256) k_build_recv(const MsgRef *__restrict__ m
       s.lrow = lrow;
       s.lcol = lcol;
       s.row_stride = 1;
-      s.col_stride = ws.nr;
+      s.col_stride = seg_col_stride(ws.nr);
       s.nr = ws.nr;
       s.nc = ws.nc;
       s.mask = ws.mask;

@@ -254,6 +254,9 @@ struct cm_matrix {
   std::vector<bool> peer_arena_open;
 
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D payload copies of the host API (overlap with kernels)
+  cudaEvent_t copy_done = nullptr;
+  bool copies_pending = false;
   long flush_threshold = CM_DEFAULT_FLUSH_THRESHOLD;
   int progress_interval = 1;
   int deterministic = 0;
@@ -375,6 +378,11 @@ void clear_staged(cm_matrix *M) {
 
 int upload_staged(cm_matrix *M) {
   const int nupd = (int)M->descs.size();
+  if (M->copies_pending) {  // host-API payloads travel on their own stream
+    CM_CUDA_TRY(cudaEventRecord(M->copy_done, M->copy_stream));
+    CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->copy_done, 0));
+    M->copies_pending = false;
+  }
   CM_TRY(M->index_arena.upload(M->stream, &M->stats.h2d_bytes));
   CM_TRY(M->d_descs.ensure(sizeof(UpdDesc) * (size_t)std::max(nupd, 1)));
   if (nupd)
@@ -643,7 +651,7 @@ int commit_exchange(cm_matrix *M) {
     long *bv = &rbase_v[(size_t)d * (P + 1)], *bm = &rbase_m[(size_t)d * (P + 1)];
     for (int s = 0; s < P; ++s) {
       const MsgCounts &c = counts[(size_t)s * P + d];
-      bv[s + 1] = bv[s] + ((c.nvals + 1) & ~1L);  // keep every message 16-byte aligned
+      bv[s + 1] = bv[s] + ((c.nvals + 31) & ~31L);  // every message starts on a 256-byte boundary
       bm[s + 1] = bm[s] + meta_bytes(c.nseg, c.nidx);
     }
     need_vals[d] = (size_t)bv[P] * esz;
@@ -658,7 +666,7 @@ int commit_exchange(cm_matrix *M) {
   for (int d = 0; d < P; ++d) {
     const MsgCounts &c = counts[(size_t)me * P + d];
     const bool staged = !M->p2p && d != me;
-    s_val_base[d + 1] = s_val_base[d] + (staged ? ((c.nvals + 1) & ~1L) : 0);
+    s_val_base[d + 1] = s_val_base[d] + (staged ? ((c.nvals + 31) & ~31L) : 0);
     s_meta_base[d + 1] = s_meta_base[d] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
   }
   if (!M->p2p) {
@@ -784,7 +792,7 @@ int commit_exchange(cm_matrix *M) {
     m.item_base = item_total;
     seg_total += c.nseg;
     item_total += c.nitems;
-    elem_total += c.nvals;
+    elem_total += c.nelems;
     max_seg = std::max(max_seg, c.nseg);
     msgs.push_back(m);
   }
@@ -884,22 +892,14 @@ int stage_host_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld
   void *d_payload = nullptr;
   CM_TRY(M->payload_arena.alloc((size_t)rows_s * cols_s * esz, &d_payload));
   if (ld == rows_s) {
-    CM_CUDA_TRY(cudaMemcpyAsync(d_payload, data, (size_t)rows_s * cols_s * esz, cudaMemcpyHostToDevice, M->stream));
+    CM_CUDA_TRY(cudaMemcpyAsync(d_payload, data, (size_t)rows_s * cols_s * esz, cudaMemcpyHostToDevice, M->copy_stream));
   } else {
     CM_CUDA_TRY(cudaMemcpy2DAsync(d_payload, (size_t)rows_s * esz, data, (size_t)ld * esz, (size_t)rows_s * esz,
-                                  (size_t)cols_s, cudaMemcpyHostToDevice, M->stream));
+                                  (size_t)cols_s, cudaMemcpyHostToDevice, M->copy_stream));
   }
+  M->copies_pending = true;
   M->stats.h2d_bytes += (long)((size_t)rows_s * cols_s * esz);
-  // reference semantics (:611): the caller may reuse `data` on return. Pageable sources are
-  // consumed before cudaMemcpyAsync returns; pinned / managed sources are DMA'd asynchronously,
-  // so wait for them.
-  cudaPointerAttributes attr;
-  if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) {
-    if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)
-      CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-  } else {
-    cudaGetLastError();
-  }
+  // index sets: host memcpy into the pinned arena while the payload DMA is in flight
   void *h_ix = nullptr, *dv_ix = nullptr, *h_jx = nullptr, *dv_jx = nullptr;
   CM_TRY(M->index_arena.alloc((size_t)m_u * 8, &h_ix, &dv_ix));
   memcpy(h_ix, ix, (size_t)m_u * 8);
@@ -908,6 +908,20 @@ int stage_host_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld
   } else {
     CM_TRY(M->index_arena.alloc((size_t)n_u * 8, &h_jx, &dv_jx));
     memcpy(h_jx, jx, (size_t)n_u * 8);
+  }
+  // reference semantics (:611): the caller may reuse `data` on return. Pageable sources are
+  // consumed before cudaMemcpyAsync returns; pinned / managed sources are DMA'd asynchronously,
+  // so wait for the DMA — polling, because a blocking synchronise costs more than the copy.
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) {
+      cudaError_t q;
+      while ((q = cudaStreamQuery(M->copy_stream)) == cudaErrorNotReady) {
+      }
+      if (q != cudaSuccess) return fail(CM_ERR_CUDA, "payload copy failed: %s", cudaGetErrorString(q));
+    }
+  } else {
+    cudaGetLastError();
   }
   CM_TRY(stage_desc(M, d_payload, m_u, n_u, rows_s, trans, static_cast<const long *>(dv_ix),
                     static_cast<const long *>(dv_jx), mask));
@@ -991,6 +1005,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->coo.resize(M->P);
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->copy_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&M->d_local, M->local_elems * M->esz);
   if (e == cudaSuccess) e = cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream);  // :431-432
   if (e == cudaSuccess) e = cudaStreamSynchronize(M->stream);
@@ -999,6 +1015,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     cudaGetLastError();
     if (M->d_local) cudaFree(M->d_local);
     if (M->stream) cudaStreamDestroy(M->stream);
+    if (M->copy_stream) cudaStreamDestroy(M->copy_stream);
+    if (M->copy_done) cudaEventDestroy(M->copy_done);
     delete M;
     return rc;
   }
@@ -1082,6 +1100,8 @@ int cm_destroy(cm_matrix *M) {
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(M->stream);
+  cudaStreamDestroy(M->copy_stream);
+  cudaEventDestroy(M->copy_done);
   delete M;
   return rc;
 }
@@ -1359,7 +1379,8 @@ static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *da
           }
           if (inds_out) {
             inds_out[n] = g.lld * (long)lcol[b] + lrow[a];
-            memcpy(data_out + (size_t)n * esz, vals + ((size_t)s.val_off + (size_t)a + (size_t)b * s.nr) * esz, esz);
+            memcpy(data_out + (size_t)n * esz,
+                   vals + ((size_t)s.val_off + (size_t)a + (size_t)b * seg_col_stride(s.nr)) * esz, esz);
           }
           ++n;
         }
