@@ -89,7 +89,20 @@ struct WireSeg {
 static_assert(sizeof(WireHdr) == 32, "wire header layout");
 static_assert(sizeof(WireSeg) == 40, "wire segment layout");
 
-// counts exchanged before the data exchange, per (source, owner) pair
+// A commit's staged updates are cut into kMaxChunks consecutive ranges; every (source, chunk,
+// owner) triple is one message. Large commits are pipelined chunk by chunk (the scatter-add of
+// chunk k overlaps the pack/exchange of chunk k+1); small ones go as one batch of messages.
+constexpr int kMaxChunks = 4;
+struct ChunkPlan {
+  int ubeg[kMaxChunks + 1];  // chunk k = updates [ubeg[k], ubeg[k+1])
+};
+__host__ __device__ inline int chunk_of(const ChunkPlan &cp, int u) {
+  int k = 0;
+  while (k + 1 < kMaxChunks && u >= cp.ubeg[k + 1]) ++k;
+  return k;
+}
+
+// counts exchanged before the data exchange, per (source, chunk, owner) triple
 struct MsgCounts {
   long nvals;   // value SLOTS of the message (segments are padded, see seg_col_stride)
   long nidx, nseg, nitems;

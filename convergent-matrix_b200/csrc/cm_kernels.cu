@@ -149,17 +149,20 @@ struct Long3 {
   __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e}; }
 };
 
-__global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas ma, ScanArenas sa) {
+__global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom g, MapArenas ma, ScanArenas sa) {
   using BlockScan = cub::BlockScan<Long3, 256>;
   __shared__ typename BlockScan::TempStorage tmp;
   const int dst = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int ub = cp.ubeg[chunk], ue = cp.ubeg[chunk + 1];
+  const int P = gridDim.x;
   const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
   const int npr = (int)g.nprow + 1, npc = (int)g.npcol + 1;
   Long3 running{0, 0, 0, 0};
-  for (int c0 = 0; c0 < nupd; c0 += 256) {
+  for (int c0 = ub; c0 < ue; c0 += 256) {
     const int u = c0 + threadIdx.x;
     Long3 v{0, 0, 0, 0};
-    if (u < nupd) {
+    if (u < ue) {
       const int nr = ma.roff[(long)u * npr + p + 1] - ma.roff[(long)u * npr + p];
       const int nc = ma.coff[(long)u * npc + q + 1] - ma.coff[(long)u * npc + q];
       const long nv = (long)nr * nc;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas m
     }
     Long3 excl, total;
     BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0, 0}, cub::Sum(), total);
-    if (u < nupd) {
+    if (u < ue) {
       sa.valoff[(long)dst * nupd + u] = running.a + excl.a;
       sa.idxoff[(long)dst * nupd + u] = running.b + excl.b;
       sa.itemoff[(long)dst * nupd + u] = running.c + excl.c;
@@ -180,12 +183,14 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, Geom g, MapArenas m
     running = running + total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) sa.totals[dst] = MsgCounts{running.a, running.b, (long)nupd, running.c, running.e, 0};
+  if (threadIdx.x == 0)
+    sa.totals[chunk * P + dst] = MsgCounts{running.a, running.b, (long)(ue - ub), running.c, running.e, 0};
 }
 
-void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
+void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
+                 cudaStream_t s) {
   const int P = (int)(g.nprow * g.npcol);
-  k_scan_dest<<<P, 256, 0, s>>>(nupd, g, ma, sa);
+  k_scan_dest<<<dim3(P, kMaxChunks), 256, 0, s>>>(nupd, cp, g, ma, sa);
 }
 
 // ------------------------------------------------------------------------------------
@@ -197,11 +202,13 @@ void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas 
 constexpr int kPackThreads = 384;
 
 template <typename T>
-__global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, Geom g, MapArenas ma,
-                                                       ScanArenas sa) {
-  const int u = blockIdx.x;
+__global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int u0, ChunkPlan cp,
+                                                       Geom g, MapArenas ma, ScanArenas sa) {
+  const int u = u0 + blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
+  const int chunk = chunk_of(cp, u);
+  const int ufirst = cp.ubeg[chunk], nseg = cp.ubeg[chunk + 1] - ufirst;  // my message's segment table
   __shared__ int roff[kMaxGridDim + 1];
   __shared__ int coff[kMaxGridDim + 1];
   __shared__ int tstart[kMaxGridDim + 1];  // first thread slot of each owner row's rows (16-aligned)
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
   if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
   if (tid <= npcol) coff[tid] = ma.coff[(long)u * (npcol + 1) + tid];
   for (int dst = tid; dst < P; dst += blockDim.x)
-    base[dst] = static_cast<T *>(sa.dst_vals[dst]) + sa.valoff[(long)dst * nupd + u];
+    base[dst] = static_cast<T *>(sa.dst_vals[chunk * P + dst]) + sa.valoff[(long)dst * nupd + u];
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
@@ -269,16 +276,16 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
     for (int dst = 0; dst < P; ++dst) {
       const int p = dst / npcol, q = dst % npcol;
       const int nr = roff[p + 1] - roff[p], nc = coff[q + 1] - coff[q];
-      char *mb = sa.dst_meta[dst];
-      if (u == 0 && tid == 0) {  // message header
-        const MsgCounts c = sa.totals[dst];
+      char *mb = sa.dst_meta[chunk * P + dst];
+      if (u == ufirst && tid == 0) {  // message header
+        const MsgCounts c = sa.totals[chunk * P + dst];
         WireHdr *h = reinterpret_cast<WireHdr *>(mb);
         h->nseg = c.nseg;
         h->nvals = c.nvals;
         h->nidx = c.nidx;
         h->nitems = c.nitems;
       }
-      WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
+      WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + (u - ufirst);
       const bool empty = (long)nr * nc == 0;
       const long ioff = sa.idxoff[(long)dst * nupd + u];
       if (tid == 0) {
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
         ws->item_off = sa.itemoff[(long)dst * nupd + u];
       }
       if (!empty) {
-        int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nupd * sizeof(WireSeg)) + ioff;
+        int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nseg * sizeof(WireSeg)) + ioff;
         for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
         for (int c = tid; c < nc; c += blockDim.x) iw[nr + c] = cl[coff[q] + c];
       }
@@ -309,14 +316,14 @@ static int pick_ytiles(int nupd, long max_cols) {
   return (int)y;
 }
 
-void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
-                 const ScanArenas &sa, cudaStream_t s) {
-  if (nupd <= 0) return;
-  const dim3 grid(nupd, pick_ytiles(nupd, 4096));
+void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int u0, int u1, const ChunkPlan &cp, const Geom &g,
+                 const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
+  if (u1 <= u0) return;
+  const dim3 grid(u1 - u0, pick_ytiles(u1 - u0, 4096));
   switch (dtype) {
-    case 0: k_pack<double><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
-    case 1: k_pack<float><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
-    default: k_pack<int><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, g, ma, sa); break;
+    case 0: k_pack<double><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
+    case 1: k_pack<float><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
+    default: k_pack<int><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
   }
 }
 
@@ -747,7 +754,7 @@ __global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict
 
 template <typename T>
 static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                                const Geom &g, cudaStream_t s) {
+                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
   static bool attr_set = false;
   static int resident1 = 0, residentM = 0;
@@ -760,21 +767,24 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   }
   const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
   const long nunits = n_local * ntiles;
+  // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
+  // the next chunk in a pipelined commit)
+  const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
   if (ntiles == 1)
-    k_apply_tile<T, false><<<(unsigned)std::min(nunits, (long)resident1), 256, smem, s>>>(d_recs, d_col_start, n_local, ntiles,
-                                                                                     m_local, d_local, g);
+    k_apply_tile<T, false><<<(unsigned)std::min({nunits, (long)resident1, cap}), 256, smem, s>>>(
+        d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
   else
-    k_apply_tile<T, true><<<(unsigned)std::min(nunits, (long)residentM), 256, smem, s>>>(d_recs, d_col_start, n_local, ntiles,
-                                                                                    m_local, d_local, g);
+    k_apply_tile<T, true><<<(unsigned)std::min({nunits, (long)residentM, cap}), 256, smem, s>>>(
+        d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
-                       long n_local, long m_local, const Geom &g, cudaStream_t s) {
+                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   if (nitems <= 0) return;
   switch (dtype) {
-    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, s); break;
-    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, s); break;
-    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, s); break;
+    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, s); break;
+    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, s); break;
+    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, s); break;
   }
 }
 

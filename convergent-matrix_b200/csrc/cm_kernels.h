@@ -33,9 +33,9 @@ struct ScanArenas {
   long *valoff;    // [P * nupd]
   long *idxoff;    // [P * nupd]
   long *itemoff;   // [P * nupd]
-  MsgCounts *totals;  // [P]
-  void **dst_vals;    // [P] where this rank's message to owner d starts: values ...
-  char **dst_meta;    // [P] ... and metadata. May point into a PEER's receive arena (NVLink stores).
+  MsgCounts *totals;  // [kMaxChunks * P], index chunk * P + owner
+  void **dst_vals;    // [kMaxChunks * P] where this rank's message (chunk, owner) starts: values ...
+  char **dst_meta;    // ... and metadata. May point into a PEER's receive arena (NVLink stores).
 };
 
 size_t dtype_size(int dtype);
@@ -44,11 +44,13 @@ size_t dtype_size(int dtype);
 void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
                       cudaStream_t s);
 // (2) per-owner scans over the staged updates (sizes of every message)
-void launch_scan(int nupd, const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
+void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
+                 cudaStream_t s);
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
-void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, const Geom &g,
-                 const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
+// Packs updates [u0, u1) (whole chunks).
+void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int u0, int u1, const ChunkPlan &cp,
+                 const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,
                          const Geom &g, const MapArenas &ma, Seg *d_segs, uint32_t *d_keys,
@@ -70,7 +72,8 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_loc
                       cudaStream_t s);
 // (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
-                       void *d_local, long n_local, long m_local, const Geom &g, cudaStream_t s);
+                       void *d_local, long n_local, long m_local, const Geom &g, int max_blocks_per_sm,
+                       cudaStream_t s);
 // COO path for elemental updates: local[inds[k]] += vals[k]
 void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local,
                       cudaStream_t s);

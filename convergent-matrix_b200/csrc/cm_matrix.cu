@@ -219,6 +219,15 @@ struct CooBin {
   std::vector<unsigned char> vals;
 };
 
+// device buffers of one scatter-add batch (one per pipelined chunk)
+struct ApplyWork {
+  DevBuf msgs, segs, keys0, keys1, items0, items1, sort_tmp, recs, col_start;
+  void release() {
+    DevBuf *b[] = {&msgs, &segs, &keys0, &keys1, &items0, &items1, &sort_tmp, &recs, &col_start};
+    for (DevBuf *x : b) x->release();
+  }
+};
+
 struct PendingTimer {
   int kind;  // 0 apply, 1 pack, 2 exchange
   cudaEvent_t a, b;
@@ -283,7 +292,15 @@ struct cm_matrix {
   DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_coo_tmp;
   DevBuf d_valoff, d_idxoff, d_itemoff, d_totals;
   DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
-  DevBuf d_counts_all, d_msgs, d_segs, d_keys0, d_keys1, d_items0, d_items1, d_sort_tmp, d_recs, d_col_start, d_dst_ptrs;
+  DevBuf d_counts_all, d_dst_ptrs;
+  ApplyWork work[kMaxChunks];
+  cudaStream_t apply_stream = nullptr;  // scatter-add of chunk k while chunk k+1 is packed / exchanged
+  cudaEvent_t ev_chunk[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_applied = nullptr;
+  int pipeline = 0;                     // chunk-pipelined commits: opt-in (CM_B200_PIPELINE=1). Measured on 2 B200s
+                                        // (K1-weak) it is slower than one batch (7.8 vs 6.6 ms per step): the
+                                        // scatter-add and the next chunk's pack do not co-schedule well yet
+  long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
   PinBuf h_counts;
 
   cm_stats stats{};
@@ -291,9 +308,11 @@ struct cm_matrix {
   std::vector<cudaEvent_t> event_pool;
 
   // wire capture (parity tests)
-  std::vector<char> dbg_meta;
-  std::vector<char> dbg_vals;
-  std::vector<long> dbg_meta_base, dbg_val_base;
+  struct DbgMsg {
+    int dst;
+    std::vector<char> meta, vals;
+  };
+  std::vector<DbgMsg> dbg_msgs;  // the messages of the last commit, owner-major, chunk order
   std::vector<CooBin> dbg_coo;
   bool dbg_valid = false;
 };
@@ -318,16 +337,18 @@ struct ScopedTimer {
   int kind;
   long elements;
   cudaEvent_t a = nullptr, b = nullptr;
-  ScopedTimer(cm_matrix *m, int k, long el) : M(m), kind(k), elements(el) {
+  cudaStream_t st;
+  ScopedTimer(cm_matrix *m, int k, long el, cudaStream_t stream = nullptr)
+      : M(m), kind(k), elements(el), st(stream ? stream : m->stream) {
     if (M->profiling) {
       a = get_event(M);
       b = get_event(M);
-      cudaEventRecord(a, M->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~ScopedTimer() {
     if (M->profiling) {
-      cudaEventRecord(b, M->stream);
+      cudaEventRecord(b, st);
       M->timers.push_back(PendingTimer{kind, a, b, elements});
     }
   }
@@ -412,11 +433,11 @@ MapArenas map_arenas(cm_matrix *M) {
   return ma;
 }
 
-// sort (optional) + scatter-add over nitems (key,item) pairs sitting in keys0/items0
-int sort_and_apply(cm_matrix *M, long nseg, long nitems, long elements) {
+// sort (optional) + scatter-add over nitems (key,item) pairs sitting in w.keys0 / w.items0
+int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0) {
   if (nitems <= 0) return CM_OK;
-  const uint64_t *items = M->d_items0.as<uint64_t>();
-  const uint32_t *keys = M->d_keys0.as<uint32_t>();
+  const uint64_t *items = w.items0.as<uint64_t>();
+  const uint32_t *keys = w.keys0.as<uint32_t>();
   // which scatter-add: the column-tile kernel pays 2*s bytes per touched sector of a touched
   // column and no atomics; RED pays one sector round trip per element. Dense flushes -> tile.
   const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
@@ -426,27 +447,27 @@ int sort_and_apply(cm_matrix *M, long nseg, long nitems, long elements) {
   if (sorted) {
     const int end_bit = std::max(1, ceil_log2(std::max(M->n_local, 2L)));
     const size_t tmp = sort_temp_bytes(nitems, end_bit);
-    CM_TRY(M->d_sort_tmp.ensure(tmp));
-    CM_TRY(M->d_keys1.ensure(4 * (size_t)nitems));
-    CM_TRY(M->d_items1.ensure(8 * (size_t)nitems));
-    launch_sort(M->d_sort_tmp.p, tmp, M->d_keys0.as<uint32_t>(), M->d_keys1.as<uint32_t>(), M->d_items0.as<uint64_t>(),
-                M->d_items1.as<uint64_t>(), nitems, end_bit, M->stream);
+    CM_TRY(w.sort_tmp.ensure(tmp));
+    CM_TRY(w.keys1.ensure(4 * (size_t)nitems));
+    CM_TRY(w.items1.ensure(8 * (size_t)nitems));
+    launch_sort(w.sort_tmp.p, tmp, w.keys0.as<uint32_t>(), w.keys1.as<uint32_t>(), w.items0.as<uint64_t>(),
+                w.items1.as<uint64_t>(), nitems, end_bit, st);
     M->stats.kernel_launches += 3;  // CUB radix sort passes (library metadata sort, not the hot op)
-    items = M->d_items1.as<uint64_t>();
-    keys = M->d_keys1.as<uint32_t>();
+    items = w.items1.as<uint64_t>();
+    keys = w.keys1.as<uint32_t>();
   }
-  CM_TRY(M->d_recs.ensure(sizeof(ItemRec) * (size_t)nitems));
-  if (tile) CM_TRY(M->d_col_start.ensure(8 * (size_t)(M->n_local + 1)));
-  launch_build_recs(M->dtype, M->d_segs.as<Seg>(), keys, items, nitems, M->d_recs.as<ItemRec>(), M->n_local,
-                    tile ? M->d_col_start.as<long>() : nullptr, M->stream);
+  CM_TRY(w.recs.ensure(sizeof(ItemRec) * (size_t)nitems));
+  if (tile) CM_TRY(w.col_start.ensure(8 * (size_t)(M->n_local + 1)));
+  launch_build_recs(M->dtype, w.segs.as<Seg>(), keys, items, nitems, w.recs.as<ItemRec>(), M->n_local,
+                    tile ? w.col_start.as<long>() : nullptr, st);
   M->stats.kernel_launches += tile ? 2 : 1;
   {
-    ScopedTimer t(M, 0, elements);
+    ScopedTimer t(M, 0, elements, st);
     if (tile)
-      launch_apply_tile(M->dtype, M->d_recs.as<ItemRec>(), M->d_col_start.as<long>(), nitems, M->d_local, M->n_local,
-                        M->m_local, M->g, M->stream);
+      launch_apply_tile(M->dtype, w.recs.as<ItemRec>(), w.col_start.as<long>(), nitems, M->d_local, M->n_local,
+                        M->m_local, M->g, max_blocks_per_sm, st);
     else
-      launch_apply_red(M->dtype, M->d_recs.as<ItemRec>(), nitems, M->d_local, M->g, M->stream);
+      launch_apply_red(M->dtype, w.recs.as<ItemRec>(), nitems, M->d_local, M->g, st);
     M->stats.kernel_launches += 1;
     if (tile) M->stats.tile_launches += 1;
   }
@@ -491,18 +512,19 @@ int flush_direct(cm_matrix *M) {
     const long nitems = M->staged_items;
     CM_TRY(M->d_item_base.ensure(8 * (size_t)nupd));
     CM_CUDA_TRY(cudaMemcpyAsync(M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, cudaMemcpyHostToDevice, M->stream));
-    CM_TRY(M->d_segs.ensure(sizeof(Seg) * (size_t)nupd));
-    CM_TRY(M->d_keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
-    CM_TRY(M->d_items0.ensure(8 * (size_t)std::max(nitems, 1L)));
+    ApplyWork &w = M->work[0];
+    CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)nupd));
+    CM_TRY(w.keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
+    CM_TRY(w.items0.ensure(8 * (size_t)std::max(nitems, 1L)));
     const MapArenas ma = map_arenas(M);
     {
       ScopedTimer t(M, 1, 0);
       launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
       launch_build_direct(M->dtype, M->d_descs.as<UpdDesc>(), M->d_item_base.as<long>(), nupd, M->g, ma,
-                          M->d_segs.as<Seg>(), M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
+                          w.segs.as<Seg>(), w.keys0.as<uint32_t>(), w.items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
     }
-    CM_TRY(sort_and_apply(M, nupd, nitems, M->staged_elems));
+    CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems));
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
@@ -594,19 +616,33 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
 // that is the owner's receive arena itself (pack and exchange are ONE kernel whose stores cross
 // NVLink); otherwise a local send arena that a grouped ncclSend/ncclRecv all-to-all-v moves.
 int commit_exchange(cm_matrix *M) {
-  const int P = M->P, me = M->me;
+  const int P = M->P, me = M->me, K = kMaxChunks;
   const int nupd = (int)M->descs.size();
   Transport *tp = M->ctx->tp;
   const size_t esz = M->esz;
+  auto cidx = [P, K](int src, int k, int dst) { return ((size_t)src * K + k) * P + dst; };  // counts index
 
-  // -- source side: owner map + per-owner sizes -------------------------------------------
+  // -- chunk plan: consecutive update ranges holding about the same number of elements -------
+  ChunkPlan cp;
+  {
+    cp.ubeg[0] = 0;
+    long acc = 0;
+    int k = 1;
+    for (int u = 0; u < nupd && k < K; ++u) {
+      acc += (long)M->descs[u].m * M->descs[u].n;
+      if (acc * K >= M->staged_elems * k) cp.ubeg[k++] = u + 1;
+    }
+    for (; k <= K; ++k) cp.ubeg[k] = nupd;
+  }
+
+  // -- source side: owner map + per-(chunk, owner) sizes ---------------------------------------
   CM_TRY(upload_staged(M));
   const size_t pu = (size_t)P * std::max(nupd, 1);
   CM_TRY(M->d_valoff.ensure(8 * pu));
   CM_TRY(M->d_idxoff.ensure(8 * pu));
   CM_TRY(M->d_itemoff.ensure(8 * pu));
-  CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P));
-  CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P));
+  CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P * K));
+  CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P * K));
   const MapArenas ma = map_arenas(M);
   ScanArenas sa;
   sa.valoff = M->d_valoff.as<long>();
@@ -614,7 +650,7 @@ int commit_exchange(cm_matrix *M) {
   sa.itemoff = M->d_itemoff.as<long>();
   sa.totals = M->d_totals.as<MsgCounts>();
   sa.dst_vals = M->d_dst_ptrs.as<void *>();
-  sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + P);
+  sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
   cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
   if (M->profiling) {
     ev_pack0 = get_event(M);
@@ -622,20 +658,20 @@ int commit_exchange(cm_matrix *M) {
     cudaEventRecord(ev_pack0, M->stream);
   }
   launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
-  launch_scan(nupd, M->g, ma, sa, M->stream);
+  launch_scan(nupd, cp, M->g, ma, sa, M->stream);
   M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
   CM_CUDA_TRY(cudaGetLastError());
 
-  // -- counts: all-gather the per-owner totals, read them back (the one host sync) --------
-  CM_TRY(M->d_counts_all.ensure(sizeof(MsgCounts) * (size_t)P * P));
-  CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, sizeof(MsgCounts) * (size_t)P, M->stream));
-  CM_TRY(M->h_counts.ensure(sizeof(MsgCounts) * (size_t)P * P + 8 * (size_t)P * P));
-  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src * P + dst]
-  CM_CUDA_TRY(cudaMemcpyAsync(counts, M->d_counts_all.p, sizeof(MsgCounts) * (size_t)P * P, cudaMemcpyDeviceToHost,
-                              M->stream));
-  M->stats.d2h_bytes += (long)(sizeof(MsgCounts) * (size_t)P * P);
+  // -- counts: all-gather the totals, read them back (the one host sync of a commit) -----------
+  const size_t per_rank = sizeof(MsgCounts) * (size_t)P * K;
+  CM_TRY(M->d_counts_all.ensure(per_rank * P));
+  CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, per_rank, M->stream));
+  CM_TRY(M->h_counts.ensure(per_rank * P + 8 * (size_t)P * P));
+  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][chunk][dst]
+  CM_CUDA_TRY(cudaMemcpyAsync(counts, M->d_counts_all.p, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
+  M->stats.d2h_bytes += (long)(per_rank * P);
   // COO counts travel on the host side of the same exchange
-  long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + sizeof(MsgCounts) * (size_t)P * P);
+  long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + per_rank * P);
   {
     std::vector<long> mine(P);
     for (int d = 0; d < P; ++d) mine[d] = (long)M->coo[d].inds.size();
@@ -643,62 +679,72 @@ int commit_exchange(cm_matrix *M) {
   }
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
 
-  // -- layout of every rank's receive arenas (identical computation on every rank) ----------
-  // rbase_v[d*(P+1) + s]: element offset of source s's values inside owner d's arena
-  std::vector<long> rbase_v((size_t)P * (P + 1), 0), rbase_m((size_t)P * (P + 1), 0);
+  // -- pipeline or not: same decision on every rank, taken from the global counts. Every chunk's
+  // scatter-add sweeps the whole local block once, so pipelining pays only when a chunk brings
+  // at least about two updates per matrix element; smaller commits go as one batch.
+  bool pipelined = false;
+  if (P > 1 && M->p2p && M->pipeline) {
+    long total = 0;
+    for (int src = 0; src < P; ++src)
+      for (int k = 0; k < K; ++k)
+        for (int d = 0; d < P; ++d) total += counts[cidx(src, k, d)].nelems;
+    pipelined = total >= 2L * K * M->g.m * M->g.n && total / P >= M->pipeline_min_elems;
+  }
+
+  // -- layout of every rank's receive arenas (identical computation on every rank):
+  // owner d holds, chunk after chunk, the messages of every source
+  std::vector<long> rbase_v((size_t)P * (K * P + 1), 0), rbase_m((size_t)P * (K * P + 1), 0);
+  auto ridx = [P, K](int d, int k, int src) { return (size_t)d * (K * P + 1) + (size_t)k * P + src; };
   std::vector<size_t> need_vals(P), need_meta(P);
   for (int d = 0; d < P; ++d) {
-    long *bv = &rbase_v[(size_t)d * (P + 1)], *bm = &rbase_m[(size_t)d * (P + 1)];
-    for (int s = 0; s < P; ++s) {
-      const MsgCounts &c = counts[(size_t)s * P + d];
-      bv[s + 1] = bv[s] + ((c.nvals + 31) & ~31L);  // every message starts on a 256-byte boundary
-      bm[s + 1] = bm[s] + meta_bytes(c.nseg, c.nidx);
-    }
-    need_vals[d] = (size_t)bv[P] * esz;
-    need_meta[d] = (size_t)bm[P];
+    for (int k = 0; k < K; ++k)
+      for (int src = 0; src < P; ++src) {
+        const MsgCounts &c = counts[cidx(src, k, d)];
+        const size_t i = ridx(d, k, src);
+        rbase_v[i + 1] = rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
+        rbase_m[i + 1] = rbase_m[i] + meta_bytes(c.nseg, c.nidx);
+      }
+    need_vals[d] = (size_t)rbase_v[ridx(d, K - 1, P - 1) + 1] * esz;
+    need_meta[d] = (size_t)rbase_m[ridx(d, K - 1, P - 1) + 1];
   }
   CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
 
-  // -- where my messages go ------------------------------------------------------------------
-  // p2p: straight into the owners' arenas. Otherwise: my own message into my arena, the others
-  // into a local send arena laid out owner after owner.
-  std::vector<long> s_val_base(P + 1, 0), s_meta_base(P + 1, 0);
-  for (int d = 0; d < P; ++d) {
-    const MsgCounts &c = counts[(size_t)me * P + d];
-    const bool staged = !M->p2p && d != me;
-    s_val_base[d + 1] = s_val_base[d] + (staged ? ((c.nvals + 31) & ~31L) : 0);
-    s_meta_base[d + 1] = s_meta_base[d] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
-  }
-  if (!M->p2p) {
-    CM_TRY(M->d_send_vals.ensure(std::max((size_t)s_val_base[P] * esz, (size_t)256)));
-    CM_TRY(M->d_send_meta.ensure(std::max((size_t)s_meta_base[P], (size_t)256)));
-  }
-  std::vector<void *> dst_ptrs(2 * (size_t)P);
-  for (int d = 0; d < P; ++d) {
-    if (M->p2p || d == me) {
-      dst_ptrs[d] = static_cast<char *>(M->peer_vals[d]) + (size_t)rbase_v[(size_t)d * (P + 1) + me] * esz;
-      dst_ptrs[P + d] = static_cast<char *>(M->peer_meta[d]) + rbase_m[(size_t)d * (P + 1) + me];
-    } else {
-      dst_ptrs[d] = M->d_send_vals.as<char>() + (size_t)s_val_base[d] * esz;
-      dst_ptrs[P + d] = M->d_send_meta.as<char>() + s_meta_base[d];
+  // -- where my messages go: p2p = straight into the owners' arenas; otherwise my own messages
+  // into my arena and the others into a local send arena --------------------------------------
+  std::vector<long> s_val_base((size_t)K * P + 1, 0), s_meta_base((size_t)K * P + 1, 0);
+  for (int k = 0; k < K; ++k)
+    for (int d = 0; d < P; ++d) {
+      const MsgCounts &c = counts[cidx(me, k, d)];
+      const bool staged = !M->p2p && d != me;
+      const size_t i = (size_t)k * P + d;
+      s_val_base[i + 1] = s_val_base[i] + (staged ? ((c.nvals + 31) & ~31L) : 0);
+      s_meta_base[i + 1] = s_meta_base[i] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
     }
+  if (!M->p2p) {
+    CM_TRY(M->d_send_vals.ensure(std::max((size_t)s_val_base[(size_t)K * P] * esz, (size_t)256)));
+    CM_TRY(M->d_send_meta.ensure(std::max((size_t)s_meta_base[(size_t)K * P], (size_t)256)));
   }
+  std::vector<void *> dst_ptrs(2 * (size_t)K * P);
+  for (int k = 0; k < K; ++k)
+    for (int d = 0; d < P; ++d) {
+      const size_t i = (size_t)k * P + d;
+      if (M->p2p || d == me) {
+        dst_ptrs[i] = static_cast<char *>(M->peer_vals[d]) + (size_t)rbase_v[ridx(d, k, me)] * esz;
+        dst_ptrs[(size_t)K * P + i] = static_cast<char *>(M->peer_meta[d]) + rbase_m[ridx(d, k, me)];
+      } else {
+        dst_ptrs[i] = M->d_send_vals.as<char>() + (size_t)s_val_base[i] * esz;
+        dst_ptrs[(size_t)K * P + i] = M->d_send_meta.as<char>() + s_meta_base[i];
+      }
+    }
   CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
                               M->stream));
-  launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, M->g, ma, sa, M->stream);
-  M->stats.kernel_launches += nupd ? 1 : 0;
-  if (M->profiling) {
-    cudaEventRecord(ev_pack1, M->stream);
-    M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
-  }
-  CM_CUDA_TRY(cudaGetLastError());
 
   // -- COO blobs (elemental updates): [inds x n][vals x n] per owner, always via the transport --
   auto coo_blob = [esz](long n) { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); };
   std::vector<long> r_coo_base(P + 1, 0), s_coo_base(P + 1, 0);
-  for (int s = 0; s < P; ++s) {
-    r_coo_base[s + 1] = r_coo_base[s] + (s != me ? coo_blob(coo_counts[(size_t)s * P + me]) : 0);
-    s_coo_base[s + 1] = s_coo_base[s] + coo_blob((long)M->coo[s].inds.size());
+  for (int r = 0; r < P; ++r) {
+    r_coo_base[r + 1] = r_coo_base[r] + (r != me ? coo_blob(coo_counts[(size_t)r * P + me]) : 0);
+    s_coo_base[r + 1] = s_coo_base[r] + coo_blob((long)M->coo[r].inds.size());
   }
   CM_TRY(M->d_recv_coo.ensure(std::max((size_t)r_coo_base[P], (size_t)256)));
   CM_TRY(M->d_send_coo.ensure(std::max((size_t)s_coo_base[P], (size_t)256)));
@@ -712,108 +758,156 @@ int commit_exchange(cm_matrix *M) {
     M->stats.h2d_bytes += n * (long)(8 + esz);
   }
 
-  // -- exchange --------------------------------------------------------------------------------
-  std::vector<std::vector<XferSpec>> sends(3, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
-  std::vector<std::vector<XferSpec>> recvs(3, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
-  long sent = 0, received = 0;
-  bool any_lane = false;
+  // -- owner side of a group of chunks [k0, k1): messages -> Seg table + items -> sort -> scatter-add
+  auto apply_chunks = [&](int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) -> int {
+    std::vector<MsgRef> msgs;
+    long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+    for (int k = k0; k < k1; ++k)
+      for (int src = 0; src < P; ++src) {
+        const MsgCounts &c = counts[cidx(src, k, me)];
+        if (c.nvals == 0) continue;
+        MsgRef m;
+        m.meta = static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, src)];
+        m.vals = static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, src)] * esz;
+        m.seg_base = seg_total;
+        m.item_base = item_total;
+        seg_total += c.nseg;
+        item_total += c.nitems;
+        elem_total += c.nelems;
+        max_seg = std::max(max_seg, c.nseg);
+        msgs.push_back(m);
+      }
+    if (seg_total >= (1L << kItemSegBits))
+      return fail(CM_ERR_INVALID, "too many segments in one commit (%ld); commit more often", seg_total);
+    if (msgs.empty()) return CM_OK;
+    CM_TRY(w.msgs.ensure(sizeof(MsgRef) * msgs.size()));
+    CM_CUDA_TRY(cudaMemcpyAsync(w.msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, st));
+    CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)seg_total));
+    CM_TRY(w.keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
+    CM_TRY(w.items0.ensure(8 * (size_t)std::max(item_total, 1L)));
+    launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
+                      w.items0.as<uint64_t>(), st);
+    M->stats.kernel_launches += 1;
+    CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
+    M->stats.elements_applied += elem_total;
+    return CM_OK;
+  };
+
+  // -- exchange lanes of the transport (values + metadata only without p2p; COO always) ---------
+  auto transport_lanes = [&](int k0, int k1, bool with_coo) -> int {
+    const int nl = 2 * (k1 - k0) + 1;
+    std::vector<std::vector<XferSpec>> sends(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
+    std::vector<std::vector<XferSpec>> recvs(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
+    bool global_lane = false;  // every rank must take the same branch: decide from the global counts
+    for (int r = 0; r < P; ++r) {
+      if (r == me) continue;
+      if (!M->p2p)
+        for (int k = k0; k < k1; ++k) {
+          const MsgCounts &cs = counts[cidx(me, k, r)];
+          const MsgCounts &cr = counts[cidx(r, k, me)];
+          const size_t i = (size_t)k * P + r;
+          const int l = 2 * (k - k0);
+          sends[l][r] = XferSpec{dst_ptrs[i], (size_t)cs.nvals * esz};
+          sends[l + 1][r] = XferSpec{dst_ptrs[(size_t)K * P + i], cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
+          recvs[l][r] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, r)] * esz,
+                                 (size_t)cr.nvals * esz};
+          recvs[l + 1][r] = XferSpec{static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, r)],
+                                     cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
+        }
+      if (with_coo) {
+        if (M->coo[r].inds.size())
+          sends[nl - 1][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r], (size_t)coo_blob((long)M->coo[r].inds.size())};
+        if (coo_counts[(size_t)r * P + me])
+          recvs[nl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r], (size_t)coo_blob(coo_counts[(size_t)r * P + me])};
+      }
+    }
+    for (int src = 0; src < P && !global_lane; ++src)
+      for (int d = 0; d < P && !global_lane; ++d) {
+        if (src == d) continue;
+        if (with_coo && coo_counts[(size_t)src * P + d]) global_lane = true;
+        if (!M->p2p)
+          for (int k = k0; k < k1; ++k)
+            if (counts[cidx(src, k, d)].nvals) global_lane = true;
+      }
+    if (global_lane) {
+      ScopedTimer t(M, 2, 0);
+      CM_TRY(tp->alltoallv(sends, recvs, M->stream));
+    }
+    return CM_OK;
+  };
+
   for (int r = 0; r < P; ++r) {
     if (r == me) continue;
-    const MsgCounts &cs = counts[(size_t)me * P + r];
-    const MsgCounts &cr = counts[(size_t)r * P + me];
-    if (!M->p2p) {
-      sends[0][r] = XferSpec{dst_ptrs[r], (size_t)cs.nvals * esz};
-      sends[1][r] = XferSpec{dst_ptrs[P + r], cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
-      recvs[0][r] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[(size_t)me * (P + 1) + r] * esz,
-                             (size_t)cr.nvals * esz};
-      recvs[1][r] = XferSpec{static_cast<char *>(M->peer_meta[me]) + rbase_m[(size_t)me * (P + 1) + r],
-                             cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
+    for (int k = 0; k < K; ++k) {
+      const MsgCounts &cs = counts[cidx(me, k, r)], &cr = counts[cidx(r, k, me)];
+      M->stats.bytes_sent += (long)(cs.nvals * esz + (cs.nvals ? meta_bytes(cs.nseg, cs.nidx) : 0));
+      M->stats.bytes_received += (long)(cr.nvals * esz + (cr.nvals ? meta_bytes(cr.nseg, cr.nidx) : 0));
     }
-    sends[2][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r], (size_t)coo_blob((long)M->coo[r].inds.size())};
-    recvs[2][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r], (size_t)coo_blob(coo_counts[(size_t)r * P + me])};
-    if (!M->coo[r].inds.size()) sends[2][r].bytes = 0;
-    if (!coo_counts[(size_t)r * P + me]) recvs[2][r].bytes = 0;
-    sent += (long)(cs.nvals * esz + (cs.nvals ? meta_bytes(cs.nseg, cs.nidx) : 0)) + (long)sends[2][r].bytes;
-    received += (long)(cr.nvals * esz + (cr.nvals ? meta_bytes(cr.nseg, cr.nidx) : 0)) + (long)recvs[2][r].bytes;
+    M->stats.bytes_sent += coo_blob((long)M->coo[r].inds.size()) * (M->coo[r].inds.empty() ? 0 : 1);
+    M->stats.bytes_received += coo_blob(coo_counts[(size_t)r * P + me]) * (coo_counts[(size_t)r * P + me] ? 1 : 0);
   }
-  for (int lane = 0; lane < 3; ++lane)
-    for (int r = 0; r < P; ++r) any_lane |= sends[lane][r].bytes || recvs[lane][r].bytes;
-  // every rank must take the same branch: a rank with nothing to move still joins the group when
-  // any pair moves something. The counts matrix is global knowledge, so decide from it.
-  bool global_lane = false;
-  for (int s = 0; s < P && !global_lane; ++s)
-    for (int d = 0; d < P; ++d)
-      if (s != d && ((!M->p2p && counts[(size_t)s * P + d].nvals) || coo_counts[(size_t)s * P + d])) global_lane = true;
-  (void)any_lane;
-  if (global_lane) {
-    ScopedTimer t(M, 2, 0);
-    CM_TRY(tp->alltoallv(sends, recvs, M->stream));
+
+  if (!pipelined) {
+    // one batch: pack everything, (all-to-all-v), barrier, one scatter-add over all messages
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, nupd, cp, M->g, ma, sa, M->stream);
+    M->stats.kernel_launches += nupd ? 1 : 0;
+    if (M->profiling) {
+      cudaEventRecord(ev_pack1, M->stream);
+      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+    }
+    CM_CUDA_TRY(cudaGetLastError());
+    CM_TRY(transport_lanes(0, K, true));
+    // p2p: every source's pack kernel has finished storing into my arenas
+    if (M->p2p && P > 1) CM_TRY(tp->stream_barrier(M->stream));
+  } else {
+    // pipelined (p2p only): chunk k is packed straight into the owners' arenas, a stream-ordered
+    // barrier says "everybody's chunk k has landed", and its scatter-add runs on the apply stream
+    // while chunk k+1 is being packed and stored across NVLink on the main stream
+    CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
+    for (int k = 0; k < K; ++k) {
+      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, cp.ubeg[k], cp.ubeg[k + 1], cp, M->g, ma, sa, M->stream);
+      M->stats.kernel_launches += cp.ubeg[k + 1] > cp.ubeg[k] ? 1 : 0;
+      CM_TRY(tp->stream_barrier(M->stream));
+      CM_CUDA_TRY(cudaEventRecord(M->ev_chunk[k], M->stream));
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_chunk[k], 0));
+      // all but the last chunk's scatter-add share the SMs with the next chunk's pack kernel
+      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < K ? 2 : 0));
+    }
+    if (M->profiling) {
+      cudaEventRecord(ev_pack1, M->stream);
+      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+    }
+    CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
+    CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
   }
-  M->stats.bytes_sent += sent;
-  M->stats.bytes_received += received;
-  // every source has finished writing into my arenas (p2p: their pack kernels; the transports'
-  // all-to-all-v completes on the stream by itself)
-  if (M->p2p && P > 1) CM_TRY(tp->stream_barrier(M->stream));
 
   if (M->keep_wire) {
-    // what THIS rank sent to every owner, read back from wherever pack put it
+    // what THIS rank sent to every owner, chunk after chunk, read back from wherever pack put it
     CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-    M->dbg_meta_base.assign(P + 1, 0);
-    M->dbg_val_base.assign(P + 1, 0);
-    for (int d = 0; d < P; ++d) {
-      const MsgCounts &c = counts[(size_t)me * P + d];
-      M->dbg_meta_base[d + 1] = M->dbg_meta_base[d] + (c.nvals ? meta_bytes(c.nseg, c.nidx) : 0);
-      M->dbg_val_base[d + 1] = M->dbg_val_base[d] + c.nvals;
-    }
-    M->dbg_meta.resize((size_t)M->dbg_meta_base[P]);
-    M->dbg_vals.resize((size_t)M->dbg_val_base[P] * esz);
-    for (int d = 0; d < P; ++d) {
-      const MsgCounts &c = counts[(size_t)me * P + d];
-      if (!c.nvals) continue;
-      CM_CUDA_TRY(cudaMemcpy(M->dbg_meta.data() + M->dbg_meta_base[d], dst_ptrs[P + d], (size_t)meta_bytes(c.nseg, c.nidx),
-                             cudaMemcpyDefault));
-      CM_CUDA_TRY(cudaMemcpy(M->dbg_vals.data() + (size_t)M->dbg_val_base[d] * esz, dst_ptrs[d], (size_t)c.nvals * esz,
-                             cudaMemcpyDefault));
-    }
+    M->dbg_msgs.clear();
+    for (int d = 0; d < P; ++d)
+      for (int k = 0; k < K; ++k) {
+        const MsgCounts &c = counts[cidx(me, k, d)];
+        cm_matrix::DbgMsg dm;
+        dm.dst = d;
+        if (c.nvals) {
+          const size_t i = (size_t)k * P + d;
+          dm.meta.resize((size_t)meta_bytes(c.nseg, c.nidx));
+          dm.vals.resize((size_t)c.nvals * esz);
+          CM_CUDA_TRY(cudaMemcpy(dm.meta.data(), dst_ptrs[(size_t)K * P + i], dm.meta.size(), cudaMemcpyDefault));
+          CM_CUDA_TRY(cudaMemcpy(dm.vals.data(), dst_ptrs[i], dm.vals.size(), cudaMemcpyDefault));
+        }
+        M->dbg_msgs.push_back(std::move(dm));
+      }
     M->dbg_coo = M->coo;
     M->dbg_valid = true;
   }
 
-  // -- owner side: message table -> Seg table + items -> sort -> scatter-add ---------------
-  std::vector<MsgRef> msgs;
-  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
-  for (int s = 0; s < P; ++s) {
-    const MsgCounts &c = counts[(size_t)s * P + me];
-    if (c.nvals == 0) continue;
-    MsgRef m;
-    m.meta = static_cast<char *>(M->peer_meta[me]) + rbase_m[(size_t)me * (P + 1) + s];
-    m.vals = static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[(size_t)me * (P + 1) + s] * esz;
-    m.seg_base = seg_total;
-    m.item_base = item_total;
-    seg_total += c.nseg;
-    item_total += c.nitems;
-    elem_total += c.nelems;
-    max_seg = std::max(max_seg, c.nseg);
-    msgs.push_back(m);
-  }
-  if (seg_total >= (1L << kItemSegBits))
-    return fail(CM_ERR_INVALID, "too many segments in one commit (%ld); commit more often", seg_total);
-  if (!msgs.empty()) {
-    CM_TRY(M->d_msgs.ensure(sizeof(MsgRef) * msgs.size()));
-    CM_CUDA_TRY(cudaMemcpyAsync(M->d_msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, M->stream));
-    CM_TRY(M->d_segs.ensure(sizeof(Seg) * (size_t)seg_total));
-    CM_TRY(M->d_keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
-    CM_TRY(M->d_items0.ensure(8 * (size_t)std::max(item_total, 1L)));
-    launch_build_recv(M->dtype, M->d_msgs.as<MsgRef>(), (int)msgs.size(), max_seg, M->d_segs.as<Seg>(),
-                      M->d_keys0.as<uint32_t>(), M->d_items0.as<uint64_t>(), M->stream);
-    M->stats.kernel_launches += 1;
-    CM_TRY(sort_and_apply(M, seg_total, item_total, elem_total));
-    M->stats.elements_applied += elem_total;
-  }
-  for (int s = 0; s < P; ++s) {
-    const long n = coo_counts[(size_t)s * P + me];
+  if (!pipelined) CM_TRY(apply_chunks(0, K, M->work[0], M->stream, 0));
+  for (int src = 0; src < P; ++src) {
+    const long n = coo_counts[(size_t)src * P + me];
     if (!n) continue;
-    const char *blob = s == me ? M->d_send_coo.as<char>() + s_coo_base[me] : M->d_recv_coo.as<char>() + r_coo_base[s];
+    const char *blob = src == me ? M->d_send_coo.as<char>() + s_coo_base[me] : M->d_recv_coo.as<char>() + r_coo_base[src];
     CM_TRY(apply_coo_blob(M, blob, n));
   }
   CM_CUDA_TRY(cudaGetLastError());
@@ -1006,6 +1100,9 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->apply_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_chunk[k], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_applied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->copy_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&M->d_local, M->local_elems * M->esz);
   if (e == cudaSuccess) e = cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream);  // :431-432
@@ -1064,6 +1161,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (rc0 != CM_OK) return rc0;
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
+    if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0;
     const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
     if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;
@@ -1094,9 +1192,12 @@ int cm_destroy(cm_matrix *M) {
   DevBuf *bufs[] = {&M->d_fill_ix, &M->d_fill_jx, &M->d_descs, &M->d_item_base, &M->d_rl, &M->d_rpos, &M->d_roff,
                     &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
                     &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
-                    &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_msgs, &M->d_segs,
-                    &M->d_keys0, &M->d_keys1, &M->d_items0, &M->d_items1, &M->d_sort_tmp, &M->d_recs, &M->d_col_start, &M->d_dst_ptrs};
+                    &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_dst_ptrs};
   for (DevBuf *b : bufs) b->release();
+  for (auto &w : M->work) w.release();
+  cudaStreamDestroy(M->apply_stream);
+  for (auto e : M->ev_chunk) cudaEventDestroy(e);
+  cudaEventDestroy(M->ev_applied);
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(M->stream);
@@ -1361,13 +1462,13 @@ static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *da
   const size_t esz = M->esz;
   const int dp = dst / (int)g.npcol, dq = dst % (int)g.npcol;
   long n = 0;
-  const char *meta = M->dbg_meta.data() + M->dbg_meta_base[dst];
-  const long meta_len = M->dbg_meta_base[dst + 1] - M->dbg_meta_base[dst];
-  if (meta_len >= (long)sizeof(WireHdr)) {
+  for (const auto &dm : M->dbg_msgs) {
+    if (dm.dst != dst || dm.meta.size() < sizeof(WireHdr)) continue;
+    const char *meta = dm.meta.data();
     const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
     const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
     const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
-    const unsigned char *vals = reinterpret_cast<const unsigned char *>(M->dbg_vals.data()) + (size_t)M->dbg_val_base[dst] * esz;
+    const unsigned char *vals = reinterpret_cast<const unsigned char *>(dm.vals.data());
     for (long u = 0; u < h->nseg; ++u) {
       const WireSeg &s = ws[u];
       const int *lrow = idx + s.idx_off, *lcol = lrow + s.nr;

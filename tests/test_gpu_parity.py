@@ -1,4 +1,6 @@
 """-m gpu parity tests: CUDA path (through the C ABI) vs the oracle on seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -74,6 +76,54 @@ def test_both_exchange_modes(mode):
     got = run_cuda(cfg, steps, exchange_mode=mode)
     assert_blocks_match(cfg, got, want)
     assert all(st["bytes_sent"] > 0 for st in got["stats"])
+
+
+def test_pipelined_commit_chunks():
+    """a commit big enough to be pipelined chunk by chunk (scatter-add of chunk k on the apply stream
+    while chunk k+1 is packed): > 32 Mi elements per rank and > 8 updates per matrix element"""
+    import torch
+    os.environ["CM_B200_PIPELINE"] = "1"  # opt-in path (read at cm_create)
+    cfg = Cfg(cm.F32, 1024, 1024, 2, 2, 64, 64, 512)
+    world = cm.LoopbackWorld(4, 0)
+    try:
+        mats = world.run(lambda r: cm.Matrix(*cfg.args()))
+        g = torch.Generator(device="cuda")
+        g.manual_seed(3)
+        U, m_u, n_u = 140, 512, 512  # 36.7 Mi elements per rank
+        keep, sums = [], []
+        for r in range(4):
+            ix = torch.rand((U, cfg.m), generator=g, device="cuda").topk(m_u, dim=1).indices.sort(dim=1).values.contiguous()
+            jx = torch.rand((U, cfg.n), generator=g, device="cuda").topk(n_u, dim=1).indices.sort(dim=1).values.contiguous()
+            data = torch.randint(-3, 4, (U, n_u, m_u), generator=g, device="cuda").to(torch.float32).contiguous()
+            keep.append((ix, jx, data))
+            dense = torch.zeros((cfg.n, cfg.m), dtype=torch.float32, device="cuda")
+            for u in range(U):
+                dense[jx[u][:, None], ix[u][None, :]] += data[u]
+            sums.append(dense)
+        want = sum(sums).cpu().numpy()  # want[j, i]; small integers: exact in fp32 in any order
+        torch.cuda.synchronize()
+
+        def issue(r):
+            ix, jx, data = keep[r]
+            for u in range(U):
+                mats[r].update_device(data[u].data_ptr(), m_u, n_u, m_u, False, ix[u].data_ptr(), jx[u].data_ptr())
+            mats[r].commit()
+            return mats[r].local(), mats[r].stats()
+        out = world.run(issue)
+        for r, (blk, st) in enumerate(out):
+            blk = blk.reshape(-1, cfg.lld)
+            pr, pc = r // 2, r % 2
+            gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(512)])
+            gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(512)])
+            assert np.array_equal(blk[:512, :512], want[np.ix_(gj, gi)])
+        # 4 chunks => 4 scatter-add launches per rank for the second commit
+        world.run(lambda r: (mats[r].reset_stats(), mats[r].set_profiling(True)))
+        out2 = world.run(issue)
+        assert all(st["apply_launches"] == 4 for _, st in out2), [st["apply_launches"] for _, st in out2]
+        world.run(lambda r: mats[r].destroy())
+    finally:
+        os.environ.pop("CM_B200_PIPELINE", None)
+        world.close()
 
 
 @pytest.mark.parametrize("grid", [(2, 3, 4, 8, 64, 100, 190), (3, 2, 8, 4, 96, 250, 150), (2, 4, 64, 64, 1024, 2000, 3000),
