@@ -310,7 +310,7 @@ def bench_ours(args):
         # wall clock is the honest e2e time: the host API blocks on its own H2D copies
         e2e = {"value": nranks * e_bytes * e_steps / ewall / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": est["h2d_bytes"] // e_steps, "d2h_bytes_per_step": est["d2h_bytes"] // e_steps,
-               "updates_per_rank": Ue, "steps": e_steps, "api": "cm_update_slice (host pinned buffers) + cm_commit + cm_get",
+               "updates_per_rank": Ue, "steps": e_steps, "api": "cm_update_slices (one batch call per commit, host pinned payloads) + cm_commit + cm_get",
                "device_ms_per_step": ems / e_steps, "wall_ms_per_step": ewall * 1e3 / e_steps,
                "pinned_h2d_copy_GBps": pcie_gbs,
                "note": "strict reference semantics: every update's payload is on the device before update() returns"}

@@ -107,7 +107,7 @@ struct MsgCounts {
   long nvals;   // value SLOTS of the message (segments are padded, see seg_col_stride)
   long nidx, nseg, nitems;
   long nelems;  // update elements carried (what the scatter-add will add)
-  long pad;
+  long ncoo;    // elemental updates (COO lane) from this source to this owner; chunk 0 only
 };
 
 // Layout of one segment's values inside a message: column-major nr x nc with column stride

@@ -149,7 +149,8 @@ struct Long3 {
   __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e}; }
 };
 
-__global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom g, MapArenas ma, ScanArenas sa) {
+__global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom g, MapArenas ma, ScanArenas sa,
+                                                   const long *__restrict__ coo_counts) {
   using BlockScan = cub::BlockScan<Long3, 256>;
   __shared__ typename BlockScan::TempStorage tmp;
   const int dst = blockIdx.x;
@@ -184,13 +185,14 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom 
     __syncthreads();
   }
   if (threadIdx.x == 0)
-    sa.totals[chunk * P + dst] = MsgCounts{running.a, running.b, (long)(ue - ub), running.c, running.e, 0};
+    sa.totals[chunk * P + dst] =
+        MsgCounts{running.a, running.b, (long)(ue - ub), running.c, running.e, chunk == 0 ? coo_counts[dst] : 0};
 }
 
 void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
-                 cudaStream_t s) {
+                 const long *d_coo_counts, cudaStream_t s) {
   const int P = (int)(g.nprow * g.npcol);
-  k_scan_dest<<<dim3(P, kMaxChunks), 256, 0, s>>>(nupd, cp, g, ma, sa);
+  k_scan_dest<<<dim3(P, kMaxChunks), 256, 0, s>>>(nupd, cp, g, ma, sa, d_coo_counts);
 }
 
 // ------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const Map
                       cudaStream_t s);
 // (2) per-owner scans over the staged updates (sizes of every message)
 void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
-                 cudaStream_t s);
+                 const long *d_coo_counts, cudaStream_t s);
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
 // Packs updates [u0, u1) (whole chunks).

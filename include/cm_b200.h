@@ -119,8 +119,9 @@ int cm_fill_lower(cm_matrix *M);
 int cm_update_slice_device(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld,
                            int trans, const long *d_ix, const long *d_jx, int mask);
 
-/* Batch forms: exactly `count` consecutive cm_update_slice_device / cm_update_slice calls
- * (arrays of per-update arguments; trans may be NULL = all 0). */
+/* Batch forms: the effect of `count` consecutive cm_update_slice_device / cm_update_slice calls
+ * (arrays of per-update arguments; trans may be NULL = all 0). The host form returns when every
+ * payload of the batch has been copied, so the copies of one batch overlap each other on PCIe. */
 int cm_update_slices_device(cm_matrix *M, long count, const void *const *d_data,
                             const long *m_u, const long *n_u, const long *ld, const int *trans,
                             const long *const *d_ix, const long *const *d_jx, int mask);
