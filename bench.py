@@ -51,6 +51,11 @@ def workload_spec(name, nranks):
         return dict(name=f"K2: N=32768 f64 MB=NB=64 grid {nprow}x{npcol}, 2048 updates/rank of 512x512, commit every 256",
                     dtype=0, m=32768, n=32768, nprow=nprow, npcol=npcol, mb=64, nb=64, lld=32768 // nprow,
                     m_u=512, n_u=512, U=2048, commit_every=256)
+    if name == "K3":  # BASELINE.json configs[3]: clustered / skewed index sets (owner load imbalance)
+        return dict(name=f"K3: N=65536 f64 MB=NB=64 grid {nprow}x{npcol}, 1024 updates/rank of 512x512, index sets = 8 runs of 64 "
+                         f"consecutive indices at block boundaries, blocks owned by grid row/column 0 drawn with weight 4; commit every 256",
+                    dtype=0, m=65536, n=65536, nprow=nprow, npcol=npcol, mb=64, nb=64, lld=65536 // nprow,
+                    m_u=512, n_u=512, U=1024, commit_every=256, skew=True)
     if name == "K4":  # BASELINE.json configs[4]: tiny updates, many commits
         nprow, npcol = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
         return dict(name=f"K4: N=32768 f32 MB=NB=64 grid {nprow}x{npcol}, 125000 updates/rank of 32x32, commit every 1024",
@@ -141,6 +146,18 @@ def gen_inputs(spec, rank, torch, device):
         b = min(U, a + chunk)
         data[a:b] = torch.rand((b - a, n_u, m_u), generator=g, device=device, dtype=tdt) * 2 - 1
 
+    def skewed_sets(hi, k, blk, np_):
+        # k/64 runs of 64 consecutive indices starting at 64*b; blocks b
+        # drawn without replacement with weight 4 if b % np_ == 0 else 1
+        nb_ = hi // blk
+        w = torch.ones(nb_, device=device)
+        w[torch.arange(0, nb_, np_, device=device)] = 4.0
+        blocks = torch.multinomial(w.expand(U, nb_), k // blk, replacement=False, generator=g).sort(dim=1).values
+        return (blocks[:, :, None] * blk + torch.arange(blk, device=device)[None, None, :]).reshape(U, k).contiguous()
+
+    if spec.get("skew"):
+        return data, skewed_sets(spec["m"], m_u, spec["mb"], spec["nprow"]), skewed_sets(spec["n"], n_u, spec["nb"], spec["npcol"])
+
     def index_sets(hi, k):
         out = torch.empty((U, k), dtype=torch.int64, device=device)
         step = max(1, (1 << 26) // hi)
@@ -209,7 +226,7 @@ def bench_ours(args):
         M.set_deterministic(True)
     M.set_apply_kernel({"auto": 0, "red": 1, "tile": 2}[args.apply_kernel])
     if nranks > 1:
-        M.set_exchange_mode({"auto": 0, "nccl": 1, "p2p": 2}[args.exchange])
+        M.set_exchange_mode({"auto": 0, "nccl": 1, "p2p": 2, "dma": 3}[args.exchange])
     data, ix, jx = gen_inputs(spec, rank, torch, device)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(M.stream(), device=device)
@@ -338,11 +355,14 @@ def bench_ours(args):
                 "elements_per_launch": st["apply_elements"] // max(1, st["apply_launches"]),
                 "kernel_share_of_step": st["apply_ms"] / ms}
         if nranks > 1:
-            p2p = M.exchange_mode() == 2
-            # p2p: the exchange IS the pack kernel (its stores cross NVLink); nccl: the all-to-all-v
+            xm = M.exchange_mode()
+            p2p = xm == 2
+            # p2p: the exchange IS the pack kernel (its stores cross NVLink); nccl: the all-to-all-v;
+            # dma: the copy-engine pushes (timed only when the commit is not pipelined)
             xms = st["pack_ms"] if p2p else st["exchange_ms"]
             if xms > 0:
-                roof["exchange"] = {"mode": "p2p (pack kernel stores over NVLink)" if p2p else "nccl all-to-all-v",
+                roof["exchange"] = {"mode": {1: "nccl all-to-all-v", 2: "p2p (pack kernel stores over NVLink)",
+                                             3: "dma (copy-engine pushes + flag waits)"}[xm],
                                     "bytes_sent_per_rank_per_step": st["bytes_sent"] // args.steps,
                                     "exchange_ms_per_step": xms / args.steps,
                                     "achieved_GBps_per_direction": st["bytes_sent"] / (xms * 1e-3) / 1e9,
@@ -353,6 +373,13 @@ def bench_ours(args):
     if rank == 0 and nranks == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(spec, data, ix, jx, args.cpu_updates, reps=1)
 
+    owned = None
+    if nranks > 1:
+        t_own = torch.tensor([float(st["elements_applied"])], dtype=torch.float64, device=device)
+        gathered = [torch.zeros_like(t_own) for _ in range(nranks)]
+        dist.all_gather(gathered, t_own)
+        tot = sum(float(x) for x in gathered)
+        owned = [round(float(x) / tot, 4) for x in gathered] if tot > 0 else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": nranks, "steps": args.steps,
@@ -361,10 +388,11 @@ def bench_ours(args):
             "config": {"workload": spec["name"], "updates_per_rank_per_step": spec["U"], "grid": [spec["nprow"], spec["npcol"]],
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
-                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": ("p2p" if M.exchange_mode() == 2 else "nccl") if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes},
+                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": {1: "nccl", 2: "p2p", 3: "dma"}[M.exchange_mode()] if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
             "commit_latency_us": {"empty": lat_empty, "one_update": lat_one},
+            "owner_share_of_elements": owned,
             "wall_ms_per_step": wall * 1e3 / args.steps,
             "pack_ms_per_step": st["pack_ms"] / args.steps, "apply_ms_per_step": st["apply_ms"] / args.steps,
         }
@@ -451,12 +479,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="K1", choices=["K1", "K2", "K4"])
+    ap.add_argument("--workload", default="K1", choices=["K1", "K2", "K3", "K4"])
     ap.add_argument("--flush-threshold", type=int, default=0, help="elements; 0 = library default")
     ap.add_argument("--unsorted", action="store_true", help="disable the column-sorted sweep")
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--apply-kernel", default="auto", choices=["auto", "red", "tile"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "dma"],
                     help="auto/p2p: the pack kernel stores into the owners' arenas over NVLink; nccl: grouped send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-updates", type=int, default=0, help="updates per rank per e2e step (0 = all)")

@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "cm_kernels.h"
 
@@ -585,8 +586,7 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_loc
 // traffic is the compulsory s*E + 2*s*(touched sectors) instead of one sector round trip
 // per element. Best when the flush hits the local block densely.
 // ------------------------------------------------------------------------------------
-constexpr int kRecChunk = 132;  // items of a run staged in shared memory at a time (multiple of 2*kTileBlk)
-constexpr int kTileBlk = 6;     // items whose values / row indices a thread keeps in flight in registers
+constexpr int kRecChunk = 144;  // items of a run staged in shared memory at a time (multiple of 2*BLK)
 
 template <typename T>
 struct TileItem {  // one staged item, 32 bytes
@@ -616,12 +616,12 @@ __device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geo
   return (int)lo - 1;
 }
 
-// fetch element `tid` of the kTileBlk items starting at staged index j0 (plain items: stride 1)
-template <typename T, bool kMulti>
-__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int r0, int h, int (&row)[kTileBlk],
-                                                T (&val)[kTileBlk]) {
+// fetch element `tid` of the BLK items starting at staged index j0 (plain items: stride 1)
+template <typename T, bool kMulti, int BLK>
+__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int r0, int h, int (&row)[BLK],
+                                                T (&val)[BLK]) {
 #pragma unroll
-  for (int i = 0; i < kTileBlk; ++i) {
+  for (int i = 0; i < BLK; ++i) {
     const TileItem<T> t = it[i];
     const bool ok = tid < t.n;
     const int aa = ok ? tid : 0;  // idle threads re-read element 0 (always valid memory)
@@ -631,22 +631,24 @@ __device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, 
   }
   if (kMulti) {  // taller than one tile: fetch the value only if this tile owns the row
 #pragma unroll
-    for (int i = 0; i < kTileBlk; ++i) val[i] = __ldg(it[i].v + (row[i] >= 0 ? tid : 0));
+    for (int i = 0; i < BLK; ++i) val[i] = __ldg(it[i].v + (row[i] >= 0 ? tid : 0));
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void tile_add_block(T *acc, const int (&row)[kTileBlk], const T (&val)[kTileBlk]) {
+template <typename T, int BLK>
+__device__ __forceinline__ void tile_add_block(T *acc, const int (&row)[BLK], const T (&val)[BLK]) {
 #pragma unroll
-  for (int i = 0; i < kTileBlk; ++i) {
+  for (int i = 0; i < BLK; ++i) {
     if (row[i] >= 0) acc[row[i]] += val[i];
     __syncthreads();  // items strictly in order
   }
 }
 
 // kMulti: the local block is taller than one tile, so a block only owns part of each item's rows.
-template <typename T, bool kMulti>
-__global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
+// BLK: items a thread keeps in flight per register set (two sets); CTAS: resident blocks per SM
+// the register budget is sized for (3 x 6-item sets or 2 x 12-item sets).
+template <typename T, bool kMulti, int BLK, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
                                                        long ncols, int ntiles, long m_local, T *local, Geom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
@@ -683,16 +685,16 @@ __global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict
       if (plain) {
         // thread t owns element t of every item; block b+1's elements are in flight while block b
         // is added; one barrier per item keeps the items in order
-        int rowA[kTileBlk], rowB[kTileBlk];
-        T valA[kTileBlk], valB[kTileBlk];
-        const int nblk = (cnt + kTileBlk - 1) / kTileBlk;  // staged padding covers up to kRecChunk
-        tile_load_block<T, kMulti>(sm.item, tid, r0, h, rowA, valA);
+        int rowA[BLK], rowB[BLK];
+        T valA[BLK], valB[BLK];
+        const int nblk = (cnt + BLK - 1) / BLK;  // staged padding covers up to kRecChunk
+        tile_load_block<T, kMulti, BLK>(sm.item, tid, r0, h, rowA, valA);
         for (int b = 0; b < nblk; b += 2) {
-          if (b + 1 < nblk) tile_load_block<T, kMulti>(sm.item + (b + 1) * kTileBlk, tid, r0, h, rowB, valB);
-          tile_add_block<T>(sm.acc, rowA, valA);
+          if (b + 1 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 1) * BLK, tid, r0, h, rowB, valB);
+          tile_add_block<T, BLK>(sm.acc, rowA, valA);
           if (b + 1 < nblk) {
-            if (b + 2 < nblk) tile_load_block<T, kMulti>(sm.item + (b + 2) * kTileBlk, tid, r0, h, rowA, valA);
-            tile_add_block<T>(sm.acc, rowB, valB);
+            if (b + 2 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 2) * BLK, tid, r0, h, rowA, valA);
+            tile_add_block<T, BLK>(sm.acc, rowB, valB);
           }
         }
       } else {
@@ -754,30 +756,40 @@ __global__ void __launch_bounds__(256, 3) k_apply_tile(const ItemRec *__restrict
   }
 }
 
-template <typename T>
-static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+template <typename T, bool kMulti, int BLK, int CTAS>
+static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
+                                T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
-  static bool attr_set = false;
-  static int resident1 = 0, residentM = 0;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_apply_tile<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_apply_tile<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resident1 = resident_blocks(k_apply_tile<T, false>, 256, smem);
-    residentM = resident_blocks(k_apply_tile<T, true>, 256, smem);
-    attr_set = true;
+  static int resident = 0;
+  if (resident == 0) {
+    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
   }
-  const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
   const long nunits = n_local * ntiles;
   // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
   // the next chunk in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  if (ntiles == 1)
-    k_apply_tile<T, false><<<(unsigned)std::min({nunits, (long)resident1, cap}), 256, smem, s>>>(
-        d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
-  else
-    k_apply_tile<T, true><<<(unsigned)std::min({nunits, (long)residentM, cap}), 256, smem, s>>>(
-        d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
+  k_apply_tile<T, kMulti, BLK, CTAS><<<(unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s>>>(
+      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
+}
+
+template <typename T>
+static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
+                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+  const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
+  // variant 0 (default): 6-item sets, 3 blocks per SM; variant 1: 12-item sets, 2 blocks per SM
+  static const int variant = getenv("CM_B200_TILE_VARIANT") ? atoi(getenv("CM_B200_TILE_VARIANT")) : 0;
+  if (ntiles == 1) {
+    if (variant == 1)
+      launch_tile_variant<T, false, 12, 2>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    else
+      launch_tile_variant<T, false, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+  } else {
+    if (variant == 1)
+      launch_tile_variant<T, true, 12, 2>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    else
+      launch_tile_variant<T, true, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+  }
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,

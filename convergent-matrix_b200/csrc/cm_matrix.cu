@@ -256,8 +256,21 @@ struct cm_matrix {
   std::vector<bool> peer_ipc_open;
   // receive arenas of every rank (mine included), see ensure_recv_arenas()
   bool p2p_possible = false;
-  bool p2p = false;         // sources store straight into the owners' arenas (pack == exchange)
-  int exchange_mode = 0;    // 0 auto, 1 transport all-to-all-v, 2 peer-to-peer stores
+  bool p2p = false;         // every rank maps every rank's receive arenas (modes 2 and 3)
+  bool dma = false;         // mode 3: messages are packed locally and moved by the copy engines
+  int exchange_mode = 0;    // 0 auto, 1 transport all-to-all-v, 2 peer-to-peer stores, 3 copy-engine pushes
+  // mode 3 signalling: flags[src] on every rank, written by the source after its copies (a 4-byte
+  // copy ordered behind them on the same stream), awaited with cuStreamWaitValue32 by the owner
+  DevBuf d_flags;
+  std::vector<void *> peer_flags;
+  std::vector<bool> peer_flags_open;
+  uint32_t xfer_seq = 0;
+  PinBuf h_seq;
+  unsigned seq_slot = 0;
+  static constexpr int kXferStreams = 4;  // peers are spread over several streams = several copy engines
+  cudaStream_t xfer_stream[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_packed[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_xfer[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void *> peer_vals, peer_meta;
   std::vector<size_t> cap_vals, cap_meta;
   std::vector<bool> peer_arena_open;
@@ -303,9 +316,10 @@ struct cm_matrix {
   cudaStream_t apply_stream = nullptr;  // scatter-add of chunk k while chunk k+1 is packed / exchanged
   cudaEvent_t ev_chunk[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
-  int pipeline = 0;                     // chunk-pipelined commits: opt-in (CM_B200_PIPELINE=1). Measured on 2 B200s
-                                        // (K1-weak) it is slower than one batch (7.8 vs 6.6 ms per step): the
-                                        // scatter-add and the next chunk's pack do not co-schedule well yet
+  int pipeline = -1;                    // chunk-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
+                                        // forces it in mode 2 too (measured slower there, 2 B200s K1-weak 7.8 vs
+                                        // 6.6 ms per step: the scatter-add and the next chunk's pack kernel compete
+                                        // for the SMs), =0 disables it everywhere
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
   PinBuf h_counts;
 
@@ -548,6 +562,24 @@ int flush_direct(cm_matrix *M) {
   return CM_OK;
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no libcuda link dependency)
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StreamWaitValue32Fn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
 // ---- receive arenas ---------------------------------------------------------------------
 // Every rank owns a values arena and a metadata arena that hold the messages of ONE commit from
 // all sources (its own included). With peer-to-peer exchange the sources' pack kernels store
@@ -695,7 +727,7 @@ int commit_exchange(cm_matrix *M) {
   // scatter-add sweeps the whole local block once, so pipelining pays only when a chunk brings
   // at least about two updates per matrix element; smaller commits go as one batch.
   bool pipelined = false;
-  if (P > 1 && M->p2p && M->pipeline) {
+  if (P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1)) {
     long total = 0;
     for (int src = 0; src < P; ++src)
       for (int k = 0; k < K; ++k)
@@ -721,18 +753,19 @@ int commit_exchange(cm_matrix *M) {
   }
   CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
 
-  // -- where my messages go: p2p = straight into the owners' arenas; otherwise my own messages
-  // into my arena and the others into a local send arena --------------------------------------
+  // -- where my messages go: mode 2 = straight into the owners' arenas; otherwise my own messages
+  // into my arena and the others into a local send arena (moved by NCCL or by the copy engines)
+  const bool remote_store = M->p2p && !M->dma;
   std::vector<long> s_val_base((size_t)K * P + 1, 0), s_meta_base((size_t)K * P + 1, 0);
   for (int k = 0; k < K; ++k)
     for (int d = 0; d < P; ++d) {
       const MsgCounts &c = counts[cidx(me, k, d)];
-      const bool staged = !M->p2p && d != me;
+      const bool staged = !remote_store && d != me;
       const size_t i = (size_t)k * P + d;
       s_val_base[i + 1] = s_val_base[i] + (staged ? ((c.nvals + 31) & ~31L) : 0);
       s_meta_base[i + 1] = s_meta_base[i] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
     }
-  if (!M->p2p) {
+  if (!remote_store) {
     CM_TRY(M->d_send_vals.ensure(std::max((size_t)s_val_base[(size_t)K * P] * esz, (size_t)256)));
     CM_TRY(M->d_send_meta.ensure(std::max((size_t)s_meta_base[(size_t)K * P], (size_t)256)));
   }
@@ -740,7 +773,7 @@ int commit_exchange(cm_matrix *M) {
   for (int k = 0; k < K; ++k)
     for (int d = 0; d < P; ++d) {
       const size_t i = (size_t)k * P + d;
-      if (M->p2p || d == me) {
+      if (remote_store || d == me) {
         dst_ptrs[i] = static_cast<char *>(M->peer_vals[d]) + (size_t)rbase_v[ridx(d, k, me)] * esz;
         dst_ptrs[(size_t)K * P + i] = static_cast<char *>(M->peer_meta[d]) + rbase_m[ridx(d, k, me)];
       } else {
@@ -813,7 +846,7 @@ int commit_exchange(cm_matrix *M) {
     bool global_lane = false;  // every rank must take the same branch: decide from the global counts
     for (int r = 0; r < P; ++r) {
       if (r == me) continue;
-      if (!M->p2p)
+      if (!M->p2p)  // NCCL mode only: values and metadata lanes
         for (int k = k0; k < k1; ++k) {
           const MsgCounts &cs = counts[cidx(me, k, r)];
           const MsgCounts &cr = counts[cidx(r, k, me)];
@@ -848,6 +881,50 @@ int commit_exchange(cm_matrix *M) {
     return CM_OK;
   };
 
+  // -- mode 3: push chunks [k0, k1) to their owners with the copy engines, then tell every owner.
+  // `after` = event on the main stream behind the pack of those chunks; the owner-side wait for
+  // all sources is enqueued on `waiter`.
+  auto dma_push = [&](int k0, int k1, cudaEvent_t after, cudaStream_t waiter) -> int {
+    constexpr int NS = cm_matrix::kXferStreams;
+    for (int x = 0; x < NS; ++x) CM_CUDA_TRY(cudaStreamWaitEvent(M->xfer_stream[x], after, 0));
+    const uint32_t seq = ++M->xfer_seq;
+    uint32_t *ring = static_cast<uint32_t *>(M->h_seq.p);
+    // peer r's traffic rides on stream (r - me) mod NS: at any moment the ranks target different peers
+    for (int dr = 1; dr < P; ++dr) {
+      const int r = (me + dr) % P;
+      cudaStream_t xs = M->xfer_stream[dr % NS];
+      for (int k = k0; k < k1; ++k) {
+        const MsgCounts &cs = counts[cidx(me, k, r)];
+        if (!cs.nvals) continue;
+        const size_t i = (size_t)k * P + r;
+        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_vals[r]) + (size_t)rbase_v[ridx(r, k, me)] * esz, dst_ptrs[i],
+                                    (size_t)cs.nvals * esz, cudaMemcpyDefault, xs));
+        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_meta[r]) + rbase_m[ridx(r, k, me)],
+                                    dst_ptrs[(size_t)K * P + i], (size_t)meta_bytes(cs.nseg, cs.nidx), cudaMemcpyDefault, xs));
+      }
+      if (!tp->same_process()) {  // tell owner r: everything of mine for these chunks has landed
+        uint32_t *slot = ring + (M->seq_slot++ % 1024);
+        *slot = seq;
+        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)me, slot, 4, cudaMemcpyDefault, xs));
+      }
+    }
+    if (tp->same_process()) {
+      // threads-as-ranks on one device: a host rendezvous instead of device-side flag waits
+      // (many streams of one process share hardware queues; a stream wait could block its releaser)
+      for (int x = 0; x < NS; ++x) CM_CUDA_TRY(cudaStreamSynchronize(M->xfer_stream[x]));
+      CM_TRY(tp->stream_barrier(M->xfer_stream[0]));
+      return CM_OK;
+    }
+    StreamWaitValue32Fn wait32 = stream_wait_value32();
+    for (int r = 0; r < P; ++r) {
+      if (r == me) continue;
+      const int rc = wait32(waiter, (unsigned long long)(uintptr_t)(M->d_flags.as<char>() + 4 * (size_t)r), seq,
+                            /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0);
+      if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
+    }
+    return CM_OK;
+  };
+
   for (int r = 0; r < P; ++r) {
     if (r == me) continue;
     for (int k = 0; k < K; ++k) {
@@ -869,10 +946,40 @@ int commit_exchange(cm_matrix *M) {
     }
     CM_CUDA_TRY(cudaGetLastError());
     CM_TRY(transport_lanes(0, K, true));
-    // p2p: every source's pack kernel has finished storing into my arenas
-    if (M->p2p && P > 1) CM_TRY(tp->stream_barrier(M->stream));
+    if (M->dma && P > 1) {
+      // copy engines push my messages; the scatter-add waits for every source's flag
+      CM_CUDA_TRY(cudaEventRecord(M->ev_packed[0], M->stream));
+      ScopedTimer t(M, 2, 0);
+      CM_TRY(dma_push(0, K, M->ev_packed[0], M->stream));
+    } else if (M->p2p && P > 1) {
+      // mode 2: every source's pack kernel has finished storing into my arenas
+      CM_TRY(tp->stream_barrier(M->stream));
+    }
+  } else if (M->dma) {
+    // pipelined, mode 3: chunk k is packed locally (main stream), pushed by the copy engines
+    // (xfer stream) and scatter-added (apply stream) while chunk k+1 is packed and pushed. The
+    // exchange uses no SM at all, so the two kernels never compete with communication.
+    CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
+    for (int k = 0; k < K; ++k) {
+      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, cp.ubeg[k], cp.ubeg[k + 1], cp, M->g, ma, sa, M->stream);
+      M->stats.kernel_launches += cp.ubeg[k + 1] > cp.ubeg[k] ? 1 : 0;
+      CM_CUDA_TRY(cudaEventRecord(M->ev_packed[k], M->stream));
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_packed[k], 0));  // my own message of chunk k
+      CM_TRY(dma_push(k, k + 1, M->ev_packed[k], M->apply_stream));
+      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, 0));
+    }
+    if (M->profiling) {
+      cudaEventRecord(ev_pack1, M->stream);
+      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+    }
+    CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
+    CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
+    for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
+      CM_CUDA_TRY(cudaEventRecord(M->ev_xfer[x], M->xfer_stream[x]));
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_xfer[x], 0));
+    }
   } else {
-    // pipelined (p2p only): chunk k is packed straight into the owners' arenas, a stream-ordered
+    // pipelined, mode 2: chunk k is packed straight into the owners' arenas, a stream-ordered
     // barrier says "everybody's chunk k has landed", and its scatter-add runs on the apply stream
     // while chunk k+1 is being packed and stored across NVLink on the main stream
     CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
@@ -916,6 +1023,12 @@ int commit_exchange(cm_matrix *M) {
   }
 
   if (!pipelined) CM_TRY(apply_chunks(0, K, M->work[0], M->stream, 0));
+  if (M->dma && P > 1 && !pipelined) {  // my pushes are complete before anyone may reuse the arenas
+    for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
+      CM_CUDA_TRY(cudaEventRecord(M->ev_xfer[x], M->xfer_stream[x]));
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_xfer[x], 0));
+    }
+  }
   for (int src = 0; src < P; ++src) {
     const long n = coo_counts[(size_t)src * P + me];
     if (!n) continue;
@@ -1143,6 +1256,11 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->apply_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < cm_matrix::kXferStreams && e == cudaSuccess; ++k) {
+    e = cudaStreamCreateWithFlags(&M->xfer_stream[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_xfer[k], cudaEventDisableTiming);
+  }
+  for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_packed[k], cudaEventDisableTiming);
   for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_chunk[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_applied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->copy_done, cudaEventDisableTiming);
@@ -1189,6 +1307,43 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
       }
     }
   }
+  // per-source arrival flags for the copy-engine exchange, mapped like the local block
+  bool flags_ok = true;
+  M->peer_flags.assign(M->P, nullptr);
+  M->peer_flags_open.assign(M->P, false);
+  if (M->P > 1) {
+    int rcf = M->d_flags.ensure(4 * (size_t)M->P);
+    if (rcf == CM_OK) rcf = M->h_seq.ensure(4 * 1024);
+    if (rcf != CM_OK) return rcf;
+    cudaMemsetAsync(M->d_flags.p, 0, 4 * (size_t)M->P, M->stream);
+    cudaStreamSynchronize(M->stream);
+    M->peer_flags[M->me] = M->d_flags.p;
+    if (ctx->tp->same_process()) {
+      std::vector<void *> all(M->P);
+      int rc1 = ctx->tp->host_allgather(&M->d_flags.p, all.data(), sizeof(void *), M->stream);
+      if (rc1 != CM_OK) return rc1;
+      M->peer_flags = all;
+    } else {
+      cudaIpcMemHandle_t mine;
+      std::vector<cudaIpcMemHandle_t> all(M->P);
+      memset(&mine, 0, sizeof(mine));
+      const bool have = cudaIpcGetMemHandle(&mine, M->d_flags.p) == cudaSuccess;
+      if (!have) cudaGetLastError();
+      int rc1 = ctx->tp->host_allgather(&mine, all.data(), sizeof(mine), M->stream);
+      if (rc1 != CM_OK) return rc1;
+      for (int r = 0; r < M->P; ++r) {
+        if (r == M->me) continue;
+        void *pp = nullptr;
+        if (have && cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+          M->peer_flags[r] = pp;
+          M->peer_flags_open[r] = true;
+        } else {
+          cudaGetLastError();
+          flags_ok = false;
+        }
+      }
+    }
+  }
   M->peer_vals.assign(M->P, nullptr);
   M->peer_meta.assign(M->P, nullptr);
   M->cap_vals.assign(M->P, 0);
@@ -1196,18 +1351,22 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->peer_arena_open.assign(M->P, false);
   {
     // peer-to-peer stores need every rank to be able to map every other rank's memory
-    int mine_ok = 1;
+    int mine_ok = flags_ok ? 1 : 0;
     for (int r = 0; r < M->P; ++r) mine_ok &= M->peer_local[r] != nullptr;
+    flags_ok = true;  // folded into the collective decision below
     std::vector<int> all_ok(M->P, 0);
     int rc0 = ctx->tp->host_allgather(&mine_ok, all_ok.data(), sizeof(int), M->stream);
     if (rc0 != CM_OK) return rc0;
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
-    if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0;
-    const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" override, must agree on all ranks
+    if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
+    const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" / "dma" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
     if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;
+    if (env && !strcmp(env, "dma")) M->exchange_mode = 3;
+    M->p2p_possible &= flags_ok;
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
+    M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
   }
   int rc = ctx->tp->barrier(M->stream);
   if (rc != CM_OK) return rc;
@@ -1225,6 +1384,7 @@ int cm_destroy(cm_matrix *M) {
       cudaIpcCloseMemHandle(M->peer_vals[r]);
       cudaIpcCloseMemHandle(M->peer_meta[r]);
     }
+    if (M->peer_flags_open[r]) cudaIpcCloseMemHandle(M->peer_flags[r]);
   }
   M->ctx->tp->barrier(M->stream);  // nobody still reads my block
   cudaFree(M->d_local);
@@ -1238,6 +1398,11 @@ int cm_destroy(cm_matrix *M) {
   for (DevBuf *b : bufs) b->release();
   for (auto &w : M->work) w.release();
   cudaStreamDestroy(M->apply_stream);
+  for (auto st : M->xfer_stream) cudaStreamDestroy(st);
+  for (auto e : M->ev_packed) cudaEventDestroy(e);
+  for (auto e : M->ev_xfer) cudaEventDestroy(e);
+  M->d_flags.release();
+  M->h_seq.release();
   for (auto e : M->ev_chunk) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);
   M->h_counts.release();
@@ -1445,12 +1610,16 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density) {
 }
 int cm_set_exchange_mode(cm_matrix *M, int mode) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
-  if (mode < 0 || mode > 2) return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v) or 2 (peer-to-peer)");
+  if (mode < 0 || mode > 3)
+    return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v), 2 (peer-to-peer stores) or 3 (copy engines)");
   if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the exchange mode only with nothing staged");
-  if (mode == 2 && M->P > 1 && !M->p2p_possible)
+  if (mode >= 2 && M->P > 1 && !M->p2p_possible)
     return fail(CM_ERR_STATE, "peer-to-peer exchange needs every rank's memory mapped (CUDA IPC unavailable)");
+  if (mode == 3 && M->P > 1 && !M->ctx->tp->same_process() && stream_wait_value32() == nullptr)
+    return fail(CM_ERR_STATE, "copy-engine exchange needs cuStreamWaitValue32");
   M->exchange_mode = mode;
   M->p2p = M->P > 1 && M->p2p_possible && mode != 1;
+  M->dma = M->p2p && mode == 3;
   // arenas allocated under the other mode are not mapped by the peers: start over
   for (int r = 0; r < M->P; ++r) {
     if (M->peer_arena_open[r]) {
@@ -1466,7 +1635,7 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
   M->d_recv_meta.release();
   return CM_OK;
 }
-int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->p2p ? 2 : 1) : -1; }
+int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->dma ? 3 : (M->p2p ? 2 : 1)) : -1; }
 int cm_set_profiling(cm_matrix *M, int on) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   M->profiling = on ? 1 : 0;

@@ -182,11 +182,14 @@ int cm_set_sorted_sweep(cm_matrix *M, int on);
 int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
 
 /* How commit() moves the per-owner messages (COLLECTIVE: same call on every rank, nothing staged):
- * 0 = auto, 1 = grouped ncclSend/ncclRecv all-to-all-v from a local send arena, 2 = peer-to-peer:
- * the pack kernel stores each message straight into the owner's receive arena over NVLink (arenas
- * mapped with CUDA IPC), so packing and exchange are one kernel. Auto picks 2 when every rank can
- * map every other rank's memory. The environment variable CM_B200_EXCHANGE=nccl|p2p sets the
- * default. cm_get_exchange_mode returns the mode in effect (1 or 2). */
+ * 0 = auto, 1 = grouped ncclSend/ncclRecv all-to-all-v from a local send arena, 2 = peer-to-peer
+ * stores: the pack kernel writes each message straight into the owner's receive arena over NVLink
+ * (arenas mapped with CUDA IPC), so packing and exchange are one kernel, 3 = copy engines: messages
+ * are packed locally and pushed into the owners' arenas with peer cudaMemcpyAsync, arrival is
+ * signalled with a flag the owner awaits with cuStreamWaitValue32 (no SM does communication, so
+ * the scatter-add of one chunk overlaps the push of the next). Auto picks 2 when every rank can map
+ * every other rank's memory, else 1. The environment variable CM_B200_EXCHANGE=nccl|p2p|dma sets
+ * the default. cm_get_exchange_mode returns the mode in effect (1, 2 or 3). */
 int cm_set_exchange_mode(cm_matrix *M, int mode);
 int cm_get_exchange_mode(const cm_matrix *M);
 

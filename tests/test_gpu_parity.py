@@ -62,10 +62,10 @@ def test_k0_grid_2x2_slices(dtype):
     assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_both_exchange_modes(mode):
     """1 = all-to-all-v through the transport from a send arena, 2 = pack kernel stores straight into
-    the owners' receive arenas (peer-to-peer); same messages, same result"""
+    the owners' receive arenas (peer-to-peer), 3 = copy-engine pushes; same messages, same result"""
     cfg = Cfg(cm.F64, 2000, 1000, 2, 2, 64, 64, 1024)
     rng = np.random.default_rng(22)
     steps = slice_steps(cfg, rng, 4, 500, 300, commit_every=1)  # growing then steady arenas
@@ -78,15 +78,19 @@ def test_both_exchange_modes(mode):
     assert all(st["bytes_sent"] > 0 for st in got["stats"])
 
 
-def test_pipelined_commit_chunks():
+@pytest.mark.parametrize("mode", [2, 3])
+def test_pipelined_commit_chunks(mode):
     """a commit big enough to be pipelined chunk by chunk (scatter-add of chunk k on the apply stream
-    while chunk k+1 is packed): > 32 Mi elements per rank and > 8 updates per matrix element"""
+    while chunk k+1 is packed / pushed): > 32 Mi elements per rank and > 8 updates per matrix element.
+    Mode 3 (copy engines) pipelines by default, mode 2 (peer stores) only with CM_B200_PIPELINE=1."""
     import torch
-    os.environ["CM_B200_PIPELINE"] = "1"  # opt-in path (read at cm_create)
+    if mode == 2:
+        os.environ["CM_B200_PIPELINE"] = "1"  # opt-in path (read at cm_create)
     cfg = Cfg(cm.F32, 1024, 1024, 2, 2, 64, 64, 512)
     world = cm.LoopbackWorld(4, 0)
     try:
         mats = world.run(lambda r: cm.Matrix(*cfg.args()))
+        world.run(lambda r: mats[r].set_exchange_mode(mode))
         g = torch.Generator(device="cuda")
         g.manual_seed(3)
         U, m_u, n_u = 140, 512, 512  # 36.7 Mi elements per rank
