@@ -756,6 +756,202 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
   }
 }
 
+// ------------------------------------------------------------------------------------
+// (6c) column-tile scatter-add, TMA variant. Same ownership and ordering as k_apply_tile, but the
+// values (n*s bytes, contiguous) and row indices (n*4 bytes) of each item are brought into a
+// kTmaStages-deep shared-memory ring by 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that one
+// thread issues and that complete on per-stage mbarriers: a dozen items are in flight per block at
+// no register cost. Eligible items are 16-byte aligned with n % 4 == 0 (always true for the
+// payloads of K1-shaped updates); other items fall back to per-thread loads inside the same loop.
+// ------------------------------------------------------------------------------------
+constexpr int kTmaStages = 12;
+
+template <typename T>
+struct TileSmemTma {
+  static constexpr int kTileRows = 65536 / (int)sizeof(T);
+  T acc[kTileRows];
+  alignas(16) T vals[kTmaStages][256];
+  alignas(16) int rows[kTmaStages][256];
+  TileItem<T> item[kRecChunk];
+  alignas(8) unsigned long long full[kTmaStages];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) k_apply_tile_tma(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
+                                                           long ncols, long m_local, T *local, Geom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmemTma<T> &sm = *reinterpret_cast<TileSmemTma<T> *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int h = (int)m_local;  // one tile covers all local rows (the launcher guarantees it)
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase = 0;  // bit s = parity the next wait on stage s expects (identical in every thread)
+
+  // thread 0: start the bulk copies of staged item j into its ring stage (or just arrive)
+  auto fill = [&](int j) {
+    const TileItem<T> t = sm.item[j];
+    const int s = j % kTmaStages;
+    if (t.pad) {
+      mbar_arrive_expect_tx(&sm.full[s], (unsigned)t.n * (unsigned)(sizeof(T) + 4));
+      tma_load_1d(sm.vals[s], t.v, (unsigned)t.n * (unsigned)sizeof(T), &sm.full[s]);
+      tma_load_1d(sm.rows[s], t.rows, (unsigned)t.n * 4u, &sm.full[s]);
+    } else {
+      mbar_arrive(&sm.full[s]);
+    }
+  };
+
+  for (long c = blockIdx.x; c < ncols; c += gridDim.x) {
+    const long lo = col_start[c], hi = col_start[c + 1];
+    if (lo == hi) continue;  // uniform: nothing for this column in this flush
+    for (int i = tid; i < h; i += 256) sm.acc[i] = T(0);
+
+    for (long base = lo; base < hi; base += kRecChunk) {
+      const int cnt = (int)min((long)kRecChunk, hi - base);
+      __syncthreads();  // previous chunk fully consumed; acc zeroed
+      int special = 0;
+      if (tid < cnt) {
+        const ItemRec r = recs[base + tid];
+        TileItem<T> t;
+        t.v = static_cast<const T *>(r.v);
+        t.rows = r.lrow;
+        t.n = r.n;
+        t.stride = r.row_stride;
+        t.mf = r.mask_flags;
+        // bulk-copy eligible: unit stride, 16-byte aligned sources, sizes multiples of 16 bytes
+        t.pad = (r.row_stride == 1 && (r.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(r.v) & 15) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(r.lrow) & 15) == 0))
+                    ? 1
+                    : 0;
+        sm.item[tid] = t;
+        special = r.mask_flags | (r.row_stride != 1);
+      }
+      const bool plain = __syncthreads_or(special) == 0;  // no mask, no repeated rows, unit stride
+      if (plain) {
+        if (tid == 0)
+          for (int j = 0; j < min(cnt, kTmaStages); ++j) fill(j);
+        for (int k = 0; k < cnt; ++k) {
+          const int s = k % kTmaStages;
+          mbar_wait(&sm.full[s], (phase >> s) & 1u);
+          phase ^= 1u << s;
+          const TileItem<T> t = sm.item[k];
+          if (tid < t.n) {
+            int rr;
+            T x;
+            if (t.pad) {
+              rr = sm.rows[s][tid];
+              x = sm.vals[s][tid];
+            } else {
+              rr = __ldg(t.rows + tid);
+              x = __ldg(t.v + tid);
+            }
+            if ((unsigned)rr < (unsigned)h) sm.acc[rr] += x;
+          }
+          __syncthreads();  // items strictly in order; stage s is free again
+          if (tid == 0 && k + kTmaStages < cnt) fill(k + kTmaStages);
+        }
+      } else {
+        // masked (symmetric update / fill_lower), strided or repeated-row items: simple in-order loop
+        const int thr = mask_threshold(global_index(c, g.nb, g.npcol, g.mypcol), m_local, g);
+        for (int j = 0; j < cnt; ++j) {
+          const TileItem<T> t = sm.item[j];
+          const int mask = t.mf & 0xff;
+          if (t.mf >> 8) {
+            if (tid == 0) {  // rows may repeat: one thread applies the item serially
+              for (int a = 0; a < t.n; ++a) {
+                const int rr = t.rows[a];
+                if ((unsigned)rr >= (unsigned)h) continue;
+                if (mask != 0 && (mask == 1) != (rr <= thr)) continue;
+                sm.acc[rr] += t.v[(long)a * t.stride];
+              }
+            }
+          } else if (tid < t.n) {
+            const int rr = __ldg(t.rows + tid);
+            if ((unsigned)rr < (unsigned)h && (mask == 0 || (mask == 1) == (rr <= thr)))
+              sm.acc[rr] += __ldg(t.v + (long)tid * t.stride);
+          }
+          __syncthreads();
+        }
+      }
+    }
+    __syncthreads();
+
+    // write-back: local[c, i] += acc[i], 16 bytes per thread step, untouched pieces skipped
+    T *dcol = local + c * g.lld;
+    constexpr int kPer = 16 / (int)sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) {
+      const int hv = h / kPer;
+#pragma unroll 4
+      for (int i = tid; i < hv; i += 256) {
+        T a[kPer];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          a[k] = sm.acc[i * kPer + k];
+          any |= a[k] != T(0);
+        }
+        if (any) {
+          T *p = dcol + (long)i * kPer;
+          T q[kPer];
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) q[k] = p[k];
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) p[k] = q[k] + a[k];
+        }
+      }
+      for (int i = hv * kPer + tid; i < h; i += 256)
+        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
+    } else {
+      for (int i = tid; i < h; i += 256)
+        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
+    }
+    __syncthreads();  // the next column re-zeroes acc
+  }
+}
+
+template <typename T>
+static void launch_tile_tma(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
+                            const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+  const size_t smem = sizeof(TileSmemTma<T>);
+  static int resident = 0;
+  if (resident == 0) {
+    cudaFuncSetAttribute(k_apply_tile_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident = resident_blocks(k_apply_tile_tma<T>, 256, smem);
+  }
+  const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
+  k_apply_tile_tma<T><<<(unsigned)std::min({n_local, (long)resident, cap}), 256, smem, s>>>(d_recs, d_col_start, n_local,
+                                                                                       m_local, d_local, g);
+}
+
 template <typename T, bool kMulti, int BLK, int CTAS>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
                                 T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
@@ -775,8 +971,17 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
 
 template <typename T>
 static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+                                const Geom &g, int max_blocks_per_sm, bool tma_hint, cudaStream_t s) {
   const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
+  // TMA ring variant: opt-in (CM_B200_TILE_TMA=1 when the caller knows the items are bulk-copy
+  // eligible, =2 always). Measured on K1 (B200) it is slower than the register-prefetch kernel,
+  // 0.97 vs 0.61 ms per 131 M elements: two 1-2 KiB bulk copies per item keep the SM's TMA unit
+  // busy ~550 cycles per item, more than the whole register path costs.
+  static const int tma_mode = getenv("CM_B200_TILE_TMA") ? atoi(getenv("CM_B200_TILE_TMA")) : 0;  // 0 never, 1 hint, 2 always
+  if (ntiles == 1 && (tma_mode == 2 || (tma_mode == 1 && tma_hint))) {
+    launch_tile_tma<T>(d_recs, d_col_start, n_local, m_local, d_local, g, max_blocks_per_sm, s);
+    return;
+  }
   // variant 0 (default): 6-item sets, 3 blocks per SM; variant 1: 12-item sets, 2 blocks per SM
   static const int variant = getenv("CM_B200_TILE_VARIANT") ? atoi(getenv("CM_B200_TILE_VARIANT")) : 0;
   if (ntiles == 1) {
@@ -793,12 +998,12 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
-                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, bool tma_hint, cudaStream_t s) {
   if (nitems <= 0) return;
   switch (dtype) {
-    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, s); break;
-    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, s); break;
-    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, s); break;
+    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
+    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
+    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
   }
 }
 
