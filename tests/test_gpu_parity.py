@@ -334,3 +334,27 @@ def test_full_size_properties_k1():
         M.destroy()
     finally:
         cm.finalize()
+
+
+@pytest.mark.parametrize("env", [{"CM_B200_TILE_TMA": "2"}, {"CM_B200_TILE_VARIANT": "1"}])
+def test_opt_in_tile_kernel_variants(env):
+    """the TMA-ring and the 12-item/2-blocks variants of the column-tile kernel are selected by
+    environment variables read once per process, so they run in a child process"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, 'tests')\n"
+        "import cm_b200 as cm\n"
+        "from scenario import Cfg, assert_blocks_match, run_checker, run_cuda, slice_steps\n"
+        "for dtype, m in [(cm.F64, 2048), (cm.F32, 1000), (cm.F64, 20000)]:\n"
+        "    cfg = Cfg(dtype, m, 512, 1, 1, 64, 64, m)\n"
+        "    steps = slice_steps(cfg, np.random.default_rng(4), 12, min(m, 600) // 4 * 4, 100, commit_every=6)\n"
+        "    got = run_cuda(cfg, steps, apply_kernel=2)\n"
+        "    assert got['stats'][0]['tile_launches'] > 0\n"
+        "    assert_blocks_match(cfg, got, run_checker(cfg, steps))\n"
+        "print('VARIANT_OK')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0 and "VARIANT_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
