@@ -616,30 +616,53 @@ __device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geo
   return (int)lo - 1;
 }
 
-// fetch element `tid` of the BLK items starting at staged index j0 (plain items: stride 1)
+// fetch element `tid` of the BLK items starting at `it` (plain items: stride 1). The loaded
+// registers are NOT touched here — not even to subtract the tile's first row — so the warp leaves
+// this phase with its loads still in flight and meets them again only in tile_add_block, after the
+// previous block's adds; `okmask` (bit i: thread has an element in item i) depends on shared memory only.
 template <typename T, bool kMulti, int BLK>
 __device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int r0, int h, int (&row)[BLK],
-                                                T (&val)[BLK]) {
+                                                T (&val)[BLK], unsigned &okmask) {
+  okmask = 0;
 #pragma unroll
   for (int i = 0; i < BLK; ++i) {
     const TileItem<T> t = it[i];
     const bool ok = tid < t.n;
     const int aa = ok ? tid : 0;  // idle threads re-read element 0 (always valid memory)
-    const int rr = __ldg(t.rows + aa) - r0;
-    row[i] = (ok && (unsigned)rr < (unsigned)h) ? rr : -1;
+    okmask |= (ok ? 1u : 0u) << i;
+    row[i] = __ldg(t.rows + aa);
     if (!kMulti) val[i] = __ldg(t.v + aa);
   }
   if (kMulti) {  // taller than one tile: fetch the value only if this tile owns the row
 #pragma unroll
-    for (int i = 0; i < BLK; ++i) val[i] = __ldg(it[i].v + (row[i] >= 0 ? tid : 0));
+    for (int i = 0; i < BLK; ++i) {
+      const bool mine = ((okmask >> i) & 1u) && (unsigned)(row[i] - r0) < (unsigned)h;
+      val[i] = __ldg(it[i].v + (mine ? tid : 0));
+    }
+  }
+}
+
+// L2 prefetch of the value lines of the BLK items starting at `it` (item i: threads 16*i .. 16*i+15,
+// one 128-byte line each): issued kTilePrefetch blocks ahead, so that the register loads that
+// follow later find their data in L2 instead of waiting a full DRAM round trip behind a barrier
+__constant__ int c_tile_prefetch = 2;  // blocks ahead (CM_B200_TILE_PREFETCH)
+template <typename T, int BLK>
+__device__ __forceinline__ void tile_prefetch_block(const TileItem<T> *it, int tid) {
+  const int i = tid >> 4, line = tid & 15;
+  if (i < BLK) {
+    const TileItem<T> t = it[i];
+    if (line * 128 < t.n * (int)sizeof(T))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(t.v) + line * 128));
   }
 }
 
 template <typename T, int BLK>
-__device__ __forceinline__ void tile_add_block(T *acc, const int (&row)[BLK], const T (&val)[BLK]) {
+__device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int (&row)[BLK], const T (&val)[BLK],
+                                               unsigned okmask) {
 #pragma unroll
   for (int i = 0; i < BLK; ++i) {
-    if (row[i] >= 0) acc[row[i]] += val[i];
+    const int rr = row[i] - r0;
+    if (((okmask >> i) & 1u) && (unsigned)rr < (unsigned)h) acc[rr] += val[i];
     __syncthreads();  // items strictly in order
   }
 }
@@ -687,14 +710,20 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         // is added; one barrier per item keeps the items in order
         int rowA[BLK], rowB[BLK];
         T valA[BLK], valB[BLK];
+        unsigned okA = 0, okB = 0;
         const int nblk = (cnt + BLK - 1) / BLK;  // staged padding covers up to kRecChunk
-        tile_load_block<T, kMulti, BLK>(sm.item, tid, r0, h, rowA, valA);
+        const int kTilePrefetch = c_tile_prefetch;
+        if (!kMulti)
+          for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm.item + b * BLK, tid);
+        tile_load_block<T, kMulti, BLK>(sm.item, tid, r0, h, rowA, valA, okA);
         for (int b = 0; b < nblk; b += 2) {
-          if (b + 1 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 1) * BLK, tid, r0, h, rowB, valB);
-          tile_add_block<T, BLK>(sm.acc, rowA, valA);
+          if (!kMulti && b + 1 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 1 + kTilePrefetch) * BLK, tid);
+          if (b + 1 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 1) * BLK, tid, r0, h, rowB, valB, okB);
+          tile_add_block<T, BLK>(sm.acc, r0, h, rowA, valA, okA);
           if (b + 1 < nblk) {
-            if (b + 2 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 2) * BLK, tid, r0, h, rowA, valA);
-            tile_add_block<T, BLK>(sm.acc, rowB, valB);
+            if (!kMulti && b + 2 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 2 + kTilePrefetch) * BLK, tid);
+            if (b + 2 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 2) * BLK, tid, r0, h, rowA, valA, okA);
+            tile_add_block<T, BLK>(sm.acc, r0, h, rowB, valB, okB);
           }
         }
       } else {
@@ -958,6 +987,10 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
   const size_t smem = sizeof(TileSmem<T>);
   static int resident = 0;
   if (resident == 0) {
+    if (getenv("CM_B200_TILE_PREFETCH")) {
+      const int pf = atoi(getenv("CM_B200_TILE_PREFETCH"));
+      cudaMemcpyToSymbol(c_tile_prefetch, &pf, sizeof(int));
+    }
     cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
   }
@@ -987,6 +1020,8 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   if (ntiles == 1) {
     if (variant == 1)
       launch_tile_variant<T, false, 12, 2>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    else if (variant == 2)
+      launch_tile_variant<T, false, 8, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
     else
       launch_tile_variant<T, false, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
   } else {
