@@ -173,6 +173,11 @@ struct MirrorArena {
     b.used += bytes;
     return CM_OK;
   }
+  size_t used() const {
+    size_t u = 0;
+    for (auto &b : blocks) u += b.used;
+    return u;
+  }
   int upload(cudaStream_t s, long *bytes_moved) {
     for (auto &b : blocks)
       if (b.used) {
@@ -532,9 +537,18 @@ int apply_coo_local(cm_matrix *M, const CooBin &bin) {
 }
 
 // ---- single-rank flush: map -> (sort) -> scatter-add straight from the staged payloads ----
-int flush_direct(cm_matrix *M) {
+// sync = false (threshold flushes of device-resident updates only): the kernels are left running
+// on the stream while the host stages the next batch; nothing host-side is reused by them
+int flush_direct(cm_matrix *M, bool sync = true) {
   const int nupd = (int)M->descs.size();
-  if (nupd == 0 && M->coo_total == 0) return CM_OK;
+  if (nupd == 0 && M->coo_total == 0) {
+    if (sync) {
+      CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+      resolve_timers(M);
+    }
+    return CM_OK;
+  }
+  if (M->payload_arena.used() || M->index_arena.used() || M->coo_total) sync = true;
   if (nupd) {
     CM_TRY(upload_staged(M));
     const long nitems = M->staged_items;
@@ -557,9 +571,11 @@ int flush_direct(cm_matrix *M) {
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
-  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-  CM_CUDA_TRY(cudaGetLastError());
-  resolve_timers(M);
+  if (sync) {
+    CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+    CM_CUDA_TRY(cudaGetLastError());
+    resolve_timers(M);
+  }
   M->stats.flushes += 1;
   M->mirror_valid = false;
   clear_staged(M);
@@ -1101,7 +1117,7 @@ int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, in
 
 // reference flush(thresh) trigger, :346 / :614: strict '>' on the number of staged elements
 int maybe_flush(cm_matrix *M) {
-  if (M->P == 1 && !M->keep_wire && M->staged_elems + M->coo_total > M->flush_threshold) return flush_direct(M);
+  if (M->P == 1 && !M->keep_wire && M->staged_elems + M->coo_total > M->flush_threshold) return flush_direct(M, false);
   return CM_OK;
 }
 
