@@ -347,6 +347,8 @@ namespace {
 
 int roc_ok(long v) { return v > 0; }
 
+int flush_direct(cm_matrix *M, bool sync);
+
 cudaEvent_t get_event(cm_matrix *M) {
   if (!M->event_pool.empty()) {
     cudaEvent_t e = M->event_pool.back();
@@ -1090,7 +1092,8 @@ int check_dims(long m_u, long n_u) {
 int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, int trans, const long *d_ix,
                const long *d_jx, int mask) {
   if (m_u == 0 || n_u == 0) return CM_OK;
-  if ((long)M->descs.size() + 1 >= (1L << kItemSegBits)) CM_TRY(M->P == 1 ? flush_direct(M) : fail(CM_ERR_INVALID, "too many staged updates; commit more often"));
+  if ((long)M->descs.size() + 1 >= (1L << kItemSegBits))
+    return fail(CM_ERR_INVALID, "more than %ld updates staged; flush or commit more often", (1L << kItemSegBits) - 1);
   UpdDesc d;
   d.data = d_data;
   d.ix = d_ix;

@@ -358,3 +358,55 @@ def test_opt_in_tile_kernel_variants(env):
     p = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
                        timeout=600)
     assert p.returncode == 0 and "VARIANT_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
+
+
+def test_empty_ragged_and_lopsided_inputs():
+    """zero-sized updates are no-ops, ranks may stage nothing at all, every element of an update may
+    belong to a single owner (all other owners receive empty segments), commits may be empty"""
+    cfg = Cfg(cm.F64, 512, 512, 2, 2, 64, 64, 256)
+    rng = np.random.default_rng(91)
+    empty = np.zeros(0, dtype=np.int64)
+    steps = [("commit",)]  # nothing staged anywhere
+    # rank 0: rows and columns all inside blocks owned by grid position (1,1) = rank 3
+    ix = np.concatenate([np.arange(64, 128), np.arange(192, 230)]).astype(np.int64)
+    jx = np.concatenate([np.arange(64, 100), np.arange(448, 512)]).astype(np.int64)
+    steps.append(("slice", 0, rand_payload(rng, cfg.dtype, (len(jx), len(ix))), len(ix), len(jx), len(ix), False, ix, jx))
+    # rank 1: zero rows / zero columns
+    steps.append(("slice", 1, np.zeros(0), 0, 5, 1, False, empty, np.arange(5, dtype=np.int64)))
+    steps.append(("slice", 1, np.zeros(0), 7, 0, 7, False, np.arange(7, dtype=np.int64), empty))
+    # rank 2 stages nothing; rank 3 a ragged pair of updates (1 x 300 and 300 x 1)
+    one = np.array([511], dtype=np.int64)
+    many = sorted_unique(rng, 512, 300)
+    steps.append(("slice", 3, rand_payload(rng, cfg.dtype, (300, 1)), 1, 300, 1, False, one, many))
+    steps.append(("slice", 3, rand_payload(rng, cfg.dtype, (1, 300)), 300, 1, 300, False, many, one))
+    steps += [("commit",), ("commit",)]
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
+    got = run_cuda(cfg, steps, wire=True)
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+    assert len(got["wire"][(0, 3)][0]) == len(ix) * len(jx) and len(got["wire"][(0, 0)][0]) == 0
+
+
+def test_contract_violations_fail_loudly():
+    """what the reference asserts on (or leaves undefined) is an error code here, never a silent fallback"""
+    cm.init(0, 1, 0)
+    try:
+        M = cm.Matrix(cm.F64, 256, 256, 1, 1, 64, 64, 256)
+        d = np.zeros((4, 4))
+        ix = np.arange(4, dtype=np.int64)
+        with pytest.raises(cm.CmError):
+            M.update(d, ix, ix, m_u=-1, n_u=4)
+        with pytest.raises(cm.CmError):
+            M.update(d, ix, ix, m_u=4, n_u=4, ld=2)  # leading dimension smaller than the rows stored
+        with pytest.raises(cm.CmError):
+            M.update_device(0, 4, 4, 4, False, 0, 0)  # null device pointers
+        with pytest.raises(cm.CmError):
+            M.set_apply_kernel(7)
+        with pytest.raises(cm.CmError):
+            M.set_exchange_mode(9)
+        M.update(d + 1.0, ix, ix)  # the matrix is still usable afterwards
+        M.commit()
+        assert M.local().sum() == 16.0
+        M.destroy()
+    finally:
+        cm.finalize()
