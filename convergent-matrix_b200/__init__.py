@@ -71,6 +71,8 @@ SYMBOLS = {
     "cm_local_data_host": (_i, [_vp, C.POINTER(_vp)]),
     "cm_local_data_copy": (_i, [_vp, _vp]),
     "cm_get": (_i, [_vp, _l, _l, _vp]),
+    "cm_save": (_i, [_vp, C.c_char_p]),
+    "cm_load": (_i, [_vp, C.c_char_p]),
     "cm_m": (_l, [_vp]),
     "cm_n": (_l, [_vp]),
     "cm_m_local": (_l, [_vp]),
@@ -257,6 +259,12 @@ class Matrix:
         v = np.zeros(1, dtype=self.np_dtype)
         _check(self.L.cm_get(self.h, i, j, _np_ptr(v)))
         return v[0]
+
+    def save(self, fname):
+        _check(self.L.cm_save(self.h, fname.encode()))
+
+    def load(self, fname):
+        _check(self.L.cm_load(self.h, fname.encode()))
 
     # accessors -----------------------------------------------------------------------
     m = property(lambda s: s.L.cm_m(s.h))

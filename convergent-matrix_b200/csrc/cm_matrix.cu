@@ -9,9 +9,13 @@
 //   commit() (:723-742)                commit(): map -> scan -> pack -> counts all-gather ->
 //                                      all-to-all-v -> build -> sort -> scatter-add -> barrier
 //   Bin<T> for elemental updates       host COO bins per owner (:192-208, :623-629)
+#include <errno.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <vector>
@@ -1579,6 +1583,92 @@ int cm_local_data_host(cm_matrix *M, const void **out) {
   }
   *out = M->h_mirror;
   return CM_OK;
+}
+
+// ---- save() / load(), reference :788-873 / :888-967 ------------------------------------------------
+// Same file as the reference's MPI-IO darray view produces: the dense GLOBAL matrix, column-major
+// (element (i,j) at byte (i + j*M) * sizeof(T)), native endianness, no header. No MPI: every rank
+// writes / reads the runs of MB consecutive global rows it owns with pwrite / pread. As in the
+// reference there is no implicit commit (:778-779) and both calls are collective.
+static int for_each_owned_run(cm_matrix *M, int fd, unsigned char *host, bool write) {
+  const Geom &g = M->g;
+  const size_t esz = M->esz;
+  for (long lj = 0; lj < M->n_local; ++lj) {
+    const long gj = global_index(lj, g.nb, g.npcol, g.mypcol);
+    if (gj >= g.n) continue;
+    for (long li = 0; li < M->m_local; li += g.mb) {
+      const long gi = global_index(li, g.mb, g.nprow, g.myprow);
+      if (gi >= g.m) continue;
+      const long len = std::min(std::min(g.mb, M->m_local - li), g.m - gi);
+      unsigned char *p = host + ((size_t)lj * g.lld + li) * esz;
+      const off_t off = (off_t)(((size_t)gj * g.m + gi) * esz);
+      size_t done = 0;
+      while (done < (size_t)len * esz) {
+        const ssize_t k = write ? pwrite(fd, p + done, (size_t)len * esz - done, off + (off_t)done)
+                                : pread(fd, p + done, (size_t)len * esz - done, off + (off_t)done);
+        if (k <= 0) return fail(CM_ERR_STATE, "%s failed at offset %lld: %s", write ? "pwrite" : "pread",
+                                (long long)off, k == 0 ? "short file" : strerror(errno));
+        done += (size_t)k;
+      }
+    }
+  }
+  return CM_OK;
+}
+
+int cm_save(cm_matrix *M, const char *fname) {
+  if (!M || !fname) return fail(CM_ERR_INVALID, "null argument");
+  Transport *tp = M->ctx->tp;
+  CM_TRY(tp->barrier(M->stream));  // :798
+  std::vector<unsigned char> host(M->local_elems * M->esz);
+  CM_TRY(cm_local_data_copy(M, host.data()));
+  if (M->me == 0) {  // one rank creates the file at its full size
+    const int fd0 = open(fname, O_CREAT | O_WRONLY | O_TRUNC, 0644);
+    if (fd0 < 0 || ftruncate(fd0, (off_t)((size_t)M->g.m * M->g.n * M->esz)) != 0) {
+      const int e = errno;
+      if (fd0 >= 0) close(fd0);
+      tp->barrier(M->stream);
+      tp->barrier(M->stream);
+      return fail(CM_ERR_STATE, "cannot create %s: %s", fname, strerror(e));
+    }
+    close(fd0);
+  }
+  CM_TRY(tp->barrier(M->stream));
+  int rc = CM_OK;
+  const int fd = open(fname, O_WRONLY);
+  if (fd < 0)
+    rc = fail(CM_ERR_STATE, "cannot open %s: %s", fname, strerror(errno));
+  else {
+    rc = for_each_owned_run(M, fd, host.data(), true);
+    if (fsync(fd) != 0 && rc == CM_OK) rc = fail(CM_ERR_STATE, "fsync(%s): %s", fname, strerror(errno));
+    close(fd);
+  }
+  const int rcb = tp->barrier(M->stream);  // :869
+  return rc != CM_OK ? rc : rcb;
+}
+
+int cm_load(cm_matrix *M, const char *fname) {
+  if (!M || !fname) return fail(CM_ERR_INVALID, "null argument");
+  Transport *tp = M->ctx->tp;
+  CM_TRY(tp->barrier(M->stream));  // :898
+  std::vector<unsigned char> host(M->local_elems * M->esz, 0);  // padding rows stay zero
+  int rc = CM_OK;
+  const int fd = open(fname, O_RDONLY);
+  if (fd < 0)
+    rc = fail(CM_ERR_STATE, "cannot open %s: %s", fname, strerror(errno));
+  else {
+    rc = for_each_owned_run(M, fd, host.data(), false);
+    close(fd);
+  }
+  if (rc == CM_OK) {
+    // replaces the current contents of the local block (:879)
+    if (cudaMemcpyAsync(M->d_local, host.data(), host.size(), cudaMemcpyHostToDevice, M->stream) != cudaSuccess ||
+        cudaStreamSynchronize(M->stream) != cudaSuccess)
+      rc = fail(CM_ERR_CUDA, "cm_load: %s", cudaGetErrorString(cudaGetLastError()));
+    M->stats.h2d_bytes += (long)host.size();
+    M->mirror_valid = false;
+  }
+  const int rcb = tp->barrier(M->stream);  // :963
+  return rc != CM_OK ? rc : rcb;
 }
 
 int cm_get(cm_matrix *M, long i, long j, void *out) {

@@ -1,7 +1,8 @@
 // cpp_tests/cm_test.cpp — the reference's test scenarios (swfrench/convergent-matrix
 // test/cm_test.cpp) re-run against include/convergent_matrix.hpp over libcm_b200.so:
 //   randomElementUpdates (:44-101), randomElementUpdatesSymmetricFill (:103-158),
-//   randomSliceUpdates (:160-218), randomSliceUpdatesSymmetricFill (:220-282)
+//   randomSliceUpdates (:160-218), randomSliceUpdatesSymmetricFill (:220-282),
+//   randomElementUpdatesMPIIO (:286-349, here save()/load() without MPI)
 // on the reference's geometry: 2 x 2 grid, MB = NB = 64, LLD = 1024, 2000 x 1000 / 2000 x 2000,
 // T in {int, float, double} (the reference instantiates int and float; double is BASELINE.json's).
 //
@@ -20,6 +21,8 @@
 #include <cstdlib>
 #include <numeric>
 #include <random>
+#include <string>
+#include <type_traits>
 #include <vector>
 
 #include "convergent_matrix.hpp"
@@ -202,6 +205,37 @@ bool randomSliceUpdatesSymmetricFill() {
   return verify<T>(dist, want, scale, m, "randomSliceUpdatesSymmetricFill", g_epochs);
 }
 
+// test/cm_test.cpp:286-349 (randomElementUpdatesMPIIO) — save, load into a second instance, re-verify
+template <typename T>
+bool randomElementUpdatesSaveLoad() {
+  const long m = 2000, n = 1000;
+  const int nupdate = 10000;
+  cm::ConvergentMatrix<T, NPROW, NPCOL, MB, NB, LLD> dist1(m, n);
+  std::vector<T> want(m * n, T(0)), scale(m * n, T(0));
+  for (int r = 0; r < cm::rank_n(); ++r) {
+    std::mt19937 gen(kSeed + 23 * r);
+    for (int k = 0; k < nupdate; ++k) {
+      const long i = gen() % m, j = gen() % n;
+      const T v = payload<T>(gen);
+      if (r == cm::rank_me()) dist1.update(v, i, j);
+      want[i + m * j] += v;
+      scale[i + m * j] += magnitude(v);
+    }
+  }
+  dist1.commit();
+  if (!verify<T>(dist1, want, scale, m, "randomElementUpdatesSaveLoad (built)", 0)) return false;
+  const char *dir = std::getenv("CM_TEST_DIR");
+  std::string path = std::string(dir ? dir : "/tmp") + "/cm_b200_dist_mat1_" + std::to_string((int)sizeof(T)) +
+                     (std::is_integral<T>::value ? "i" : "f");
+  dist1.save(path.c_str());
+  cm::ConvergentMatrix<T, NPROW, NPCOL, MB, NB, LLD> dist2(m, n);
+  dist2.load(path.c_str());
+  const bool ok = verify<T>(dist2, want, scale, m, "randomElementUpdatesSaveLoad (loaded)", 0);
+  cm::barrier();
+  if (cm::rank_me() == 0) std::remove(path.c_str());
+  return ok;
+}
+
 template <typename T>
 bool runAllTests(const char *tname) {
   bool ok = true;
@@ -209,6 +243,7 @@ bool runAllTests(const char *tname) {
   ok = ok && randomElementUpdatesSymmetricFill<T>();
   ok = ok && randomSliceUpdates<T>();
   ok = ok && randomSliceUpdatesSymmetricFill<T>();
+  ok = ok && randomElementUpdatesSaveLoad<T>();
   if (cm::rank_me() == 0) std::fprintf(stderr, "cm_test<%s>: %s\n", tname, ok ? "ok" : "FAILED");
   return ok;
 }

@@ -151,6 +151,14 @@ int cm_local_data_copy(cm_matrix *M, void *dst_host);
  * dist_object::fetch + rget). out points to one element of type T. */
 int cm_get(cm_matrix *M, long i, long j, void *out);
 
+/* save(fname) / load(fname), :788-873 / :888-967 — COLLECTIVE. The file is what the reference's
+ * MPI-IO darray view writes: the dense global matrix, column-major, native endianness, no header
+ * (element (i,j) at byte (i + j*M)*sizeof(T)). No MPI is involved: every rank pwrites / preads the
+ * runs of rows it owns; the path must be visible to all ranks. As in the reference there is no
+ * implicit commit before save (:778-779), and load replaces the local block's contents (:879). */
+int cm_save(cm_matrix *M, const char *fname);
+int cm_load(cm_matrix *M, const char *fname);
+
 /* accessors, :550-576 */
 long cm_m(const cm_matrix *M);
 long cm_n(const cm_matrix *M);

@@ -11,14 +11,16 @@
 //   * update() stages the slice in HBM (values + indices are copied before it returns, as at
 //     reference :611); owner mapping, per-owner packing and the scatter-add run in CUDA
 //     kernels; there is no progress engine, so progress_interval() is stored but unused.
-//   * With several ranks the exchange happens inside commit() (grouped ncclSend/ncclRecv);
+//   * With several ranks the exchange happens inside commit() (the pack kernel stores into the
+//     owners' arenas over NVLink, or a grouped ncclSend/ncclRecv all-to-all-v);
 //     bin_flush_threshold() bounds the elements staged per local flush on one rank.
 //   * Process-grid coordinates are row-major (pgrid_row() = rank / NPCOL), which is what the
 //     reference's owner formula implies; its ctor's rank / NPROW (:409) is a defect for
 //     NPROW != NPCOL.
 //   * get_local_data() returns a HOST mirror of the HBM-resident block (refreshed lazily);
 //     get_local_data_device() is the PBLAS-layout block in HBM itself.
-// Not provided (out of scope of the hot path): MPI-IO save()/load() (:772-969).
+//   * save()/load() write / read the reference's on-disk format (:772-969) with pwrite/pread
+//     instead of MPI-IO; they are always available (no ENABLE_MPIIO_SUPPORT switch).
 #pragma once
 
 #include <cstdio>
@@ -184,6 +186,11 @@ class ConvergentMatrix {
       }
     return true;
   }
+
+  // dense column-major global matrix on disk, the file format of the reference's MPI-IO save/load
+  // (:788-873, :888-967); collective; commit() first, as in the reference. No MPI needed.
+  void save(const char *fname) { internal::check(cm_save(h_, fname), "save"); }
+  void load(const char *fname) { internal::check(cm_load(h_, fname), "load"); }
 
   // PBLAS array descriptor {1, ictxt, M, N, MB, NB, 0, 0, LLD} of the local block
   void descinit(int ictxt, int desc[9]) const { internal::check(cm_descinit(h_, ictxt, desc), "descinit"); }

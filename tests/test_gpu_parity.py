@@ -410,3 +410,55 @@ def test_contract_violations_fail_loudly():
         M.destroy()
     finally:
         cm.finalize()
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_save_load_reference_file_format(P, tmp_path):
+    """randomElementUpdatesMPIIO (test/cm_test.cpp:286-349) without MPI: save() writes the dense global
+    matrix column-major with no header (what the reference's MPI darray view writes), load() into a
+    second instance reproduces every local block"""
+    cfg = Cfg(cm.F64, 2000, 1000, 2, 2, 64, 64, 1024) if P == 4 else Cfg(cm.F64, 2000, 1000, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(95)
+    steps = slice_steps(cfg, rng, 2, 300, 200)
+    for r in range(cfg.P):
+        steps.insert(-1, ("elems", r, rand_payload(rng, cfg.dtype, 2000), rng.integers(0, cfg.m, 2000), rng.integers(0, cfg.n, 2000)))
+    want = run_checker(cfg, steps)
+    dense = np.zeros((cfg.n, cfg.m))  # dense[j, i] = column-major global matrix
+    for r in range(cfg.P):
+        blk = want["local"][r].reshape(-1, cfg.lld)
+        gi = np.array([(l // 64) * 64 * cfg.nprow + (r // cfg.npcol) * 64 + l % 64 for l in range(want["m_local"][r])])
+        gj = np.array([(l // 64) * 64 * cfg.npcol + (r % cfg.npcol) * 64 + l % 64 for l in range(want["n_local"][r])])
+        dense[np.ix_(gj, gi)] = blk[:len(gj), :len(gi)]
+    path = str(tmp_path / "dist_mat1")
+    world = None
+    if P == 1:
+        cm.init(0, 1, 0)
+        run, on = (lambda fn: [fn(0)]), (lambda r, fn: fn(r))
+    else:
+        world = cm.LoopbackWorld(P, 0)
+        run, on = world.run, world.on
+    try:
+        mats = run(lambda r: cm.Matrix(*cfg.args()))
+        for st in steps:
+            if st[0] == "slice":
+                on(st[1], lambda rr: mats[rr].update(st[2], st[7], st[8], st[3], st[4], st[5], st[6]))
+            elif st[0] == "elems":
+                on(st[1], lambda rr: mats[rr].update_elems(st[2], st[3], st[4]))
+            else:
+                run(lambda r: mats[r].commit())
+        run(lambda r: mats[r].save(path))
+        on_disk = np.fromfile(path, dtype=np.float64)
+        assert on_disk.size == cfg.m * cfg.n
+        err = np.linalg.norm(on_disk - dense.reshape(-1)) / np.linalg.norm(dense)
+        assert err <= 1e-12
+        mats2 = run(lambda r: cm.Matrix(*cfg.args()))
+        run(lambda r: mats2[r].load(path))
+        a, b = run(lambda r: mats[r].local()), run(lambda r: mats2[r].local())
+        for r in range(cfg.P):
+            assert np.array_equal(a[r], b[r])  # bit-exact round trip, padding rows stay zero
+        run(lambda r: (mats[r].destroy(), mats2[r].destroy()))
+    finally:
+        if world is not None:
+            world.close()
+        else:
+            cm.finalize()
