@@ -442,10 +442,20 @@ void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint3
 // single dependent load instead of item -> Seg -> lists), the start of every destination
 // column's run in the sorted order.
 // ------------------------------------------------------------------------------------
+// col_start (optional, sorted keys only): col_start[c] = first sorted position whose key >= c, for
+// c in [0, ncols]; the thread at the head of a run writes the entries of its column and of the
+// empty columns before it, the last thread the tail.
 __global__ void __launch_bounds__(256) k_build_recs(const Seg *__restrict__ segs, const uint32_t *__restrict__ keys,
                                                     const uint64_t *__restrict__ items, long nitems, int esz,
-                                                    ItemRec *__restrict__ recs) {
+                                                    ItemRec *__restrict__ recs, long ncols, long *__restrict__ col_start) {
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nitems; t += (long)gridDim.x * blockDim.x) {
+    if (col_start) {
+      const long key = keys[t];
+      const long prev = t == 0 ? -1 : (long)keys[t - 1];
+      for (long c = prev + 1; c <= key && c <= ncols; ++c) col_start[c] = t;
+      if (t == nitems - 1)
+        for (long c = key + 1; c <= ncols; ++c) col_start[c] = nitems;
+    }
     const uint64_t it = items[t];
     const long sid = (long)(it >> (kItemColBits + kItemChunkBits));
     const int b = (int)((it >> kItemChunkBits) & ((1u << kItemColBits) - 1u));
@@ -463,19 +473,6 @@ __global__ void __launch_bounds__(256) k_build_recs(const Seg *__restrict__ segs
   }
 }
 
-// col_start[c] = first sorted position whose key >= c, for c in [0, ncols]
-__global__ void __launch_bounds__(256) k_col_starts(const uint32_t *__restrict__ keys, long nitems, long ncols,
-                                                    long *__restrict__ col_start) {
-  for (long c = (long)blockIdx.x * blockDim.x + threadIdx.x; c <= ncols; c += (long)gridDim.x * blockDim.x) {
-    long lo = 0, hi = nitems;
-    while (lo < hi) {
-      const long mid = (lo + hi) >> 1;
-      if (keys[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
-    }
-    col_start[c] = lo;
-  }
-}
-
 int tile_count(int dtype, long m_local) {
   const long tile_rows = 65536 / (long)dtype_size(dtype);
   return (int)((m_local + tile_rows - 1) / tile_rows);
@@ -486,11 +483,8 @@ void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, con
   if (nitems <= 0) return;
   const long cap = (long)kernel_sm_count() * 8;
   long blocks = std::min((nitems + 255) / 256, cap);
-  k_build_recs<<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs);
-  if (d_col_start) {
-    blocks = std::min((n_local + 256) / 256, cap);
-    k_col_starts<<<(unsigned)blocks, 256, 0, s>>>(d_keys, nitems, n_local, d_col_start);
-  }
+  k_build_recs<<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs, n_local,
+                                                d_col_start);
 }
 
 // ------------------------------------------------------------------------------------
