@@ -327,9 +327,9 @@ struct cm_matrix {
   cudaEvent_t ev_chunk[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
   int pipeline = -1;                    // chunk-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
-                                        // forces it in mode 2 too (measured slower there, 2 B200s K1-weak 7.8 vs
-                                        // 6.6 ms per step: the scatter-add and the next chunk's pack kernel compete
-                                        // for the SMs), =0 disables it everywhere
+                                        // forces it in mode 2 too (2 B200s, K1-weak: 6.7 vs 6.3 ms per step as one
+                                        // batch — every chunk's scatter-add sweeps the whole block again), =0
+                                        // disables it everywhere
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
   PinBuf h_counts;
 
@@ -1284,7 +1284,14 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->apply_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    // the scatter-add of chunk k must get SM slots while the pack kernel of chunk k+1 (launched
+    // earlier, thousands of short blocks) is running: give its stream the higher priority, so that
+    // freed slots go to its pending blocks first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&M->apply_stream, cudaStreamNonBlocking, prio_hi);
+  }
   for (int k = 0; k < cm_matrix::kXferStreams && e == cudaSuccess; ++k) {
     e = cudaStreamCreateWithFlags(&M->xfer_stream[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_xfer[k], cudaEventDisableTiming);
