@@ -12,6 +12,7 @@
 //   item     one column chunk of one segment: the unit of work of the scatter-add
 #pragma once
 
+#include <cuda_runtime.h>  // __host__ / __device__ (implicit under nvcc; explicit for host-compiled builds)
 #include <stdint.h>
 
 namespace cmb {

@@ -18,6 +18,15 @@
 
 #include "cm_kernels.h"
 
+// Kernel launches and dynamic shared memory are spelled through two macros so that the very same
+// kernel sources can also be compiled by the host compiler against tests/emu/ (a test double of the
+// CUDA runtime that runs a block's threads as fibers; it backs the CPU-side kernel-logic tests and
+// is never part of libcm_b200.so). Under nvcc they are the plain CUDA spellings.
+#ifndef CM_EMU
+#define CM_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#define CM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace cmb {
 
 size_t dtype_size(int dtype) { return dtype == 0 ? 8 : 4; }
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
 
 void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma, cudaStream_t s) {
   if (nupd <= 0) return;
-  k_map_group<<<dim3(nupd, 2), 256, 0, s>>>(d_descs, g, ma);
+  CM_LAUNCH(dim3(nupd, 2), 256, 0, s, k_map_group)(d_descs, g, ma);
 }
 
 // ------------------------------------------------------------------------------------
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom 
 void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
                  const long *d_coo_counts, cudaStream_t s) {
   const int P = (int)(g.nprow * g.npcol);
-  k_scan_dest<<<dim3(P, kMaxChunks), 256, 0, s>>>(nupd, cp, g, ma, sa, d_coo_counts);
+  CM_LAUNCH(dim3(P, kMaxChunks), 256, 0, s, k_scan_dest)(nupd, cp, g, ma, sa, d_coo_counts);
 }
 
 // ------------------------------------------------------------------------------------
@@ -324,9 +333,9 @@ void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int u0, int u1, co
   if (u1 <= u0) return;
   const dim3 grid(u1 - u0, pick_ytiles(u1 - u0, 4096));
   switch (dtype) {
-    case 0: k_pack<double><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
-    case 1: k_pack<float><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
-    default: k_pack<int><<<grid, kPackThreads, 0, s>>>(d_descs, nupd, u0, cp, g, ma, sa); break;
+    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double>)(d_descs, nupd, u0, cp, g, ma, sa); break;
+    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float>)(d_descs, nupd, u0, cp, g, ma, sa); break;
+    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int>)(d_descs, nupd, u0, cp, g, ma, sa); break;
   }
 }
 
@@ -367,7 +376,7 @@ void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_b
                          const MapArenas &ma, Seg *d_segs, uint32_t *d_keys, uint64_t *d_items, cudaStream_t s) {
   if (nupd <= 0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 64));
-  k_build_direct<<<grid, 256, 0, s>>>(d_descs, d_item_base, (int)dtype_size(dtype), ma, d_segs, d_keys, d_items);
+  CM_LAUNCH(grid, 256, 0, s, k_build_direct)(d_descs, d_item_base, (int)dtype_size(dtype), ma, d_segs, d_keys, d_items);
 }
 
 // ------------------------------------------------------------------------------------
@@ -418,7 +427,7 @@ void launch_build_recv(int dtype, const MsgRef *d_msgs, int nmsgs, long max_seg_
   long blocks = (max_seg_per_msg + 7) / 8;  // 8 warps per block, one warp per segment
   const long cap = (long)kernel_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  k_build_recv<<<dim3((unsigned)blocks, nmsgs), 256, 0, s>>>(d_msgs, (int)dtype_size(dtype), d_segs, d_keys, d_items);
+  CM_LAUNCH(dim3((unsigned)blocks, nmsgs), 256, 0, s, k_build_recv)(d_msgs, (int)dtype_size(dtype), d_segs, d_keys, d_items);
 }
 
 // ------------------------------------------------------------------------------------
@@ -483,7 +492,7 @@ void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, con
   if (nitems <= 0) return;
   const long cap = (long)kernel_sm_count() * 8;
   long blocks = std::min((nitems + 255) / 256, cap);
-  k_build_recs<<<(unsigned)blocks, 256, 0, s>>>(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs, n_local,
+  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_build_recs)(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs, n_local,
                                                 d_col_start);
 }
 
@@ -553,7 +562,7 @@ static void launch_apply_red_t(const ItemRec *d_recs, long nitems, T *d_local, c
   // exactly one resident wave: the strided item order is also the time order of the sweep
   static const int resident = resident_blocks(k_apply_red<T>, 256, 0);
   const long blocks = std::min((nitems + 7) / 8, (long)resident);
-  k_apply_red<T><<<(unsigned)blocks, 256, 0, s>>>(d_recs, nitems, d_local, g);
+  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_red<T>)(d_recs, nitems, d_local, g);
 }
 
 void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_local, const Geom &g, cudaStream_t s) {
@@ -645,8 +654,10 @@ __device__ __forceinline__ void tile_prefetch_block(const TileItem<T> *it, int t
   const int i = tid >> 4, line = tid & 15;
   if (i < BLK) {
     const TileItem<T> t = it[i];
+#ifndef CM_EMU
     if (line * 128 < t.n * (int)sizeof(T))
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(t.v) + line * 128));
+#endif
   }
 }
 
@@ -667,7 +678,7 @@ __device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int 
 template <typename T, bool kMulti, int BLK, int CTAS>
 __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
                                                        long ncols, int ntiles, long m_local, T *local, Geom g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CM_DYN_SMEM(smem_raw);
   TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
   constexpr int kTileRows = TileSmem<T>::kTileRows;
   const int tid = threadIdx.x;
@@ -787,6 +798,7 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
 // no register cost. Eligible items are 16-byte aligned with n % 4 == 0 (always true for the
 // payloads of K1-shaped updates); other items fall back to per-thread loads inside the same loop.
 // ------------------------------------------------------------------------------------
+#ifndef CM_EMU  // inline PTX (mbarrier, cp.async.bulk): not part of the host-compiled logic tests
 constexpr int kTmaStages = 12;
 
 template <typename T>
@@ -829,7 +841,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, un
 template <typename T>
 __global__ void __launch_bounds__(256, 2) k_apply_tile_tma(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
                                                            long ncols, long m_local, T *local, Geom g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CM_DYN_SMEM(smem_raw);
   TileSmemTma<T> &sm = *reinterpret_cast<TileSmemTma<T> *>(smem_raw);
   const int tid = threadIdx.x;
   const int h = (int)m_local;  // one tile covers all local rows (the launcher guarantees it)
@@ -971,9 +983,11 @@ static void launch_tile_tma(const ItemRec *d_recs, const long *d_col_start, long
     resident = resident_blocks(k_apply_tile_tma<T>, 256, smem);
   }
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  k_apply_tile_tma<T><<<(unsigned)std::min({n_local, (long)resident, cap}), 256, smem, s>>>(d_recs, d_col_start, n_local,
+  CM_LAUNCH((unsigned)std::min({n_local, (long)resident, cap}), 256, smem, s, k_apply_tile_tma<T>)(d_recs, d_col_start, n_local,
                                                                                        m_local, d_local, g);
 }
+
+#endif  // CM_EMU
 
 template <typename T, bool kMulti, int BLK, int CTAS>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
@@ -992,7 +1006,7 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
   // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
   // the next chunk in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  k_apply_tile<T, kMulti, BLK, CTAS><<<(unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s>>>(
+  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS>)(
       d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
 }
 
@@ -1005,10 +1019,14 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   // 0.97 vs 0.61 ms per 131 M elements: two 1-2 KiB bulk copies per item keep the SM's TMA unit
   // busy ~550 cycles per item, more than the whole register path costs.
   static const int tma_mode = getenv("CM_B200_TILE_TMA") ? atoi(getenv("CM_B200_TILE_TMA")) : 0;  // 0 never, 1 hint, 2 always
+#ifndef CM_EMU
   if (ntiles == 1 && (tma_mode == 2 || (tma_mode == 1 && tma_hint))) {
     launch_tile_tma<T>(d_recs, d_col_start, n_local, m_local, d_local, g, max_blocks_per_sm, s);
     return;
   }
+#else
+  (void)tma_mode;
+#endif
   // variant 0 (default): 6-item sets, 3 blocks per SM; variant 1: 12-item sets, 2 blocks per SM
   static const int variant = getenv("CM_B200_TILE_VARIANT") ? atoi(getenv("CM_B200_TILE_VARIANT")) : 0;
   if (ntiles == 1) {
@@ -1053,15 +1071,15 @@ void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n,
   if (blocks > cap) blocks = cap;
   switch (dtype) {
     case 0:
-      k_apply_coo<double><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const double *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo<double>)(d_inds, static_cast<const double *>(d_vals), n,
                                                           static_cast<double *>(d_local));
       break;
     case 1:
-      k_apply_coo<float><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const float *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo<float>)(d_inds, static_cast<const float *>(d_vals), n,
                                                          static_cast<float *>(d_local));
       break;
     default:
-      k_apply_coo<int><<<(unsigned)blocks, 256, 0, s>>>(d_inds, static_cast<const int *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo<int>)(d_inds, static_cast<const int *>(d_vals), n,
                                                        static_cast<int *>(d_local));
       break;
   }
@@ -1111,20 +1129,20 @@ void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, lon
   long blocks = (n + 255) / 256;
   const long cap = (long)kernel_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  k_iota_u32<<<(unsigned)blocks, 256, 0, s>>>(iota, n);
+  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_iota_u32)(iota, n);
   cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, reinterpret_cast<const unsigned long long *>(d_inds), sorted, iota,
                                   perm, n, 0, 64, s);
   switch (dtype) {
     case 0:
-      k_apply_coo_det<double><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const double *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo_det<double>)(sorted, perm, static_cast<const double *>(d_vals), n,
                                                               static_cast<double *>(d_local));
       break;
     case 1:
-      k_apply_coo_det<float><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const float *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo_det<float>)(sorted, perm, static_cast<const float *>(d_vals), n,
                                                              static_cast<float *>(d_local));
       break;
     default:
-      k_apply_coo_det<int><<<(unsigned)blocks, 256, 0, s>>>(sorted, perm, static_cast<const int *>(d_vals), n,
+      CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_coo_det<int>)(sorted, perm, static_cast<const int *>(d_vals), n,
                                                            static_cast<int *>(d_local));
       break;
   }
@@ -1140,7 +1158,7 @@ void launch_iota_global(long *d_out, long count, long blk, long np, long p, cuda
   if (count <= 0) return;
   long blocks = (count + 255) / 256;
   if (blocks > 1024) blocks = 1024;
-  k_iota_global<<<(unsigned)blocks, 256, 0, s>>>(d_out, count, blk, np, p);
+  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_iota_global)(d_out, count, blk, np, p);
 }
 
 }  // namespace cmb

@@ -1396,6 +1396,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
+    if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
     const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" / "dma" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
     if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;

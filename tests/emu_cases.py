@@ -1,0 +1,95 @@
+"""Extra cases for tests/emu/run_cases.py: the GPU tests that stage device-resident inputs with
+torch (which needs a real GPU) restated with numpy — under the CUDA-runtime test double a "device"
+pointer is a host pointer. They run ONLY against tests/emu/libcm_b200_emu.so."""
+import os
+
+import numpy as np
+
+import cm_b200 as cm
+from scenario import Cfg, assert_blocks_match, rand_payload, run_checker, slice_steps, sorted_unique
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
+def device_api_single_rank():
+    """cm_update_slice_device on one rank (borrowed payloads, no staging copies), threshold flushes"""
+    cfg = Cfg(cm.F64, 2048, 2048, 1, 1, 64, 64, 2048)
+    rng = np.random.default_rng(13)
+    steps = slice_steps(cfg, rng, 20, 256, 256)
+    cm.init(0, 1, 0)
+    try:
+        M = cm.Matrix(*cfg.args())
+        M.set_flush_threshold(300000)
+        keep = []
+        for st in steps:
+            if st[0] == "slice":
+                _, _, data, m_u, n_u, ld, trans, ix, jx = st
+                d, i, j = np.ascontiguousarray(data), np.ascontiguousarray(ix), np.ascontiguousarray(jx)
+                keep.append((d, i, j))
+                M.update_device(_ptr(d), m_u, n_u, ld, trans, _ptr(i), _ptr(j))
+            else:
+                M.commit()
+        got = {"local": [M.local()], "m_local": [M.m_local], "n_local": [M.n_local], "stats": [M.stats()]}
+        M.destroy()
+    finally:
+        cm.finalize()
+    assert got["stats"][0]["flushes"] > 2
+    assert_blocks_match(cfg, got, run_checker(cfg, steps))
+
+
+def _pipelined(mode, env):
+    """a commit large enough to be cut into chunks (scatter-add of chunk k while chunk k+1 is packed):
+    the thresholds are lowered through the environment so that it stays small enough for fibers"""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    cfg = Cfg(cm.F32, 256, 256, 2, 2, 64, 64, 128)
+    world = cm.LoopbackWorld(4, 0)
+    try:
+        mats = world.run(lambda r: cm.Matrix(*cfg.args()))
+        world.run(lambda r: mats[r].set_exchange_mode(mode))
+        rng = np.random.default_rng(3)
+        U, m_u, n_u = 24, 128, 128
+        keep, want = [], np.zeros((cfg.n, cfg.m), dtype=np.float32)
+        for r in range(4):
+            ups = []
+            for u in range(U):
+                ix, jx = sorted_unique(rng, cfg.m, m_u), sorted_unique(rng, cfg.n, n_u)
+                data = rng.integers(-3, 4, size=(n_u, m_u)).astype(np.float32)
+                want[np.ix_(jx, ix)] += data
+                ups.append((data, ix, jx))
+            keep.append(ups)
+
+        def issue(r):
+            for data, ix, jx in keep[r]:
+                mats[r].update_device(_ptr(data), m_u, n_u, m_u, False, _ptr(ix), _ptr(jx))
+            mats[r].commit()
+            return mats[r].local(), mats[r].stats()
+        world.run(lambda r: (mats[r].reset_stats(), mats[r].set_profiling(True)))
+        out = world.run(issue)
+        for r, (blk, st) in enumerate(out):
+            blk = blk.reshape(-1, cfg.lld)
+            pr, pc = r // 2, r % 2
+            gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(128)])
+            gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(128)])
+            assert np.array_equal(blk[:128, :128], want[np.ix_(gj, gi)]), f"rank {r}"
+            assert st["apply_launches"] == 4, st["apply_launches"]  # one scatter-add per chunk
+        world.run(lambda r: mats[r].destroy())
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        world.close()
+
+
+def pipelined_commit_chunks(mode):
+    _pipelined(mode, {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_MIN_ELEMS": "1000"})
+
+
+CASES = [
+    ("device_api_single_rank", [()]),
+    ("pipelined_commit_chunks", [(2,), (3,)]),
+]
