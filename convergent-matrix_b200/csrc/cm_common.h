@@ -90,25 +90,32 @@ struct WireSeg {
 static_assert(sizeof(WireHdr) == 32, "wire header layout");
 static_assert(sizeof(WireSeg) == 40, "wire segment layout");
 
-// A commit's staged updates are cut into kMaxChunks consecutive ranges; every (source, chunk,
-// owner) triple is one message. Large commits are pipelined chunk by chunk (the scatter-add of
-// chunk k overlaps the pack/exchange of chunk k+1); small ones go as one batch of messages.
+// Column panels. A source that stages a large commit cuts every update's columns into up to
+// kMaxChunks panels of `panel_cols` consecutive LOCAL columns of the owner; every (source, panel,
+// owner) triple is one message. The owner's scatter-add of panel k touches only panel k's columns
+// of the local block, so a large commit is pipelined panel by panel (the scatter-add of panel k
+// overlaps the pack / exchange of panel k+1) without sweeping the local block more than once. A
+// small commit has one panel: one message per (source, owner), the reference's XBuff (:128-133).
+// Implementation: panels widen the column-group key of the grouping kernel from the owner column q
+// to gq = panel * NPCOL + q ("virtual owner columns"); the rest of the path sees npanel * NPCOL
+// column groups per update.
 constexpr int kMaxChunks = 4;
-struct ChunkPlan {
-  int ubeg[kMaxChunks + 1];  // chunk k = updates [ubeg[k], ubeg[k+1])
+struct PanelPlan {
+  int npanel;       // 1 .. kMaxChunks, and npanel * NPCOL <= kMaxGridDim
+  long panel_cols;  // local columns per panel (the last panel takes the rest)
 };
-__host__ __device__ inline int chunk_of(const ChunkPlan &cp, int u) {
-  int k = 0;
-  while (k + 1 < kMaxChunks && u >= cp.ubeg[k + 1]) ++k;
-  return k;
+__host__ __device__ inline int panel_of(const PanelPlan &pp, long lcol) {
+  if (pp.npanel <= 1) return 0;
+  const long k = lcol / pp.panel_cols;
+  return (int)(k < pp.npanel ? k : pp.npanel - 1);
 }
 
-// counts exchanged before the data exchange, per (source, chunk, owner) triple
+// counts exchanged before the data exchange, per (source, panel, owner) triple
 struct MsgCounts {
   long nvals;   // value SLOTS of the message (segments are padded, see seg_col_stride)
   long nidx, nseg, nitems;
   long nelems;  // update elements carried (what the scatter-add will add)
-  long ncoo;    // elemental updates (COO lane) from this source to this owner; chunk 0 only
+  long ncoo;    // elemental updates (COO lane) from this source to this owner; panel 0 only
 };
 
 // Layout of one segment's values inside a message: column-major nr x nc with column stride

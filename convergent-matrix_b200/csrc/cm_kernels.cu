@@ -51,22 +51,24 @@ __device__ __forceinline__ uint64_t encode_item(long seg, int col, int chunk) {
 // (1) owner map + stable grouping.  grid (nupd, 2): y = 0 rows (ix), y = 1 columns (jx).
 // For every index: owner coordinate p (:606/:609) and local index l (:607/:610). Output is
 // grouped by p, stable within a group (== the order the reference appends to bin (p,*)).
+// Columns of a commit cut into panels are grouped by gq = panel(l) * NPCOL + p instead (PanelPlan).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ descs, Geom g, MapArenas ma) {
+__global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ descs, Geom g, PanelPlan pp, MapArenas ma) {
   const int u = blockIdx.x;
   const int axis = blockIdx.y;
   const UpdDesc d = descs[u];
   const long *__restrict__ idx = axis == 0 ? d.ix : d.jx;
   const int len = axis == 0 ? d.m : d.n;
   const long blk = axis == 0 ? g.mb : g.nb;
-  const int np = (int)(axis == 0 ? g.nprow : g.npcol);
+  const int npo = (int)(axis == 0 ? g.nprow : g.npcol);      // owners along this axis
+  const int np = axis == 0 ? npo : npo * pp.npanel;           // groups along this axis
   const long base = axis == 0 ? d.rbase : d.cbase;
   int *__restrict__ lout = (axis == 0 ? ma.rl : ma.cl) + base;
   int *__restrict__ pout = (axis == 0 ? ma.rpos : ma.cpos) + base;
   int *__restrict__ off_out = (axis == 0 ? ma.roff : ma.coff) + (long)u * (np + 1);
 
   const int tid = threadIdx.x;
-  if (np == 1) {  // single owner along this axis: identity grouping
+  if (np == 1) {  // single group along this axis: identity grouping
     bool rep = false;
     for (int k = tid; k < len; k += blockDim.x) {
       lout[k] = (int)local_index(idx[k], blk, 1);
@@ -80,6 +82,12 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
     }
     return;
   }
+  const bool panels = axis == 1 && pp.npanel > 1;
+  auto group_of = [&](long gi) {
+    int p = owner_coord(gi, blk, npo);
+    if (panels) p += npo * panel_of(pp, local_index(gi, blk, npo));
+    return p;
+  };
 
   __shared__ int cnt[kMaxGridDim];
   __shared__ int gbase[kMaxGridDim + 1];
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
   for (int k = tid; k < 8 * kMaxGridDim; k += blockDim.x) (&wcnt[0][0])[k] = 0;
   __syncthreads();
   // pass 1: group sizes
-  for (int k = tid; k < len; k += blockDim.x) atomicAdd(&cnt[owner_coord(idx[k], blk, np)], 1);
+  for (int k = tid; k < len; k += blockDim.x) atomicAdd(&cnt[group_of(idx[k])], 1);
   if (axis == 0) {
     bool rep = false;
     for (int k = tid + 1; k < len; k += blockDim.x) rep |= idx[k] <= idx[k - 1];
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
     int p = np;  // sentinel group for lanes past the end
     if (valid) {
       gi = idx[k];
-      p = owner_coord(gi, blk, np);
+      p = group_of(gi);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, p);
     const int r = __popc(peers & ((1u << lane) - 1u));
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
     if (valid) {
       int off = gbase[p] + run[p] + r;
       for (int w = 0; w < warp; ++w) off += wcnt[w][p];
-      lout[off] = (int)local_index(gi, blk, np);
+      lout[off] = (int)local_index(gi, blk, npo);
       pout[off] = k;
     }
     __syncthreads();
@@ -146,9 +154,10 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
   }
 }
 
-void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma, cudaStream_t s) {
+void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const PanelPlan &pp, const MapArenas &ma,
+                      cudaStream_t s) {
   if (nupd <= 0) return;
-  CM_LAUNCH(dim3(nupd, 2), 256, 0, s, k_map_group)(d_descs, g, ma);
+  CM_LAUNCH(dim3(nupd, 2), 256, 0, s, k_map_group)(d_descs, g, pp, ma);
 }
 
 // ------------------------------------------------------------------------------------
@@ -159,23 +168,28 @@ struct Long3 {
   __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e}; }
 };
 
-__global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom g, MapArenas ma, ScanArenas sa,
+__global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom g, MapArenas ma, ScanArenas sa,
                                                    const long *__restrict__ coo_counts) {
   using BlockScan = cub::BlockScan<Long3, 256>;
   __shared__ typename BlockScan::TempStorage tmp;
   const int dst = blockIdx.x;
-  const int chunk = blockIdx.y;
-  const int ub = cp.ubeg[chunk], ue = cp.ubeg[chunk + 1];
+  const int panel = blockIdx.y;
   const int P = gridDim.x;
+  if (panel >= pp.npanel) {  // unused panel slot: an empty message
+    if (threadIdx.x == 0) sa.totals[panel * P + dst] = MsgCounts{0, 0, 0, 0, 0, 0};
+    return;
+  }
   const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
-  const int npr = (int)g.nprow + 1, npc = (int)g.npcol + 1;
+  const int gq = panel * (int)g.npcol + q;  // column group of (panel, owner column)
+  const int npr = (int)g.nprow + 1, npc = (int)g.npcol * pp.npanel + 1;
+  const long obase = ((long)panel * P + dst) * nupd;
   Long3 running{0, 0, 0, 0};
-  for (int c0 = ub; c0 < ue; c0 += 256) {
+  for (int c0 = 0; c0 < nupd; c0 += 256) {
     const int u = c0 + threadIdx.x;
     Long3 v{0, 0, 0, 0};
-    if (u < ue) {
+    if (u < nupd) {
       const int nr = ma.roff[(long)u * npr + p + 1] - ma.roff[(long)u * npr + p];
-      const int nc = ma.coff[(long)u * npc + q + 1] - ma.coff[(long)u * npc + q];
+      const int nc = ma.coff[(long)u * npc + gq + 1] - ma.coff[(long)u * npc + gq];
       const long nv = (long)nr * nc;
       if (nv > 0) {
         v.a = seg_slots(nr, nc);
@@ -186,50 +200,55 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, ChunkPlan cp, Geom 
     }
     Long3 excl, total;
     BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0, 0}, cub::Sum(), total);
-    if (u < ue) {
-      sa.valoff[(long)dst * nupd + u] = running.a + excl.a;
-      sa.idxoff[(long)dst * nupd + u] = running.b + excl.b;
-      sa.itemoff[(long)dst * nupd + u] = running.c + excl.c;
+    if (u < nupd) {
+      sa.valoff[obase + u] = running.a + excl.a;
+      sa.idxoff[obase + u] = running.b + excl.b;
+      sa.itemoff[obase + u] = running.c + excl.c;
     }
     running = running + total;
     __syncthreads();
   }
+  // a message without values ships nothing at all (no segment table either): nseg = 0
   if (threadIdx.x == 0)
-    sa.totals[chunk * P + dst] =
-        MsgCounts{running.a, running.b, (long)(ue - ub), running.c, running.e, chunk == 0 ? coo_counts[dst] : 0};
+    sa.totals[panel * P + dst] = MsgCounts{running.a, running.b, running.a ? (long)nupd : 0, running.c, running.e,
+                                           panel == 0 ? coo_counts[dst] : 0};
 }
 
-void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
+void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
                  const long *d_coo_counts, cudaStream_t s) {
   const int P = (int)(g.nprow * g.npcol);
-  CM_LAUNCH(dim3(P, kMaxChunks), 256, 0, s, k_scan_dest)(nupd, cp, g, ma, sa, d_coo_counts);
+  CM_LAUNCH(dim3(P, kMaxChunks), 256, 0, s, k_scan_dest)(nupd, pp, g, ma, sa, d_coo_counts);
 }
 
 // ------------------------------------------------------------------------------------
-// (3) pack. grid (nupd, ytiles): block (u, y) handles grouped columns y, y+ytiles, ...
-// of update u: for every owner row p it gathers the rows R_p of that column into the
-// (p,q) segment — contiguous, coalesced stores; gathers hit every sector of the source
+// (3) pack. grid (nupd, ytiles): block (u, y) handles the grouped columns y, y+ytiles, ... of the
+// panels [k0, k1) of update u: for every owner row p it gathers the rows R_p of that column into
+// the (panel, p, q) segment — contiguous, coalesced stores; gathers hit every sector of the source
 // column exactly once per block. Block y == 0 also writes the update's wire metadata.
 // ------------------------------------------------------------------------------------
 constexpr int kPackThreads = 384;
+constexpr int kPackMaxDst = 1024;  // (k1 - k0) * P destinations per launch
 
 template <typename T>
-__global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int u0, ChunkPlan cp,
+__global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1, PanelPlan pp,
                                                        Geom g, MapArenas ma, ScanArenas sa) {
-  const int u = u0 + blockIdx.x;
+  const int u = blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
-  const int chunk = chunk_of(cp, u);
-  const int ufirst = cp.ubeg[chunk], nseg = cp.ubeg[chunk + 1] - ufirst;  // my message's segment table
+  const int ncg = npcol * pp.npanel;  // column groups of an update
   __shared__ int roff[kMaxGridDim + 1];
   __shared__ int coff[kMaxGridDim + 1];
   __shared__ int tstart[kMaxGridDim + 1];  // first thread slot of each owner row's rows (16-aligned)
-  __shared__ T *base[1024];                // per owner: where this update's segment starts
+  __shared__ int gdst[kMaxGridDim];        // column group -> (panel - k0) * P + owner column
+  __shared__ T *base[kPackMaxDst];         // per (panel, owner): where this update's segment starts
   const int tid = threadIdx.x;
   if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
-  if (tid <= npcol) coff[tid] = ma.coff[(long)u * (npcol + 1) + tid];
-  for (int dst = tid; dst < P; dst += blockDim.x)
-    base[dst] = static_cast<T *>(sa.dst_vals[chunk * P + dst]) + sa.valoff[(long)dst * nupd + u];
+  if (tid <= ncg) coff[tid] = ma.coff[(long)u * (ncg + 1) + tid];
+  if (tid < ncg) gdst[tid] = (tid / npcol - k0) * P + tid % npcol;
+  for (int i = tid; i < (k1 - k0) * P; i += blockDim.x) {
+    const int k = k0 + i / P, dst = i % P;
+    base[i] = static_cast<T *>(sa.dst_vals[k * P + dst]) + sa.valoff[((long)k * P + dst) * nupd + u];
+  }
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
@@ -244,6 +263,8 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
   const int *__restrict__ rpos = ma.rpos + d.rbase;
   const int *__restrict__ cpos = ma.cpos + d.cbase;
   const long src_rs = d.trans ? d.ld : 1, src_cs = d.trans ? 1 : d.ld;
+  const int cbeg = coff[k0 * npcol], cend = coff[k1 * npcol];  // grouped columns of the panels [k0, k1)
+  const int gy = (int)gridDim.y;
 
   // Thread slot t -> (owner row p, slot a of that owner's segment rows). Slots of one owner row
   // start on a multiple of 16, and a tall segment's columns are 16-slot aligned in the message, so
@@ -257,17 +278,17 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
     const int stride = seg_col_stride(nr);
     const long srow = live ? (long)rpos[roff[p] + a] * src_rs : 0;
     T *const *brow = base + p * npcol;
-    int kc = blockIdx.y;
+    int kc = cbeg + (int)blockIdx.y;
+    int gq = k0 * npcol;  // column group of the current column: only moves forward
     // four columns in flight per thread
-    for (; kc + 3 * (int)gridDim.y < d.n; kc += 4 * gridDim.y) {
+    for (; kc + 3 * gy < cend; kc += 4 * gy) {
       T x[4];
       T *out[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int c = kc + i * gridDim.y;
-        int q = 0;
-        while (c >= coff[q + 1]) ++q;
-        out[i] = brow[q] + (long)(c - coff[q]) * stride + a;
+        const int c = kc + i * gy;
+        while (c >= coff[gq + 1]) ++gq;
+        out[i] = brow[gdst[gq]] + (long)(c - coff[gq]) * stride + a;
         x[i] = live ? data[srow + (long)cpos[c] * src_cs] : T(0);
       }
       if (live) {
@@ -275,46 +296,48 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
         for (int i = 0; i < 4; ++i) *out[i] = x[i];
       }
     }
-    for (; kc < d.n; kc += gridDim.y) {
-      int q = 0;
-      while (kc >= coff[q + 1]) ++q;
-      if (live) brow[q][(long)(kc - coff[q]) * stride + a] = data[srow + (long)cpos[kc] * src_cs];
+    for (; kc < cend; kc += gy) {
+      while (kc >= coff[gq + 1]) ++gq;
+      if (live) brow[gdst[gq]][(long)(kc - coff[gq]) * stride + a] = data[srow + (long)cpos[kc] * src_cs];
     }
   }
 
   if (blockIdx.y == 0) {
     const int *__restrict__ rl = ma.rl + d.rbase;
     const int *__restrict__ cl = ma.cl + d.cbase;
-    for (int dst = 0; dst < P; ++dst) {
-      const int p = dst / npcol, q = dst % npcol;
-      const int nr = roff[p + 1] - roff[p], nc = coff[q + 1] - coff[q];
-      char *mb = sa.dst_meta[chunk * P + dst];
-      if (u == ufirst && tid == 0) {  // message header
-        const MsgCounts c = sa.totals[chunk * P + dst];
-        WireHdr *h = reinterpret_cast<WireHdr *>(mb);
-        h->nseg = c.nseg;
-        h->nvals = c.nvals;
-        h->nidx = c.nidx;
-        h->nitems = c.nitems;
+    for (int k = k0; k < k1; ++k)
+      for (int dst = 0; dst < P; ++dst) {
+        const MsgCounts c = sa.totals[k * P + dst];
+        if (c.nvals == 0) continue;  // empty message: nothing was reserved for it
+        const int p = dst / npcol, q = dst % npcol, gq = k * npcol + q;
+        const int nr = roff[p + 1] - roff[p], nc = coff[gq + 1] - coff[gq];
+        char *mb = sa.dst_meta[k * P + dst];
+        if (u == 0 && tid == 0) {  // message header
+          WireHdr *h = reinterpret_cast<WireHdr *>(mb);
+          h->nseg = c.nseg;
+          h->nvals = c.nvals;
+          h->nidx = c.nidx;
+          h->nitems = c.nitems;
+        }
+        WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
+        const bool empty = (long)nr * nc == 0;
+        const long obase = ((long)k * P + dst) * nupd + u;
+        const long ioff = sa.idxoff[obase];
+        if (tid == 0) {
+          ws->nr = empty ? 0 : nr;
+          ws->nc = empty ? 0 : nc;
+          ws->mask = d.mask;
+          ws->flags = ma.uflags[u];
+          ws->val_off = sa.valoff[obase];
+          ws->idx_off = ioff;
+          ws->item_off = sa.itemoff[obase];
+        }
+        if (!empty) {
+          int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nupd * sizeof(WireSeg)) + ioff;
+          for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
+          for (int cc = tid; cc < nc; cc += blockDim.x) iw[nr + cc] = cl[coff[gq] + cc];
+        }
       }
-      WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + (u - ufirst);
-      const bool empty = (long)nr * nc == 0;
-      const long ioff = sa.idxoff[(long)dst * nupd + u];
-      if (tid == 0) {
-        ws->nr = empty ? 0 : nr;
-        ws->nc = empty ? 0 : nc;
-        ws->mask = d.mask;
-        ws->flags = ma.uflags[u];
-        ws->val_off = sa.valoff[(long)dst * nupd + u];
-        ws->idx_off = ioff;
-        ws->item_off = sa.itemoff[(long)dst * nupd + u];
-      }
-      if (!empty) {
-        int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nseg * sizeof(WireSeg)) + ioff;
-        for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
-        for (int c = tid; c < nc; c += blockDim.x) iw[nr + c] = cl[coff[q] + c];
-      }
-    }
   }
 }
 
@@ -328,14 +351,14 @@ static int pick_ytiles(int nupd, long max_cols) {
   return (int)y;
 }
 
-void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int u0, int u1, const ChunkPlan &cp, const Geom &g,
+void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp, const Geom &g,
                  const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
-  if (u1 <= u0) return;
-  const dim3 grid(u1 - u0, pick_ytiles(u1 - u0, 4096));
+  if (nupd <= 0 || k1 <= k0) return;
+  const dim3 grid(nupd, pick_ytiles(nupd, 4096));
   switch (dtype) {
-    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double>)(d_descs, nupd, u0, cp, g, ma, sa); break;
-    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float>)(d_descs, nupd, u0, cp, g, ma, sa); break;
-    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int>)(d_descs, nupd, u0, cp, g, ma, sa); break;
+    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
   }
 }
 

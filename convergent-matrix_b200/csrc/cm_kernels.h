@@ -24,32 +24,32 @@ struct MapArenas {
   int *roff;  // group starts, (nprow+1) per update
   int *cl;    // grouped local column indices     [sum n_u]
   int *cpos;
-  int *coff;  // (npcol+1) per update
+  int *coff;  // (npanel*npcol+1) per update: column groups gq = panel * npcol + owner column
   int *uflags;  // per update: kSegRowsMayRepeat if ix is not strictly increasing (zeroed by the caller)
 };
 
 // per-(owner, update) exclusive scans produced by k_scan_dest
 struct ScanArenas {
-  long *valoff;    // [P * nupd]
-  long *idxoff;    // [P * nupd]
-  long *itemoff;   // [P * nupd]
-  MsgCounts *totals;  // [kMaxChunks * P], index chunk * P + owner
-  void **dst_vals;    // [kMaxChunks * P] where this rank's message (chunk, owner) starts: values ...
+  long *valoff;    // [npanel * P * nupd], index (panel * P + owner) * nupd + update
+  long *idxoff;    // same
+  long *itemoff;   // same
+  MsgCounts *totals;  // [kMaxChunks * P], index panel * P + owner
+  void **dst_vals;    // [kMaxChunks * P] where this rank's message (panel, owner) starts: values ...
   char **dst_meta;    // ... and metadata. May point into a PEER's receive arena (NVLink stores).
 };
 
 size_t dtype_size(int dtype);
 
 // (1) owner map + stable grouping by owner row / column (warp match + prefix sums)
-void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const MapArenas &ma,
+void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const PanelPlan &pp, const MapArenas &ma,
                       cudaStream_t s);
 // (2) per-owner scans over the staged updates (sizes of every message)
-void launch_scan(int nupd, const ChunkPlan &cp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
+void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
                  const long *d_coo_counts, cudaStream_t s);
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
-// Packs updates [u0, u1) (whole chunks).
-void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int u0, int u1, const ChunkPlan &cp,
+// Packs the column panels [k0, k1) of every staged update.
+void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp,
                  const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,

@@ -228,7 +228,7 @@ struct CooBin {
   std::vector<unsigned char> vals;
 };
 
-// device buffers of one scatter-add batch (one per pipelined chunk)
+// device buffers of one scatter-add batch (one per pipelined panel)
 struct ApplyWork {
   DevBuf msgs, segs, keys0, keys1, items0, items1, sort_tmp, recs, col_start;
   void release() {
@@ -323,14 +323,13 @@ struct cm_matrix {
   DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
   DevBuf d_counts_all, d_dst_ptrs, d_coo_counts;
   ApplyWork work[kMaxChunks];
-  cudaStream_t apply_stream = nullptr;  // scatter-add of chunk k while chunk k+1 is packed / exchanged
+  cudaStream_t apply_stream = nullptr;  // scatter-add of panel k while panel k+1 is packed / exchanged
   cudaEvent_t ev_chunk[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
-  int pipeline = -1;                    // chunk-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
-                                        // forces it in mode 2 too (2 B200s, K1-weak: 6.7 vs 6.3 ms per step as one
-                                        // batch — every chunk's scatter-add sweeps the whole block again), =0
-                                        // disables it everywhere
+  int pipeline = -1;                    // panel-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
+                                        // enables them in mode 2 too, =0 disables them everywhere
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
+  int npanel_cfg = kMaxChunks;          // column panels of a pipelined commit (CM_B200_PANELS)
   PinBuf h_counts;
 
   cm_stats stats{};
@@ -342,7 +341,7 @@ struct cm_matrix {
     int dst;
     std::vector<char> meta, vals;
   };
-  std::vector<DbgMsg> dbg_msgs;  // the messages of the last commit, owner-major, chunk order
+  std::vector<DbgMsg> dbg_msgs;  // the messages of the last commit, owner-major, panel order
   std::vector<CooBin> dbg_coo;
   bool dbg_valid = false;
 };
@@ -432,7 +431,7 @@ void clear_staged(cm_matrix *M) {
 
 int issue_merged_copy(cm_matrix *M);
 
-int upload_staged(cm_matrix *M) {
+int upload_staged(cm_matrix *M, int npanel = 1) {
   const int nupd = (int)M->descs.size();
   CM_TRY(issue_merged_copy(M));
   if (M->copies_pending) {  // host-API payloads travel on their own stream
@@ -445,7 +444,7 @@ int upload_staged(cm_matrix *M) {
   if (nupd)
     CM_CUDA_TRY(cudaMemcpyAsync(M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, cudaMemcpyHostToDevice,
                                 M->stream));
-  const int npr = (int)M->g.nprow + 1, npc = (int)M->g.npcol + 1;
+  const int npr = (int)M->g.nprow + 1, npc = (int)M->g.npcol * npanel + 1;
   CM_TRY(M->d_rl.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
   CM_TRY(M->d_rpos.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
   CM_TRY(M->d_cl.ensure(4 * (size_t)std::max(M->staged_cols, 1L)));
@@ -567,7 +566,7 @@ int flush_direct(cm_matrix *M, bool sync = true) {
     const MapArenas ma = map_arenas(M);
     {
       ScopedTimer t(M, 1, 0);
-      launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
+      launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, PanelPlan{1, 1}, ma, M->stream);
       launch_build_direct(M->dtype, M->d_descs.as<UpdDesc>(), M->d_item_base.as<long>(), nupd, M->g, ma,
                           w.segs.as<Seg>(), w.keys0.as<uint32_t>(), w.items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
@@ -677,6 +676,23 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
   return CM_OK;
 }
 
+// Column panels of this commit (cm_common.h, PanelPlan). Decided by each source on its own from what
+// it has staged; the wire format carries whatever it decides.
+PanelPlan plan_panels(cm_matrix *M) {
+  PanelPlan pp{1, 1};
+  const bool wanted = M->P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1);
+  if (!wanted || M->staged_elems < M->pipeline_min_elems) return pp;
+  long k = std::min<long>(M->npanel_cfg, kMaxChunks);
+  k = std::min<long>(k, kMaxGridDim / M->g.npcol);
+  k = std::min<long>(k, 1024 / M->P);
+  const long ncols_max = cm_numroc(M->g.n, M->g.npcol, 0, M->g.nb);  // owner column 0 holds the most columns
+  k = std::min(k, ncols_max);
+  if (k <= 1) return pp;
+  pp.npanel = (int)k;
+  pp.panel_cols = (ncols_max + k - 1) / k;
+  return pp;
+}
+
 // ---- general commit path (also used for P == 1 when the wire is being captured, so the pack
 // kernels are testable on one rank):
 //   map -> scan -> counts all-gather (the one host sync) -> pack -> [all-to-all-v] -> barrier ->
@@ -691,22 +707,13 @@ int commit_exchange(cm_matrix *M) {
   const size_t esz = M->esz;
   auto cidx = [P, K](int src, int k, int dst) { return ((size_t)src * K + k) * P + dst; };  // counts index
 
-  // -- chunk plan: consecutive update ranges holding about the same number of elements -------
-  ChunkPlan cp;
-  {
-    cp.ubeg[0] = 0;
-    long acc = 0;
-    int k = 1;
-    for (int u = 0; u < nupd && k < K; ++u) {
-      acc += (long)M->descs[u].m * M->descs[u].n;
-      if (acc * K >= M->staged_elems * k) cp.ubeg[k++] = u + 1;
-    }
-    for (; k <= K; ++k) cp.ubeg[k] = nupd;
-  }
+  // -- panel plan (a LOCAL decision of this source; owners cope with any mix): a source that stages
+  // a large commit cuts its updates' columns into panels so that the owners can pipeline it
+  const PanelPlan pp = plan_panels(M);
 
-  // -- source side: owner map + per-(chunk, owner) sizes ---------------------------------------
-  CM_TRY(upload_staged(M));
-  const size_t pu = (size_t)P * std::max(nupd, 1);
+  // -- source side: owner map + per-(panel, owner) sizes ---------------------------------------
+  CM_TRY(upload_staged(M, pp.npanel));
+  const size_t pu = (size_t)pp.npanel * P * std::max(nupd, 1);
   CM_TRY(M->d_valoff.ensure(8 * pu));
   CM_TRY(M->d_idxoff.ensure(8 * pu));
   CM_TRY(M->d_itemoff.ensure(8 * pu));
@@ -731,8 +738,8 @@ int commit_exchange(cm_matrix *M) {
   for (int d = 0; d < P; ++d) my_coo[d] = (long)M->coo[d].inds.size();
   CM_TRY(M->d_coo_counts.ensure(8 * (size_t)P));
   CM_CUDA_TRY(cudaMemcpyAsync(M->d_coo_counts.p, my_coo.data(), 8 * (size_t)P, cudaMemcpyHostToDevice, M->stream));
-  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, ma, M->stream);
-  launch_scan(nupd, cp, M->g, ma, sa, M->d_coo_counts.as<long>(), M->stream);
+  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, pp, ma, M->stream);
+  launch_scan(nupd, pp, M->g, ma, sa, M->d_coo_counts.as<long>(), M->stream);
   M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
   CM_CUDA_TRY(cudaGetLastError());
 
@@ -749,20 +756,23 @@ int commit_exchange(cm_matrix *M) {
   for (int src = 0; src < P; ++src)
     for (int d = 0; d < P; ++d) coo_counts[(size_t)src * P + d] = counts[cidx(src, 0, d)].ncoo;
 
-  // -- pipeline or not: same decision on every rank, taken from the global counts. Every chunk's
-  // scatter-add sweeps the whole local block once, so pipelining pays only when a chunk brings
-  // at least about two updates per matrix element; smaller commits go as one batch.
+  // -- pipeline or not: same decision on every rank, taken from the global counts. Pipelining pays
+  // when the commit is large and most of it arrived cut into panels (panel k > 0 non-empty);
+  // everything else goes as one batch.
   bool pipelined = false;
   if (P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1)) {
-    long total = 0;
+    long total = 0, later = 0;
     for (int src = 0; src < P; ++src)
       for (int k = 0; k < K; ++k)
-        for (int d = 0; d < P; ++d) total += counts[cidx(src, k, d)].nelems;
-    pipelined = total >= 2L * K * M->g.m * M->g.n && total / P >= M->pipeline_min_elems;
+        for (int d = 0; d < P; ++d) {
+          total += counts[cidx(src, k, d)].nelems;
+          if (k > 0) later += counts[cidx(src, k, d)].nelems;
+        }
+    pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total;
   }
 
   // -- layout of every rank's receive arenas (identical computation on every rank):
-  // owner d holds, chunk after chunk, the messages of every source
+  // owner d holds, panel after panel, the messages of every source
   std::vector<long> rbase_v((size_t)P * (K * P + 1), 0), rbase_m((size_t)P * (K * P + 1), 0);
   auto ridx = [P, K](int d, int k, int src) { return (size_t)d * (K * P + 1) + (size_t)k * P + src; };
   std::vector<size_t> need_vals(P), need_meta(P);
@@ -962,9 +972,21 @@ int commit_exchange(cm_matrix *M) {
     M->stats.bytes_received += coo_blob(coo_counts[(size_t)r * P + me]) * (coo_counts[(size_t)r * P + me] ? 1 : 0);
   }
 
+  int Kp = 0;  // panel slots that hold data on any rank (same value everywhere)
+  for (int src = 0; src < P; ++src)
+    for (int k = 0; k < K; ++k)
+      for (int d = 0; d < P; ++d)
+        if (counts[cidx(src, k, d)].nvals) Kp = std::max(Kp, k + 1);
+  auto panel_has_data = [&](int k) {  // does this rank send anything in panel k?
+    if (k >= pp.npanel || nupd == 0) return false;
+    for (int d = 0; d < P; ++d)
+      if (counts[cidx(me, k, d)].nvals) return true;
+    return false;
+  };
+
   if (!pipelined) {
     // one batch: pack everything, (all-to-all-v), barrier, one scatter-add over all messages
-    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, nupd, cp, M->g, ma, sa, M->stream);
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, M->stream);
     M->stats.kernel_launches += nupd ? 1 : 0;
     if (M->profiling) {
       cudaEventRecord(ev_pack1, M->stream);
@@ -982,13 +1004,15 @@ int commit_exchange(cm_matrix *M) {
       CM_TRY(tp->stream_barrier(M->stream));
     }
   } else if (M->dma) {
-    // pipelined, mode 3: chunk k is packed locally (main stream), pushed by the copy engines
-    // (xfer stream) and scatter-added (apply stream) while chunk k+1 is packed and pushed. The
+    // pipelined, mode 3: panel k is packed locally (main stream), pushed by the copy engines
+    // (xfer stream) and scatter-added (apply stream) while panel k+1 is packed and pushed. The
     // exchange uses no SM at all, so the two kernels never compete with communication.
     CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
-    for (int k = 0; k < K; ++k) {
-      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, cp.ubeg[k], cp.ubeg[k + 1], cp, M->g, ma, sa, M->stream);
-      M->stats.kernel_launches += cp.ubeg[k + 1] > cp.ubeg[k] ? 1 : 0;
+    for (int k = 0; k < Kp; ++k) {
+      if (panel_has_data(k)) {
+        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, M->stream);
+        M->stats.kernel_launches += 1;
+      }
       CM_CUDA_TRY(cudaEventRecord(M->ev_packed[k], M->stream));
       CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_packed[k], 0));  // my own message of chunk k
       CM_TRY(dma_push(k, k + 1, M->ev_packed[k], M->apply_stream));
@@ -1005,18 +1029,21 @@ int commit_exchange(cm_matrix *M) {
       CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_xfer[x], 0));
     }
   } else {
-    // pipelined, mode 2: chunk k is packed straight into the owners' arenas, a stream-ordered
-    // barrier says "everybody's chunk k has landed", and its scatter-add runs on the apply stream
-    // while chunk k+1 is being packed and stored across NVLink on the main stream
+    // pipelined, mode 2: panel k is packed straight into the owners' arenas, a stream-ordered
+    // barrier says "everybody's panel k has landed", and its scatter-add (which touches only panel
+    // k's columns of the local block) runs on the apply stream while panel k+1 is being packed and
+    // stored across NVLink on the main stream
     CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
-    for (int k = 0; k < K; ++k) {
-      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, cp.ubeg[k], cp.ubeg[k + 1], cp, M->g, ma, sa, M->stream);
-      M->stats.kernel_launches += cp.ubeg[k + 1] > cp.ubeg[k] ? 1 : 0;
+    for (int k = 0; k < Kp; ++k) {
+      if (panel_has_data(k)) {
+        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, M->stream);
+        M->stats.kernel_launches += 1;
+      }
       CM_TRY(tp->stream_barrier(M->stream));
       CM_CUDA_TRY(cudaEventRecord(M->ev_chunk[k], M->stream));
       CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_chunk[k], 0));
       // all but the last chunk's scatter-add share the SMs with the next chunk's pack kernel
-      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < K ? 2 : 0));
+      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? 2 : 0));
     }
     if (M->profiling) {
       cudaEventRecord(ev_pack1, M->stream);
@@ -1396,6 +1423,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
+    if (getenv("CM_B200_PANELS")) M->npanel_cfg = std::max(1, atoi(getenv("CM_B200_PANELS")));
     if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
     const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" / "dma" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
@@ -1796,21 +1824,31 @@ int cm_debug_keep_wire(cm_matrix *M, int on) {
   return CM_OK;
 }
 
-// expands the compact message to owner `dst` into the reference's (inds, data) stream;
-// pass null outputs to count only
+// expands the compact messages to owner `dst` into the reference's (inds, data) stream; pass null
+// outputs to count only. The reference appends update after update to the owner's bin (:611), so the
+// panels of a commit are walked update-major: all panels of update 0, then of update 1, ... (equal to
+// the reference's order whenever an update's column indices are non-decreasing in panel number,
+// e.g. sorted jx; always equal for a one-panel commit).
 static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *data_out) {
   const Geom &g = M->g;
   const size_t esz = M->esz;
   const int dp = dst / (int)g.npcol, dq = dst % (int)g.npcol;
   long n = 0;
+  std::vector<const cm_matrix::DbgMsg *> msgs;
+  long nseg_max = 0;
   for (const auto &dm : M->dbg_msgs) {
     if (dm.dst != dst || dm.meta.size() < sizeof(WireHdr)) continue;
-    const char *meta = dm.meta.data();
-    const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
-    const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
-    const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
-    const unsigned char *vals = reinterpret_cast<const unsigned char *>(dm.vals.data());
-    for (long u = 0; u < h->nseg; ++u) {
+    msgs.push_back(&dm);
+    nseg_max = std::max(nseg_max, reinterpret_cast<const WireHdr *>(dm.meta.data())->nseg);
+  }
+  for (long u = 0; u < nseg_max; ++u)
+    for (const cm_matrix::DbgMsg *dm : msgs) {
+      const char *meta = dm->meta.data();
+      const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
+      if (u >= h->nseg) continue;
+      const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
+      const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
+      const unsigned char *vals = reinterpret_cast<const unsigned char *>(dm->vals.data());
       const WireSeg &s = ws[u];
       const int *lrow = idx + s.idx_off, *lcol = lrow + s.nr;
       for (int b = 0; b < s.nc; ++b)
@@ -1827,7 +1865,6 @@ static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *da
           ++n;
         }
     }
-  }
   const CooBin &cb = M->dbg_coo[dst];
   for (size_t k = 0; k < cb.inds.size(); ++k) {
     if (inds_out) {

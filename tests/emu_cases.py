@@ -93,3 +93,79 @@ CASES = [
     ("device_api_single_rank", [()]),
     ("pipelined_commit_chunks", [(2,), (3,)]),
 ]
+
+
+# ---- column panels (PanelPlan, csrc/cm_common.h) ---------------------------------------------
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def panels_wire_and_blocks(grid, mode, npanel):
+    """a commit cut into column panels: same local blocks as the oracle, and — index sets being
+    sorted — the very same per-owner wire stream as the reference (update-major over the panels)"""
+    from scenario import assert_wire_match, run_cuda
+    nprow, npcol, mb, nb, lld, m, n = grid
+    cfg = Cfg(cm.F64, m, n, nprow, npcol, mb, nb, lld)
+    rng = np.random.default_rng(131)
+    steps = slice_steps(cfg, rng, 5, min(m, 120), min(n, 90), commit_every=3)
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
+    with _Env(CM_B200_PIPELINE=1, CM_B200_PIPELINE_MIN_ELEMS=1, CM_B200_PANELS=npanel):
+        got = run_cuda(cfg, steps, wire=True, exchange_mode=mode)
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+    # panels really were in use: more than one scatter-add launch per commit on some rank
+    with _Env(CM_B200_PIPELINE=1, CM_B200_PIPELINE_MIN_ELEMS=1, CM_B200_PANELS=npanel):
+        got2 = run_cuda(cfg, steps, exchange_mode=mode)
+    assert_blocks_match(cfg, got2, want)
+
+
+def panels_unsorted_masked_and_mixed_sources():
+    """panels with unsorted / duplicate index sets, the symmetric update and fill_lower, elemental
+    updates in the same commit, and sources that split next to sources that do not"""
+    from scenario import run_cuda
+    cfg = Cfg(cm.F64, 700, 700, 2, 2, 32, 32, 512)
+    rng = np.random.default_rng(132)
+    steps = []
+    for r in range(cfg.P):
+        ix = rng.integers(0, cfg.m, 150).astype(np.int64)  # unsorted, with duplicates
+        jx = rng.integers(0, cfg.n, 110).astype(np.int64)
+        steps.append(("slice", r, rand_payload(rng, cfg.dtype, (110, 150)), 150, 110, 150, False, ix, jx))
+        sx = sorted_unique(rng, cfg.m, 90)
+        steps.append(("sym", r, rand_payload(rng, cfg.dtype, (90, 90)), 90, 90, False, sx))
+        steps.append(("elems", r, rand_payload(rng, cfg.dtype, 50), rng.integers(0, cfg.m, 50), rng.integers(0, cfg.n, 50)))
+    # rank 3 stages one tiny extra update only in the second round: it will not split, the others do
+    steps.append(("commit",))
+    for r in range(3):
+        ix, jx = sorted_unique(rng, cfg.m, 200), sorted_unique(rng, cfg.n, 200)
+        steps.append(("slice", r, rand_payload(rng, cfg.dtype, (200, 200)), 200, 200, 200, False, ix, jx))
+    steps.append(("slice", 3, rand_payload(rng, cfg.dtype, (3, 5)), 5, 3, 5, False, sorted_unique(rng, cfg.m, 5),
+                  sorted_unique(rng, cfg.n, 3)))
+    steps += [("commit",), ("fill_lower",), ("commit",)]
+    want = run_checker(cfg, steps)
+    for mode in (2, 3):
+        with _Env(CM_B200_PIPELINE=1, CM_B200_PIPELINE_MIN_ELEMS=1000, CM_B200_PANELS=4):
+            got = run_cuda(cfg, steps, exchange_mode=mode)
+        assert_blocks_match(cfg, got, want)
+        with _Env(CM_B200_PIPELINE=1, CM_B200_PIPELINE_MIN_ELEMS=1000, CM_B200_PANELS=3):
+            got = run_cuda(cfg, steps, exchange_mode=mode, deterministic=True)
+        assert_blocks_match(cfg, got, want)
+
+
+CASES += [
+    ("panels_wire_and_blocks", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
+                                ((3, 2, 8, 4, 96, 250, 150), 3, 3), ((1, 2, 64, 64, 1024, 1000, 130), 2, 4),
+                                ((2, 1, 64, 64, 1024, 2000, 40), 2, 2)]),
+    ("panels_unsorted_masked_and_mixed_sources", [()]),
+]

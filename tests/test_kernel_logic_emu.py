@@ -34,6 +34,8 @@ GROUPS = [
     "test_save_load_reference_file_format",
     "device_api_single_rank",
     "pipelined_commit_chunks",
+    "panels_wire_and_blocks",
+    "panels_unsorted_masked_and_mixed_sources",
 ]
 
 
