@@ -1171,6 +1171,21 @@ void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, lon
   }
 }
 
+// One half of the flag barrier (cm_matrix.cu, commit_stream_barrier): every earlier kernel of this
+// stream has completed — its stores into the peers' arenas included — when this one starts; the
+// fence orders the flag behind them at system scope, the store crosses NVLink into the peer's row.
+__global__ void k_signal_peers(uint32_t *const *__restrict__ peer_rows, int me, int nranks, uint32_t seq) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nranks && r != me) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(peer_rows[r] + me) = seq;
+  }
+}
+
+void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s) {
+  CM_LAUNCH((nranks + 127) / 128, 128, 0, s, k_signal_peers)(d_peer_rows, me, nranks, seq);
+}
+
 // global indices of local indices 0..count-1 on process p (:697, :699)
 __global__ void k_iota_global(long *out, long count, long blk, long np, long p) {
   for (long l = (long)blockIdx.x * blockDim.x + threadIdx.x; l < count; l += (long)gridDim.x * blockDim.x)

@@ -84,6 +84,9 @@ void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, lon
 // fill_lower helpers: global indices of this rank's local columns / rows (:697, :699)
 void launch_iota_global(long *d_out, long count, long blk, long np, long p, cudaStream_t s);
 
+// barrier over peer memory: flags[me] = seq in every peer's barrier row (system-scope release)
+void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s);
+
 int kernel_sm_count();
 
 }  // namespace cmb

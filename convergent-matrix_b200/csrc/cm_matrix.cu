@@ -275,6 +275,14 @@ struct cm_matrix {
   std::vector<bool> peer_flags_open;
   uint32_t xfer_seq = 0;
   PinBuf h_seq;
+  // Barrier over the same mapping (second row of d_flags): a one-block kernel stores this rank's
+  // barrier sequence number into every peer's row, then the stream waits (cuStreamWaitValue32) until
+  // every peer's number has arrived in its own row. Replaces the 1-element ncclAllReduce of a commit's
+  // barriers; opt-in (CM_B200_FLAG_BARRIER=1) until measured. =2 also allows it between rank threads
+  // of one process (kernel-logic tests only).
+  int flag_barrier = 0;
+  uint32_t bar_seq = 0;
+  DevBuf d_peer_rows;  // [P] device pointers: peer r's barrier row
   unsigned seq_slot = 0;
   static constexpr int kXferStreams = 4;  // peers are spread over several streams = several copy engines
   cudaStream_t xfer_stream[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
@@ -605,6 +613,33 @@ StreamWaitValue32Fn stream_wait_value32() {
   return fn;
 }
 
+// ---- barriers of a commit ------------------------------------------------------------------
+// stream-ordered: work enqueued on `st` afterwards starts only when every rank's stream has reached
+// its own call. Default: the transport's (a 1-element ncclAllReduce); opt-in: flags over peer memory.
+int commit_stream_barrier(cm_matrix *M, cudaStream_t st) {
+  Transport *tp = M->ctx->tp;
+  StreamWaitValue32Fn wait32 = nullptr;
+  const bool flags = M->P > 1 && M->p2p && M->flag_barrier > 0 && (M->flag_barrier > 1 || !tp->same_process()) &&
+                     (wait32 = stream_wait_value32()) != nullptr;
+  if (!flags) return tp->stream_barrier(st);
+  const uint32_t seq = ++M->bar_seq;
+  launch_signal_peers(M->d_peer_rows.as<uint32_t *>(), M->me, M->P, seq, st);
+  M->stats.kernel_launches += 1;
+  const char *row = M->d_flags.as<char>() + 4 * (size_t)M->P;
+  for (int r = 0; r < M->P; ++r) {
+    if (r == M->me) continue;
+    const int rc = wait32(st, (unsigned long long)(uintptr_t)(row + 4 * (size_t)r), seq, /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0);
+    if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
+  }
+  return CM_OK;
+}
+// returns when every rank's stream work up to its own call is complete
+int commit_barrier(cm_matrix *M, cudaStream_t st) {
+  CM_TRY(commit_stream_barrier(M, st));
+  CM_CUDA_TRY(cudaStreamSynchronize(st));
+  return CM_OK;
+}
+
 // ---- receive arenas ---------------------------------------------------------------------
 // Every rank owns a values arena and a metadata arena that hold the messages of ONE commit from
 // all sources (its own included). With peer-to-peer exchange the sources' pack kernels store
@@ -755,6 +790,28 @@ int commit_exchange(cm_matrix *M) {
   long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + per_rank * P);  // [src][dst]
   for (int src = 0; src < P; ++src)
     for (int d = 0; d < P; ++d) coo_counts[(size_t)src * P + d] = counts[cidx(src, 0, d)].ncoo;
+
+  // -- nothing staged on any rank: the counts all-gather already was the rendezvous of this commit
+  // (nobody leaves it before everybody has entered it); there is nothing to exchange, to apply or
+  // to wait for, so the two barriers below are skipped (empty-commit latency)
+  {
+    bool any = false;
+    for (size_t i = 0; i < (size_t)P * K * P && !any; ++i) any = counts[i].nvals != 0 || counts[i].ncoo != 0;
+    if (!any) {
+      if (M->profiling) {
+        M->event_pool.push_back(ev_pack0);
+        M->event_pool.push_back(ev_pack1);
+      }
+      if (M->keep_wire) {
+        M->dbg_msgs.clear();
+        M->dbg_coo = M->coo;
+        M->dbg_valid = true;
+      }
+      resolve_timers(M);
+      clear_staged(M);
+      return CM_OK;
+    }
+  }
 
   // -- pipeline or not: same decision on every rank, taken from the global counts. Pipelining pays
   // when the commit is large and most of it arrived cut into panels (panel k > 0 non-empty);
@@ -1001,7 +1058,7 @@ int commit_exchange(cm_matrix *M) {
       CM_TRY(dma_push(0, K, M->ev_packed[0], M->stream));
     } else if (M->p2p && P > 1) {
       // mode 2: every source's pack kernel has finished storing into my arenas
-      CM_TRY(tp->stream_barrier(M->stream));
+      CM_TRY(commit_stream_barrier(M, M->stream));
     }
   } else if (M->dma) {
     // pipelined, mode 3: panel k is packed locally (main stream), pushed by the copy engines
@@ -1039,9 +1096,11 @@ int commit_exchange(cm_matrix *M) {
         launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, M->stream);
         M->stats.kernel_launches += 1;
       }
-      CM_TRY(tp->stream_barrier(M->stream));
+      // "everybody's panel k has landed" is awaited on the apply stream: the main stream goes straight
+      // on to the pack of panel k+1
       CM_CUDA_TRY(cudaEventRecord(M->ev_chunk[k], M->stream));
       CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_chunk[k], 0));
+      CM_TRY(commit_stream_barrier(M, M->apply_stream));
       // all but the last chunk's scatter-add share the SMs with the next chunk's pack kernel
       CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? 2 : 0));
     }
@@ -1090,7 +1149,7 @@ int commit_exchange(cm_matrix *M) {
   }
   CM_CUDA_TRY(cudaGetLastError());
   // -- quiescence: everybody has applied everything (reference :737-741) --------------------
-  CM_TRY(tp->barrier(M->stream));
+  CM_TRY(commit_barrier(M, M->stream));
   CM_CUDA_TRY(cudaGetLastError());
   resolve_timers(M);
   M->mirror_valid = false;
@@ -1375,10 +1434,10 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->peer_flags.assign(M->P, nullptr);
   M->peer_flags_open.assign(M->P, false);
   if (M->P > 1) {
-    int rcf = M->d_flags.ensure(4 * (size_t)M->P);
+    int rcf = M->d_flags.ensure(2 * 4 * (size_t)M->P);  // row 0: arrival flags of mode 3, row 1: barrier
     if (rcf == CM_OK) rcf = M->h_seq.ensure(4 * 1024);
     if (rcf != CM_OK) return rcf;
-    cudaMemsetAsync(M->d_flags.p, 0, 4 * (size_t)M->P, M->stream);
+    cudaMemsetAsync(M->d_flags.p, 0, 2 * 4 * (size_t)M->P, M->stream);
     cudaStreamSynchronize(M->stream);
     M->peer_flags[M->me] = M->d_flags.p;
     if (ctx->tp->same_process()) {
@@ -1432,6 +1491,15 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p_possible &= flags_ok;
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
     M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
+    if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
+    if (M->P > 1 && M->p2p_possible) {
+      std::vector<void *> rows(M->P);
+      for (int r = 0; r < M->P; ++r) rows[r] = static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)M->P;
+      int rcr = M->d_peer_rows.ensure(sizeof(void *) * (size_t)M->P);
+      if (rcr != CM_OK) return rcr;
+      cudaMemcpyAsync(M->d_peer_rows.p, rows.data(), sizeof(void *) * (size_t)M->P, cudaMemcpyHostToDevice, M->stream);
+      cudaStreamSynchronize(M->stream);
+    }
   }
   int rc = ctx->tp->barrier(M->stream);
   if (rc != CM_OK) return rc;
@@ -1467,6 +1535,7 @@ int cm_destroy(cm_matrix *M) {
   for (auto e : M->ev_packed) cudaEventDestroy(e);
   for (auto e : M->ev_xfer) cudaEventDestroy(e);
   M->d_flags.release();
+  M->d_peer_rows.release();
   M->h_seq.release();
   for (auto e : M->ev_chunk) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);

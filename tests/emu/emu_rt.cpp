@@ -6,6 +6,7 @@
 #undef blockIdx
 #undef blockDim
 #undef gridDim
+#include <sched.h>
 #include <stdio.h>
 #include <sys/mman.h>
 
@@ -347,7 +348,20 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) {
   a->type = cudaMemoryTypeUnregistered;
   return cudaSuccess;
 }
-cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {
+// cuStreamWaitValue32(stream, addr, value, GEQ): streams complete immediately here, so the wait is a
+// host spin until another rank thread's kernel has stored the value
+static int emu_stream_wait_value32(cudaStream_t, unsigned long long addr, uint32_t value, unsigned) {
+  volatile uint32_t *p = reinterpret_cast<volatile uint32_t *>(static_cast<uintptr_t>(addr));
+  while ((int32_t)(*p - value) < 0) sched_yield();
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+  return 0;
+}
+cudaError_t cudaGetDriverEntryPoint(const char *sym, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {
+  if (!strcmp(sym, "cuStreamWaitValue32")) {
+    *fn = reinterpret_cast<void *>(&emu_stream_wait_value32);
+    *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
   *fn = nullptr;
   *q = cudaDriverEntryPointSymbolNotFound;
   return cudaSuccess;

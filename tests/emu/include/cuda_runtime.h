@@ -87,6 +87,7 @@ template <class T>
 inline unsigned __match_any_sync(unsigned /*full mask*/, T v) {
   return ::cmemu::match_any((unsigned long long)v);
 }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <class T>
 inline T __ldg(const T *p) {

@@ -169,3 +169,24 @@ CASES += [
                                 ((2, 1, 64, 64, 1024, 2000, 40), 2, 2)]),
     ("panels_unsorted_masked_and_mixed_sources", [()]),
 ]
+
+
+def flag_barrier_commits():
+    """commit barriers over peer-mapped flags (CM_B200_FLAG_BARRIER) instead of the transport's: batch
+    commits, panel-pipelined commits, empty commits and several rounds on two grids"""
+    from scenario import run_cuda
+    for grid, pipe in [((2, 2, 64, 64, 1024, 2000, 1000), 0), ((2, 4, 16, 16, 256, 500, 900), 1)]:
+        nprow, npcol, mb, nb, lld, m, n = grid
+        cfg = Cfg(cm.F64, m, n, nprow, npcol, mb, nb, lld)
+        rng = np.random.default_rng(141)
+        steps = [("commit",)] + slice_steps(cfg, rng, 6, min(m, 150), min(n, 100), commit_every=2) + [("commit",)]
+        for r in range(cfg.P):
+            steps.append(("elems", r, rand_payload(rng, cfg.dtype, 40), rng.integers(0, cfg.m, 40), rng.integers(0, cfg.n, 40)))
+        steps.append(("commit",))
+        want = run_checker(cfg, steps)
+        with _Env(CM_B200_FLAG_BARRIER=2, CM_B200_PIPELINE=pipe, CM_B200_PIPELINE_MIN_ELEMS=1):
+            got = run_cuda(cfg, steps, exchange_mode=2)
+        assert_blocks_match(cfg, got, want)
+
+
+CASES += [("flag_barrier_commits", [()])]

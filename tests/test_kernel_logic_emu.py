@@ -36,6 +36,7 @@ GROUPS = [
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
     "panels_unsorted_masked_and_mixed_sources",
+    "flag_barrier_commits",
 ]
 
 
