@@ -338,6 +338,8 @@ struct cm_matrix {
                                         // enables them in mode 2 too, =0 disables them everywhere
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
   int npanel_cfg = kMaxChunks;          // column panels of a pipelined commit (CM_B200_PANELS)
+  int pipeline_apply_blocks = 2;        // resident scatter-add blocks per SM while the next panel is being packed
+                                        // (CM_B200_PIPELINE_APPLY_BLOCKS; 0 = no cap)
   PinBuf h_counts;
 
   cm_stats stats{};
@@ -1102,7 +1104,7 @@ int commit_exchange(cm_matrix *M) {
       CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_chunk[k], 0));
       CM_TRY(commit_stream_barrier(M, M->apply_stream));
       // all but the last chunk's scatter-add share the SMs with the next chunk's pack kernel
-      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? 2 : 0));
+      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? M->pipeline_apply_blocks : 0));
     }
     if (M->profiling) {
       cudaEventRecord(ev_pack1, M->stream);
@@ -1482,6 +1484,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
+    if (getenv("CM_B200_PIPELINE_APPLY_BLOCKS")) M->pipeline_apply_blocks = std::max(0, atoi(getenv("CM_B200_PIPELINE_APPLY_BLOCKS")));
     if (getenv("CM_B200_PANELS")) M->npanel_cfg = std::max(1, atoi(getenv("CM_B200_PANELS")));
     if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
     const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" / "dma" override, must agree on all ranks

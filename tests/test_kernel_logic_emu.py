@@ -60,6 +60,14 @@ def test_kernel_logic(emu_lib, group):
     assert p.returncode == 0 and "fails: 0" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
+def test_fuzz_scenarios(emu_lib):
+    """a bounded slice of tests/emu/fuzz.py: random geometries / update shapes / index styles / knobs
+    (exchange modes, column panels, flag barrier, both scatter-add kernels) against the oracle"""
+    p = subprocess.run([sys.executable, os.path.join(EMU, "fuzz.py"), "--seed", "0", "--count", "80"], capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode == 0 and "fails: 0" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
 def test_product_library_is_not_the_emulator():
     """the product path never loads the test double: libcm_b200.so is an nvcc build (it embeds an
     sm_100a cubin), the package only knows that path, and nothing outside tests/ mentions CM_EMU
