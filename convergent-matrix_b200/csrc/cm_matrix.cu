@@ -600,18 +600,16 @@ int flush_direct(cm_matrix *M, bool sync = true) {
 // cuStreamWaitValue32 through the runtime's driver entry point lookup (no libcuda link dependency)
 typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
 StreamWaitValue32Fn stream_wait_value32() {
-  static StreamWaitValue32Fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // looked up once; thread-safe (rank threads of the loopback transport may race here)
+  static const StreamWaitValue32Fn fn = [] {
     void *p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<StreamWaitValue32Fn>(p);
-    else
-      cudaGetLastError();
-  }
+      return reinterpret_cast<StreamWaitValue32Fn>(p);
+    cudaGetLastError();
+    return static_cast<StreamWaitValue32Fn>(nullptr);
+  }();
   return fn;
 }
 

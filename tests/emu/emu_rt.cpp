@@ -352,7 +352,14 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) {
 // host spin until another rank thread's kernel has stored the value
 static int emu_stream_wait_value32(cudaStream_t, unsigned long long addr, uint32_t value, unsigned) {
   volatile uint32_t *p = reinterpret_cast<volatile uint32_t *>(static_cast<uintptr_t>(addr));
-  while ((int32_t)(*p - value) < 0) sched_yield();
+  const double t0 = now_ms();
+  while ((int32_t)(*p - value) < 0) {
+    sched_yield();
+    if (now_ms() - t0 > 30000.0) {  // a rank never signalled: report instead of hanging the test-suite
+      fprintf(stderr, "[cm emu] cuStreamWaitValue32 timed out: *%p = %u, waiting for >= %u\n", (void *)p, *p, value);
+      abort();
+    }
+  }
   __atomic_thread_fence(__ATOMIC_SEQ_CST);
   return 0;
 }
