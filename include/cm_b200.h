@@ -195,7 +195,7 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
  * (arenas mapped with CUDA IPC), so packing and exchange are one kernel, 3 = copy engines: messages
  * are packed locally and pushed into the owners' arenas with peer cudaMemcpyAsync, arrival is
  * signalled with a flag the owner awaits with cuStreamWaitValue32 (no SM does communication, so
- * the scatter-add of one chunk overlaps the push of the next). Auto picks 2 when every rank can map
+ * the scatter-add of one column panel overlaps the push of the next). Auto picks 2 when every rank can map
  * every other rank's memory, else 1. The environment variable CM_B200_EXCHANGE=nccl|p2p|dma sets
  * the default. cm_get_exchange_mode returns the mode in effect (1, 2 or 3). */
 int cm_set_exchange_mode(cm_matrix *M, int mode);
