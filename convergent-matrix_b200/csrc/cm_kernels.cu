@@ -598,19 +598,21 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_loc
 }
 
 // ------------------------------------------------------------------------------------
-// (6b) column-tile scatter-add. One block owns one tile of the local block — one column x
-// kTileWarps row bands — in shared memory, and each WARP owns one band of it. The block walks
-// the column's run of items in sorted order; for every item a warp takes exactly the rows
-// that fall into its band (a contiguous sub-range, because an update's row indices are
-// strictly increasing; the sub-range bounds were precomputed once per segment chunk) and adds
-// them into its band with plain shared-memory read-modify-write. Warps never touch each
-// other's bands, so there is no atomic and no block barrier inside a run; values and row
-// indices are prefetched kValStages items ahead with cp.async into warp-private rings.
-// Finally the tile is added to HBM with coalesced loads/stores, skipping 32-byte sectors
-// nobody touched. A tile has one owner and a band's items are applied in a fixed order, so
-// the result is bit-exact run to run (this is also the deterministic-order mode). DRAM
-// traffic is the compulsory s*E + 2*s*(touched sectors) instead of one sector round trip
-// per element. Best when the flush hits the local block densely.
+// (6b) column-tile scatter-add. One block owns one tile of the local block — one column x up to
+// kTileRows rows (64 KiB) — in shared memory. It walks the column's run of items in sorted order;
+// thread t owns element t of every item (an item is at most kRowChunk = 256 rows of one segment
+// column) and adds it into the tile with a plain shared-memory read-modify-write. An update's row
+// indices are strictly increasing, so the elements of ONE item never collide; one __syncthreads per
+// item keeps different items — which may hit the same rows — in order. The values and row indices
+// of BLK items are in flight in registers while the previous BLK are being added (two register
+// sets), with an L2 prefetch of the value lines a few blocks further ahead. Items whose rows may
+// repeat, masked items (symmetric update / fill_lower) and strided payloads take a simple in-order
+// loop. Local blocks taller than a tile are cut into row bands (kMulti): every band's block walks the
+// same items and takes the rows that fall into its band. Finally the tile is added to HBM with
+// 16-byte loads/stores, skipping pieces nobody touched. A tile has one owner and its items are
+// applied in a fixed order, so the result is bit-exact run to run (this is also the
+// deterministic-order mode). DRAM traffic is the compulsory s*E + 2*s*(touched pieces) instead of
+// one sector round trip per element. Best when the flush hits the local block densely.
 // ------------------------------------------------------------------------------------
 constexpr int kRecChunk = 144;  // items of a run staged in shared memory at a time (multiple of 2*BLK)
 

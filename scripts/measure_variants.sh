@@ -1,0 +1,46 @@
+#!/usr/bin/env bash
+# Measurement plan for the variants that were built without GPU time.
+# Run ON a GPU box, e.g.
+#   gpurun --gpus 2 --timeout 1500 -- 'bash scripts/measure_variants.sh 2 > gpurun_out/variants_n2.log 2>&1'
+#   gpurun --gpus 8 --timeout 1800 -- 'bash scripts/measure_variants.sh 8 > gpurun_out/variants_n8.log 2>&1'
+# Every bench line is a normal `bench.py` JSON line (device-timed, max over ranks); nothing here runs under a profiler.
+set -u
+N=${1:-2}
+PORT=29811
+run() {  # run <label> <env...> -- <bench args...>
+  local label=$1; shift
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done
+  shift
+  echo "=== $label: ${envs[*]:-} bench.py $*"
+  env "${envs[@]}" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+      --master-port $((PORT++)) bench.py --gpus "$N" --no-e2e --no-cpu-baseline --latency-reps 50 "$@" | tail -1
+}
+parity() {  # parity <label> <env...>
+  local label=$1; shift
+  echo "=== parity $label: $*"
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+      --master-port $((PORT++)) tests/mp_parity.py | tail -4
+  echo "rc=$?"
+}
+
+# 1. parity of the new paths over real NVLink / NCCL first (small commits: thresholds lowered)
+parity baseline CM_B200_PIPELINE=0
+parity panels CM_B200_PIPELINE=1 CM_B200_PIPELINE_MIN_ELEMS=1
+parity panels+flags CM_B200_PIPELINE=1 CM_B200_PIPELINE_MIN_ELEMS=1 CM_B200_FLAG_BARRIER=1
+parity flags CM_B200_FLAG_BARRIER=1
+
+# 2. K1-weak: batch commit (round-1 default) against panel pipelining
+run k1-batch CM_B200_PIPELINE=0 -- --steps 5 --warmup 3
+for AB in 1 2 3; do
+  run k1-panels4-ab$AB CM_B200_PIPELINE=1 CM_B200_PIPELINE_APPLY_BLOCKS=$AB -- --steps 5 --warmup 3
+done
+run k1-panels2 CM_B200_PIPELINE=1 CM_B200_PANELS=2 -- --steps 5 --warmup 3
+run k1-panels4-flags CM_B200_PIPELINE=1 CM_B200_FLAG_BARRIER=1 -- --steps 5 --warmup 3
+
+# 3. K2 (commit every 256 updates: 67 Mi elements per rank per commit) and K4 (tiny updates)
+run k2-batch CM_B200_PIPELINE=0 -- --workload K2 --steps 3 --warmup 3
+run k2-panels CM_B200_PIPELINE=1 -- --workload K2 --steps 3 --warmup 3
+run k2-panels-flags CM_B200_PIPELINE=1 CM_B200_FLAG_BARRIER=1 -- --workload K2 --steps 3 --warmup 3
+run k4-batch CM_B200_PIPELINE=0 -- --workload K4 --steps 3 --warmup 3
+run k4-flags CM_B200_FLAG_BARRIER=1 -- --workload K4 --steps 3 --warmup 3

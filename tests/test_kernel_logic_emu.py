@@ -60,6 +60,13 @@ def test_kernel_logic(emu_lib, group):
     assert p.returncode == 0 and "fails: 0" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
+def test_cpp_reference_suite_port_on_the_test_double(emu_lib):
+    """cpp_tests/cm_test.cpp — the reference's own four scenarios through the C++ drop-in headers,
+    T in {int, float, double}, 4 ranks as threads — linked against the kernel-logic test library"""
+    p = subprocess.run([os.path.join(EMU, "cm_test_emu"), "2"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "PASS" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
+
+
 def test_fuzz_scenarios(emu_lib):
     """a bounded slice of tests/emu/fuzz.py: random geometries / update shapes / index styles / knobs
     (exchange modes, column panels, flag barrier, both scatter-add kernels) against the oracle"""
