@@ -388,7 +388,8 @@ def bench_ours(args):
             "config": {"workload": spec["name"], "updates_per_rank_per_step": spec["U"], "grid": [spec["nprow"], spec["npcol"]],
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
-                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": {1: "nccl", 2: "p2p", 3: "dma"}[M.exchange_mode()] if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes},
+                       "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": {1: "nccl", 2: "p2p", 3: "dma"}[M.exchange_mode()] if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes,
+                       "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CM_B200_")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
             "commit_latency_us": {"empty": lat_empty, "one_update": lat_one},

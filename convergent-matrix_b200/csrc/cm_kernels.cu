@@ -284,13 +284,19 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
     for (; kc + 3 * gy < cend; kc += 4 * gy) {
       T x[4];
       T *out[4];
+      int cp[4];
+      // the four source-column positions first (independent loads), then the four gathers that
+      // depend on them; the destination lookups (shared memory) fill the wait
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cp[i] = cpos[kc + i * gy];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = kc + i * gy;
         while (c >= coff[gq + 1]) ++gq;
         out[i] = brow[gdst[gq]] + (long)(c - coff[gq]) * stride + a;
-        x[i] = live ? data[srow + (long)cpos[c] * src_cs] : T(0);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = live ? data[srow + (long)cp[i] * src_cs] : T(0);
       if (live) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) *out[i] = x[i];

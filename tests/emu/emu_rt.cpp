@@ -73,7 +73,12 @@ struct BlockState {
   int or_acc = 0, or_result = 0;
   long progress = 0;  // bumped by every barrier release / fiber exit (deadlock watchdog)
   ThreadCoords tc;
+  ~BlockState();  // rank threads come and go (one set per test scenario): give the stacks back
 };
+
+BlockState::~BlockState() {
+  if (stacks) munmap(stacks, kStackBytes * kMaxThreads);
+}
 
 static thread_local BlockState tl_block;
 

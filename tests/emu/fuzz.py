@@ -20,7 +20,7 @@ import numpy as np  # noqa: E402
 
 import cm_b200 as cm  # noqa: E402
 
-cm.LIB_PATH = os.path.join(HERE, "libcm_b200_emu.so")
+cm.LIB_PATH = os.environ.get("CM_EMU_LIB", os.path.join(HERE, "libcm_b200_emu.so"))  # e.g. a sanitizer build
 
 from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,  # noqa: E402
                       sorted_unique)

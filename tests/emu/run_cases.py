@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import cm_b200 as cm  # noqa: E402
 
-cm.LIB_PATH = os.path.join(HERE, "libcm_b200_emu.so")  # explicit: the tests' library, not the product's
+cm.LIB_PATH = os.environ.get("CM_EMU_LIB", os.path.join(HERE, "libcm_b200_emu.so"))  # e.g. a sanitizer build  # explicit: the tests' library, not the product's
 
 import test_gpu_parity as T  # noqa: E402
 import emu_cases as E  # noqa: E402
