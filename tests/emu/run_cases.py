@@ -52,6 +52,7 @@ CASES = [
     (T, "test_empty_ragged_and_lopsided_inputs", [()]),
     (T, "test_contract_violations_fail_loudly", [()]),
     (T, "test_save_load_reference_file_format", [(1, None), (4, None)]),
+    (T, "test_flag_barrier_is_refused_between_rank_threads", [()]),
 ] + [(E, name, params) for name, params in E.CASES]
 
 NAMES = [name for _, name, _ in CASES]

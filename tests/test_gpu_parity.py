@@ -80,8 +80,8 @@ def test_both_exchange_modes(mode):
 
 @pytest.mark.parametrize("mode", [2, 3])
 def test_pipelined_commit_chunks(mode):
-    """a commit big enough to be pipelined chunk by chunk (scatter-add of chunk k on the apply stream
-    while chunk k+1 is packed / pushed): > 32 Mi elements per rank and > 8 updates per matrix element.
+    """a commit big enough to be cut into column panels and pipelined (scatter-add of panel k on the
+    apply stream while panel k+1 is packed / pushed): > 32 Mi elements staged per rank.
     Mode 3 (copy engines) pipelines by default, mode 2 (peer stores) only with CM_B200_PIPELINE=1."""
     import torch
     if mode == 2:
@@ -120,7 +120,7 @@ def test_pipelined_commit_chunks(mode):
             gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(512)])
             gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(512)])
             assert np.array_equal(blk[:512, :512], want[np.ix_(gj, gi)])
-        # 4 chunks => 4 scatter-add launches per rank for the second commit
+        # 4 column panels => 4 scatter-add launches per rank for the second commit
         world.run(lambda r: (mats[r].reset_stats(), mats[r].set_profiling(True)))
         out2 = world.run(issue)
         assert all(st["apply_launches"] == 4 for _, st in out2), [st["apply_launches"] for _, st in out2]
@@ -462,3 +462,25 @@ def test_save_load_reference_file_format(P, tmp_path):
             world.close()
         else:
             cm.finalize()
+
+
+@pytest.mark.parametrize("grid,mode,npanel", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
+                                              ((3, 2, 8, 4, 96, 250, 150), 3, 3)])
+def test_column_panels_wire_bit_exact(grid, mode, npanel):
+    """commits cut into column panels (thresholds lowered through the environment so
+    that small commits are cut too): local blocks match the oracle and, index sets being sorted, the
+    per-owner wire streams are the reference's element for element"""
+    from emu_cases import panels_wire_and_blocks
+    panels_wire_and_blocks(grid, mode, npanel)
+
+
+def test_flag_barrier_is_refused_between_rank_threads():
+    """CM_B200_FLAG_BARRIER=1 applies to one-process-per-GPU runs only: rank threads sharing one GPU keep
+    the transport's barrier (mutually waiting streams of one device could deadlock), results unchanged"""
+    from emu_cases import _Env
+    cfg = Cfg(cm.F64, 600, 600, 2, 2, 64, 64, 512)
+    rng = np.random.default_rng(72)
+    steps = slice_steps(cfg, rng, 3, 100, 100, commit_every=2)
+    with _Env(CM_B200_FLAG_BARRIER=1):
+        got = run_cuda(cfg, steps, exchange_mode=2)
+    assert_blocks_match(cfg, got, run_checker(cfg, steps))
