@@ -171,10 +171,14 @@ def gen_inputs(spec, rank, torch, device):
 
 
 def run_step(M, batches, spec):
-    """one pass of the workload on this rank: U updates with the configured commit cadence"""
+    """one pass of the workload on this rank: U updates with the configured commit cadence; under the
+    deferred apply policy the step ends with a collective materialise, so that every update of the step
+    has been scatter-added inside the timed region"""
     for b in batches:
         M.update_batch(b["batch"], b["device"])
         M.commit()
+    if spec.get("deferred"):
+        M.materialize()
 
 
 def make_batches(cm, spec, data_ptr, ix_ptr, jx_ptr, esz, device):
@@ -227,6 +231,9 @@ def bench_ours(args):
     M.set_apply_kernel({"auto": 0, "red": 1, "tile": 2}[args.apply_kernel])
     if nranks > 1:
         M.set_exchange_mode({"auto": 0, "nccl": 1, "p2p": 2, "dma": 3}[args.exchange])
+    spec["deferred"] = args.apply_policy == "deferred" and nranks > 1 and M.exchange_mode() != 1
+    if spec["deferred"]:
+        M.set_apply_policy(1, args.defer_budget_gib << 30)
     data, ix, jx = gen_inputs(spec, rank, torch, device)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(M.stream(), device=device)
@@ -389,6 +396,7 @@ def bench_ours(args):
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
                        "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": {1: "nccl", 2: "p2p", 3: "dma"}[M.exchange_mode()] if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes,
+                       "apply_policy": "deferred (extension: commits deliver, ONE scatter-add per step inside the timed region)" if spec["deferred"] else "eager (reference semantics)",
                        "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CM_B200_")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
@@ -487,6 +495,9 @@ def main():
     ap.add_argument("--apply-kernel", default="auto", choices=["auto", "red", "tile"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "dma"],
                     help="auto/p2p: the pack kernel stores into the owners' arenas over NVLink; nccl: grouped send/recv")
+    ap.add_argument("--apply-policy", default="eager", choices=["eager", "deferred"],
+                    help="deferred (N > 1, p2p/dma): commits only deliver, the step ends with cm_materialize (inside the timed region)")
+    ap.add_argument("--defer-budget-gib", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-updates", type=int, default=0, help="updates per rank per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -88,6 +88,9 @@ SYMBOLS = {
     "cm_set_deterministic": (_i, [_vp, _i]),
     "cm_set_sorted_sweep": (_i, [_vp, _i]),
     "cm_set_apply_kernel": (_i, [_vp, _i, C.c_double]),
+    "cm_set_apply_policy": (_i, [_vp, _i, _l]),
+    "cm_get_apply_policy": (_i, [_vp]),
+    "cm_materialize": (_i, [_vp]),
     "cm_set_exchange_mode": (_i, [_vp, _i]),
     "cm_get_exchange_mode": (_i, [_vp]),
     "cm_descinit": (_i, [_vp, _i, C.POINTER(_i)]),
@@ -319,6 +322,16 @@ class Matrix:
 
     def set_apply_kernel(self, kernel, tile_density=0.0):
         _check(self.L.cm_set_apply_kernel(self.h, kernel, tile_density))
+
+    def set_apply_policy(self, policy, budget_bytes=0):
+        """0 = eager (reference semantics), 1 = deferred scatter-add (collective; see cm_b200.h)"""
+        _check(self.L.cm_set_apply_policy(self.h, policy, budget_bytes))
+
+    def apply_policy(self):
+        return self.L.cm_get_apply_policy(self.h)
+
+    def materialize(self):
+        _check(self.L.cm_materialize(self.h))
 
     def set_exchange_mode(self, mode):
         _check(self.L.cm_set_exchange_mode(self.h, mode))

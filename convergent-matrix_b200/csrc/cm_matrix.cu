@@ -302,6 +302,20 @@ struct cm_matrix {
   const char *merge_src = nullptr;
   char *merge_dst = nullptr;
   size_t merge_bytes = 0;
+  // Deferred scatter-add (opt-in, cm_set_apply_policy): commit() delivers the messages and returns;
+  // they stay in the receive arenas — an append-only log, laid out identically on every rank from the
+  // all-gathered counts — until the block is read, the log exceeds its budget or cm_materialize().
+  // One scatter-add over several commits' messages sweeps the local block once instead of once per commit.
+  struct PendMsg {
+    const char *meta;
+    const void *vals;
+    long nseg, nitems, nelems;
+  };
+  int apply_policy = 0;               // CM_APPLY_EAGER / CM_APPLY_DEFERRED
+  size_t defer_budget = 8ull << 30;   // bytes of logged values per owner before everybody materialises
+  std::vector<PendMsg> pend;          // messages logged in MY arenas since the last collective materialise
+  size_t pend_applied = 0;            // prefix of `pend` a local materialise has already applied
+  std::vector<long> pend_v, pend_m;   // [P] append offsets of EVERY owner's arenas (elements / bytes), same on all ranks
   long flush_threshold = CM_DEFAULT_FLUSH_THRESHOLD;
   int progress_interval = 1;
   int deterministic = 0;
@@ -711,12 +725,75 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
   return CM_OK;
 }
 
+// owner side: messages -> Seg table + (key, item) pairs -> sort -> scatter-add
+int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long item_total, long elem_total, long max_seg,
+                   ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
+  if (seg_total >= (1L << kItemSegBits))
+    return fail(CM_ERR_INVALID, "too many segments in one scatter-add (%ld); commit / materialise more often", seg_total);
+  if (msgs.empty()) return CM_OK;
+  CM_TRY(w.msgs.ensure(sizeof(MsgRef) * msgs.size()));
+  CM_CUDA_TRY(cudaMemcpyAsync(w.msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, st));
+  CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)seg_total));
+  CM_TRY(w.keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
+  CM_TRY(w.items0.ensure(8 * (size_t)std::max(item_total, 1L)));
+  launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
+                    w.items0.as<uint64_t>(), st);
+  M->stats.kernel_launches += 1;
+  CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
+  M->stats.elements_applied += elem_total;
+  return CM_OK;
+}
+
+// deferred policy: apply what has been logged in my arenas and not applied yet (local, not collective;
+// the log itself is only truncated by materialize_all, because every rank tracks its length)
+int materialize_local(cm_matrix *M) {
+  if (M->pend_applied >= M->pend.size()) return CM_OK;
+  std::vector<MsgRef> msgs;
+  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+  for (size_t i = M->pend_applied; i < M->pend.size(); ++i) {
+    const cm_matrix::PendMsg &pm = M->pend[i];
+    MsgRef m;
+    m.meta = pm.meta;
+    m.vals = pm.vals;
+    m.seg_base = seg_total;
+    m.item_base = item_total;
+    seg_total += pm.nseg;
+    item_total += pm.nitems;
+    elem_total += pm.nelems;
+    max_seg = std::max(max_seg, pm.nseg);
+    msgs.push_back(m);
+  }
+  CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, M->work[0], M->stream, 0));
+  M->pend_applied = M->pend.size();
+  M->mirror_valid = false;
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  resolve_timers(M);
+  return CM_OK;
+}
+
+int commit_barrier(cm_matrix *M, cudaStream_t st);
+
+// COLLECTIVE: everybody applies its log, then the logs are truncated everywhere
+int materialize_all(cm_matrix *M) {
+  if (M->P <= 1 || M->pend_v.empty()) return CM_OK;
+  bool any = !M->pend.empty();
+  for (int d = 0; d < M->P; ++d) any = any || M->pend_v[d] != 0 || M->pend_m[d] != 0;
+  if (!any) return CM_OK;  // same answer on every rank: the offsets are global knowledge
+  CM_TRY(materialize_local(M));
+  CM_TRY(commit_barrier(M, M->stream));  // nobody overwrites an arena that is still being read
+  M->pend.clear();
+  M->pend_applied = 0;
+  std::fill(M->pend_v.begin(), M->pend_v.end(), 0L);
+  std::fill(M->pend_m.begin(), M->pend_m.end(), 0L);
+  return CM_OK;
+}
+
 // Column panels of this commit (cm_common.h, PanelPlan). Decided by each source on its own from what
 // it has staged; the wire format carries whatever it decides.
 PanelPlan plan_panels(cm_matrix *M) {
   PanelPlan pp{1, 1};
   const bool wanted = M->P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1);
-  if (!wanted || M->staged_elems < M->pipeline_min_elems) return pp;
+  if (!wanted || M->apply_policy != 0 || M->staged_elems < M->pipeline_min_elems) return pp;
   long k = std::min<long>(M->npanel_cfg, kMaxChunks);
   k = std::min<long>(k, kMaxGridDim / M->g.npcol);
   k = std::min<long>(k, 1024 / M->P);
@@ -816,8 +893,9 @@ int commit_exchange(cm_matrix *M) {
   // -- pipeline or not: same decision on every rank, taken from the global counts. Pipelining pays
   // when the commit is large and most of it arrived cut into panels (panel k > 0 non-empty);
   // everything else goes as one batch.
+  const bool deferred = M->apply_policy != 0 && P > 1 && M->p2p;
   bool pipelined = false;
-  if (P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1)) {
+  if (!deferred && P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1)) {
     long total = 0, later = 0;
     for (int src = 0; src < P; ++src)
       for (int k = 0; k < K; ++k)
@@ -833,16 +911,31 @@ int commit_exchange(cm_matrix *M) {
   std::vector<long> rbase_v((size_t)P * (K * P + 1), 0), rbase_m((size_t)P * (K * P + 1), 0);
   auto ridx = [P, K](int d, int k, int src) { return (size_t)d * (K * P + 1) + (size_t)k * P + src; };
   std::vector<size_t> need_vals(P), need_meta(P);
-  for (int d = 0; d < P; ++d) {
-    for (int k = 0; k < K; ++k)
-      for (int src = 0; src < P; ++src) {
-        const MsgCounts &c = counts[cidx(src, k, d)];
-        const size_t i = ridx(d, k, src);
-        rbase_v[i + 1] = rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
-        rbase_m[i + 1] = rbase_m[i] + meta_bytes(c.nseg, c.nidx);
-      }
-    need_vals[d] = (size_t)rbase_v[ridx(d, K - 1, P - 1) + 1] * esz;
-    need_meta[d] = (size_t)rbase_m[ridx(d, K - 1, P - 1) + 1];
+  auto lay_out = [&]() {  // eager: from the start of the arenas; deferred: behind what is logged there
+    for (int d = 0; d < P; ++d) {
+      rbase_v[ridx(d, 0, 0)] = deferred ? M->pend_v[d] : 0;
+      rbase_m[ridx(d, 0, 0)] = deferred ? M->pend_m[d] : 0;
+      for (int k = 0; k < K; ++k)
+        for (int src = 0; src < P; ++src) {
+          const MsgCounts &c = counts[cidx(src, k, d)];
+          const size_t i = ridx(d, k, src);
+          rbase_v[i + 1] = rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
+          rbase_m[i + 1] = rbase_m[i] + meta_bytes(c.nseg, c.nidx);
+        }
+      need_vals[d] = (size_t)rbase_v[ridx(d, K - 1, P - 1) + 1] * esz;
+      need_meta[d] = (size_t)rbase_m[ridx(d, K - 1, P - 1) + 1];
+    }
+  };
+  lay_out();
+  if (deferred) {
+    // an arena that has to grow is reallocated: everybody applies and truncates its log first (the
+    // capacities are tracked identically on every rank, so this is the same decision everywhere)
+    bool grow = false;
+    for (int d = 0; d < P; ++d) grow = grow || need_vals[d] > M->cap_vals[d] || need_meta[d] > M->cap_meta[d];
+    if (grow) {
+      CM_TRY(materialize_all(M));
+      lay_out();
+    }
   }
   CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
 
@@ -896,7 +989,7 @@ int commit_exchange(cm_matrix *M) {
     M->stats.h2d_bytes += n * (long)(8 + esz);
   }
 
-  // -- owner side of a group of chunks [k0, k1): messages -> Seg table + items -> sort -> scatter-add
+  // -- owner side of the panels [k0, k1): their messages -> one scatter-add
   auto apply_chunks = [&](int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) -> int {
     std::vector<MsgRef> msgs;
     long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
@@ -915,20 +1008,7 @@ int commit_exchange(cm_matrix *M) {
         max_seg = std::max(max_seg, c.nseg);
         msgs.push_back(m);
       }
-    if (seg_total >= (1L << kItemSegBits))
-      return fail(CM_ERR_INVALID, "too many segments in one commit (%ld); commit more often", seg_total);
-    if (msgs.empty()) return CM_OK;
-    CM_TRY(w.msgs.ensure(sizeof(MsgRef) * msgs.size()));
-    CM_CUDA_TRY(cudaMemcpyAsync(w.msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, st));
-    CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)seg_total));
-    CM_TRY(w.keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
-    CM_TRY(w.items0.ensure(8 * (size_t)std::max(item_total, 1L)));
-    launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
-                      w.items0.as<uint64_t>(), st);
-    M->stats.kernel_launches += 1;
-    CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
-    M->stats.elements_applied += elem_total;
-    return CM_OK;
+    return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
   };
 
   // -- exchange lanes of the transport (values + metadata only without p2p; COO always) ---------
@@ -1134,7 +1214,23 @@ int commit_exchange(cm_matrix *M) {
     M->dbg_valid = true;
   }
 
-  if (!pipelined) CM_TRY(apply_chunks(0, K, M->work[0], M->stream, 0));
+  if (deferred) {
+    // log instead of apply: the messages of this commit stay where they landed
+    for (int k = 0; k < K; ++k)
+      for (int src = 0; src < P; ++src) {
+        const MsgCounts &c = counts[cidx(src, k, me)];
+        if (c.nvals == 0) continue;
+        M->pend.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, src)],
+                                            static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, src)] * esz,
+                                            c.nseg, c.nitems, c.nelems});
+      }
+    for (int d = 0; d < P; ++d) {
+      M->pend_v[d] = rbase_v[ridx(d, K - 1, P - 1) + 1];
+      M->pend_m[d] = rbase_m[ridx(d, K - 1, P - 1) + 1];
+    }
+  } else if (!pipelined) {
+    CM_TRY(apply_chunks(0, K, M->work[0], M->stream, 0));
+  }
   if (M->dma && P > 1 && !pipelined) {  // my pushes are complete before anyone may reuse the arenas
     for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
       CM_CUDA_TRY(cudaEventRecord(M->ev_xfer[x], M->xfer_stream[x]));
@@ -1148,6 +1244,18 @@ int commit_exchange(cm_matrix *M) {
     CM_TRY(apply_coo_blob(M, blob, n));
   }
   CM_CUDA_TRY(cudaGetLastError());
+  if (deferred) {
+    // delivery is complete (the barrier behind the pack kernels) once this stream has drained; the
+    // log is append-only, so no second barrier is needed before the next commit may store
+    CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+    CM_CUDA_TRY(cudaGetLastError());
+    resolve_timers(M);
+    clear_staged(M);
+    bool over = false;  // same decision on every rank
+    for (int d = 0; d < P; ++d) over = over || (size_t)M->pend_v[d] * esz > M->defer_budget;
+    if (over) CM_TRY(materialize_all(M));
+    return CM_OK;
+  }
   // -- quiescence: everybody has applied everything (reference :737-741) --------------------
   CM_TRY(commit_barrier(M, M->stream));
   CM_CUDA_TRY(cudaGetLastError());
@@ -1471,6 +1579,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->cap_vals.assign(M->P, 0);
   M->cap_meta.assign(M->P, 0);
   M->peer_arena_open.assign(M->P, false);
+  M->pend_v.assign(M->P, 0);
+  M->pend_m.assign(M->P, 0);
   {
     // peer-to-peer stores need every rank to be able to map every other rank's memory
     int mine_ok = flags_ok ? 1 : 0;
@@ -1511,6 +1621,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
 int cm_destroy(cm_matrix *M) {
   if (!M) return CM_OK;
   int rc = do_commit(M);  // :458
+  if (rc == CM_OK) rc = materialize_all(M);
   cudaStreamSynchronize(M->stream);
   for (int r = 0; r < M->P; ++r) {
     if (M->peer_ipc_open[r]) cudaIpcCloseMemHandle(M->peer_local[r]);
@@ -1629,6 +1740,7 @@ int cm_fill_lower(cm_matrix *M) {
   // (k,l) = local[l + k*LLD] goes to global (row = gcol(k), col = grow(l)) iff row > col, which
   // is the loop at :696-709 (ix = global column of local column j, jx = global row of local row i).
   const Geom &g = M->g;
+  CM_TRY(materialize_local(M));  // the payload is the local block itself: it must be current
   CM_TRY(M->d_fill_ix.ensure(8 * (size_t)M->n_local));
   CM_TRY(M->d_fill_jx.ensure(8 * (size_t)M->m_local));
   launch_iota_global(M->d_fill_ix.as<long>(), M->n_local, g.nb, g.npcol, g.mypcol, M->stream);
@@ -1657,6 +1769,7 @@ int cm_commit(cm_matrix *M) {
 int cm_reset(cm_matrix *M) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   CM_TRY(do_commit(M));  // :493
+  CM_TRY(materialize_all(M));
   CM_CUDA_TRY(cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream));  // :496-497
   M->mirror_valid = false;
   return M->ctx->tp->barrier(M->stream);  // :500
@@ -1664,12 +1777,14 @@ int cm_reset(cm_matrix *M) {
 
 int cm_local_data_device(cm_matrix *M, const void **out) {
   if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
+  CM_TRY(materialize_local(M));
   *out = M->d_local;
   return CM_OK;
 }
 
 int cm_local_data_copy(cm_matrix *M, void *dst_host) {
   if (!M || !dst_host) return fail(CM_ERR_INVALID, "null argument");
+  CM_TRY(materialize_local(M));
   CM_CUDA_TRY(cudaMemcpyAsync(dst_host, M->d_local, M->local_elems * M->esz, cudaMemcpyDeviceToHost, M->stream));
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
   M->stats.d2h_bytes += (long)(M->local_elems * M->esz);
@@ -1683,6 +1798,7 @@ int cm_local_data_host(cm_matrix *M, const void **out) {
     if (!M->h_mirror) return fail(CM_ERR_NOMEM, "host mirror allocation failed");
     M->mirror_valid = false;
   }
+  CM_TRY(materialize_local(M));  // may invalidate the mirror
   if (!M->mirror_valid) {
     CM_TRY(cm_local_data_copy(M, M->h_mirror));
     M->mirror_valid = true;
@@ -1755,6 +1871,7 @@ int cm_save(cm_matrix *M, const char *fname) {
 int cm_load(cm_matrix *M, const char *fname) {
   if (!M || !fname) return fail(CM_ERR_INVALID, "null argument");
   Transport *tp = M->ctx->tp;
+  CM_TRY(materialize_all(M));      // what was committed before the load is applied before it
   CM_TRY(tp->barrier(M->stream));  // :898
   std::vector<unsigned char> host(M->local_elems * M->esz, 0);  // padding rows stay zero
   int rc = CM_OK;
@@ -1784,6 +1901,10 @@ int cm_get(cm_matrix *M, long i, long j, void *out) {
   cm_owner_of(i, j, M->g.nprow, M->g.npcol, M->g.mb, M->g.nb, M->g.lld, &rank, &ij);
   if (rank < 0 || rank >= M->P || !M->peer_local[rank])
     return fail(CM_ERR_STATE, "local block of rank %d is not mapped on rank %d (CUDA IPC unavailable)", rank, M->me);
+  if (rank == M->me) CM_TRY(materialize_local(M));
+  else if (!M->pend_v.empty() && (M->pend_v[rank] || M->pend_m[rank]))
+    return fail(CM_ERR_STATE, "rank %d holds committed updates it has not applied yet (deferred scatter-add): "
+                "call cm_materialize (collective) before one-sided reads", rank);
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
   CM_CUDA_TRY(cudaMemcpy(out, static_cast<const char *>(M->peer_local[rank]) + (size_t)ij * M->esz, M->esz,
                          cudaMemcpyDefault));
@@ -1829,6 +1950,22 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density) {
   if (tile_density > 0) M->tile_density = tile_density;
   return CM_OK;
 }
+int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (policy != CM_APPLY_EAGER && policy != CM_APPLY_DEFERRED)
+    return fail(CM_ERR_INVALID, "apply policy must be CM_APPLY_EAGER (0) or CM_APPLY_DEFERRED (1)");
+  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the apply policy only with nothing staged");
+  CM_TRY(materialize_all(M));
+  M->apply_policy = policy;
+  if (budget_bytes > 0) M->defer_budget = (size_t)budget_bytes;
+  return M->ctx->tp->barrier(M->stream);
+}
+int cm_get_apply_policy(const cm_matrix *M) { return M ? M->apply_policy : -1; }
+int cm_materialize(cm_matrix *M) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  return materialize_all(M);
+}
+
 int cm_set_exchange_mode(cm_matrix *M, int mode) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   if (mode < 0 || mode > 3)
@@ -1838,6 +1975,7 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
     return fail(CM_ERR_STATE, "peer-to-peer exchange needs every rank's memory mapped (CUDA IPC unavailable)");
   if (mode == 3 && M->P > 1 && !M->ctx->tp->same_process() && stream_wait_value32() == nullptr)
     return fail(CM_ERR_STATE, "copy-engine exchange needs cuStreamWaitValue32");
+  CM_TRY(materialize_all(M));  // the arenas are about to be released
   M->exchange_mode = mode;
   M->p2p = M->P > 1 && M->p2p_possible && mode != 1;
   M->dma = M->p2p && mode == 3;

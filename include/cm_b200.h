@@ -189,6 +189,24 @@ int cm_set_sorted_sweep(cm_matrix *M, int on);
  * current value (default 0.25). Deterministic mode always uses column tiles. */
 int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
 
+/* When the owner scatter-adds what commit() delivered (COLLECTIVE, nothing staged; extension — the
+ * reference applies inside progress(), :178-187, and commit() waits for it, :737-738).
+ * CM_APPLY_EAGER (default): inside commit(), as the reference's commit() guarantees.
+ * CM_APPLY_DEFERRED (several ranks, peer-to-peer exchange modes): commit() returns when every message
+ * has been DELIVERED into the owners' receive arenas, which become an append-only log; the owner
+ * applies its log when its local block is read (cm_local_data_*, cm_get of an own element,
+ * cm_fill_lower, cm_save), when the log of any owner exceeds budget_bytes (everybody applies, inside
+ * that commit) or at cm_materialize / cm_reset / cm_load / cm_destroy. One scatter-add over several
+ * commits' messages sweeps the local block once instead of once per commit.
+ * One-sided reads of ANOTHER rank's element (cm_get) fail with CM_ERR_STATE while that rank may hold
+ * unapplied updates: call cm_materialize first. budget_bytes <= 0 keeps the current budget (8 GiB). */
+#define CM_APPLY_EAGER 0
+#define CM_APPLY_DEFERRED 1
+int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes);
+int cm_get_apply_policy(const cm_matrix *M);
+/* COLLECTIVE: every rank applies its log, then a barrier; afterwards every local block is current. */
+int cm_materialize(cm_matrix *M);
+
 /* How commit() moves the per-owner messages (COLLECTIVE: same call on every rank, nothing staged):
  * 0 = auto, 1 = grouped ncclSend/ncclRecv all-to-all-v from a local send arena, 2 = peer-to-peer
  * stores: the pack kernel writes each message straight into the owner's receive arena over NVLink

@@ -196,6 +196,11 @@ class ConvergentMatrix {
   void descinit(int ictxt, int desc[9]) const { internal::check(cm_descinit(h_, ictxt, desc), "descinit"); }
 
   // knobs without a reference counterpart
+  // extension: deferred scatter-add (cm_b200.h, cm_set_apply_policy); both calls are collective
+  void apply_policy(int policy, long budget_bytes = 0) {
+    internal::check(cm_set_apply_policy(h_, policy, budget_bytes), "apply_policy");
+  }
+  void materialize() { internal::check(cm_materialize(h_), "materialize"); }
   void deterministic(bool on) { internal::check(cm_set_deterministic(h_, on ? 1 : 0), "deterministic"); }
   cm_matrix *handle() const { return h_; }
 

@@ -87,6 +87,9 @@ def make_scenario(rng):
             steps.append(("reset",))
     knobs = dict(apply_kernel=int(rng.choice([0, 1, 2])), sorted_sweep=bool(rng.random() < 0.8),
                  deterministic=bool(rng.random() < 0.25), exchange_mode=int(rng.choice([0, 1, 2, 3])))
+    if cfg.P > 1 and knobs["exchange_mode"] != 1 and rng.random() < 0.35:  # deferred scatter-add (peer-to-peer modes)
+        knobs["apply_policy"] = 1
+        knobs["defer_budget"] = int(rng.choice([0, 1, 20000, 400000]))
     if cfg.P == 1:
         knobs["exchange_mode"] = 0
         if rng.random() < 0.5:

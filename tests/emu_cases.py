@@ -190,3 +190,80 @@ def flag_barrier_commits():
 
 
 CASES += [("flag_barrier_commits", [()])]
+
+
+# ---- deferred scatter-add (cm_set_apply_policy) ---------------------------------
+def deferred_apply(mode, budget):
+    """commit() only delivers; the log is applied when the block is read, when it outgrows its budget
+    (budget small: every other commit) or when an arena has to grow; several rounds, elemental updates,
+    the symmetric update, fill_lower and reset in between — same local blocks as the eager oracle"""
+    from scenario import run_cuda
+    cfg = Cfg(cm.F64, 900, 900, 2, 2, 32, 32, 512)
+    rng = np.random.default_rng(151)
+    steps = []
+    for rnd in range(5):
+        for r in range(cfg.P):
+            k = 60 + 40 * rnd  # growing messages: the arenas have to grow while a log is pending
+            ix, jx = sorted_unique(rng, cfg.m, k), sorted_unique(rng, cfg.n, k - 10)
+            steps.append(("slice", r, rand_payload(rng, cfg.dtype, (k - 10, k)), k, k - 10, k, False, ix, jx))
+            steps.append(("elems", r, rand_payload(rng, cfg.dtype, 30), rng.integers(0, cfg.m, 30), rng.integers(0, cfg.n, 30)))
+            sx = sorted_unique(rng, cfg.m, 50)
+            steps.append(("sym", r, rand_payload(rng, cfg.dtype, (50, 50)), 50, 50, False, sx))
+        steps.append(("commit",))
+    steps += [("fill_lower",), ("commit",), ("reset",)]
+    steps += slice_steps(cfg, rng, 3, 80, 70, commit_every=1)
+    want = run_checker(cfg, steps)
+    got = run_cuda(cfg, steps, exchange_mode=mode, apply_policy=1, defer_budget=budget)
+    assert_blocks_match(cfg, got, want)
+
+
+def deferred_apply_api():
+    """the log is really deferred (no scatter-add launches at commit), accessors materialise, one-sided
+    reads of a rank with a pending log are refused until cm_materialize, switching back to eager works"""
+    cfg = Cfg(cm.F64, 512, 512, 2, 2, 64, 64, 256)
+    rng = np.random.default_rng(152)
+    world = cm.LoopbackWorld(4, 0)
+    try:
+        mats = world.run(lambda r: cm.Matrix(*cfg.args()))
+        world.run(lambda r: (mats[r].set_exchange_mode(2), mats[r].set_apply_policy(1), mats[r].set_profiling(True)))
+        assert world.on(0, lambda r: mats[r].apply_policy()) == 1
+        dense = np.zeros((cfg.n, cfg.m))
+        for rnd in range(3):
+            for r in range(4):
+                ix, jx = sorted_unique(rng, cfg.m, 100), sorted_unique(rng, cfg.n, 90)
+                data = rand_payload(rng, cfg.dtype, (90, 100))
+                dense[np.ix_(jx, ix)] += data
+                world.on(r, lambda rr: mats[rr].update(data, ix, jx))
+            world.run(lambda r: mats[r].commit())
+        st = world.run(lambda r: mats[r].stats())
+        assert all(s["apply_launches"] == 0 and s["elements_applied"] == 0 and s["commits"] == 3 for s in st), st
+        # element (0, 0) lives on rank 0: its owner may read it, the others may not yet
+        v = world.on(0, lambda r: mats[r].get(0, 0))
+        assert np.isclose(v, dense[0, 0], rtol=1e-12, atol=1e-12)
+        try:
+            world.on(1, lambda r: mats[r].get(0, 0))
+            raise AssertionError("one-sided read of a rank with a pending log must be refused")
+        except cm.CmError:
+            pass
+        world.run(lambda r: mats[r].materialize())
+        assert np.isclose(world.on(1, lambda r: mats[r].get(0, 0)), dense[0, 0], rtol=1e-12, atol=1e-12)
+        st = world.run(lambda r: mats[r].stats())
+        assert all(s["apply_launches"] == 1 for s in st), [s["apply_launches"] for s in st]  # ONE sweep for three commits
+        blocks = world.run(lambda r: mats[r].local())
+        for r in range(4):
+            pr, pc = r // 2, r % 2
+            gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(256)])
+            gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(256)])
+            got = blocks[r].reshape(-1, cfg.lld)[:256, :256]
+            assert np.linalg.norm(got - dense[np.ix_(gj, gi)]) <= 1e-12 * np.linalg.norm(dense)
+        world.run(lambda r: mats[r].set_apply_policy(0))
+        for r in range(4):
+            world.on(r, lambda rr: mats[rr].update(np.ones((4, 4)), np.arange(4, dtype=np.int64), np.arange(4, dtype=np.int64)))
+        world.run(lambda r: mats[r].commit())
+        assert np.isclose(world.on(3, lambda r: mats[r].get(0, 0)), dense[0, 0] + 4.0)
+        world.run(lambda r: mats[r].destroy())
+    finally:
+        world.close()
+
+
+CASES += [("deferred_apply", [(2, 0), (3, 0), (2, 40000), (2, 1)]), ("deferred_apply_api", [()])]

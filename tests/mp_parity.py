@@ -55,6 +55,8 @@ def main():
         M = cm.Matrix(*cfg.args())
         if os.environ.get("CM_TEST_EXCHANGE_MODE"):
             M.set_exchange_mode(int(os.environ["CM_TEST_EXCHANGE_MODE"]))
+        if os.environ.get("CM_TEST_APPLY_POLICY"):  # 1 = deferred scatter-add (peer-to-peer modes)
+            M.set_apply_policy(int(os.environ["CM_TEST_APPLY_POLICY"]), int(os.environ.get("CM_TEST_DEFER_BUDGET", "0")))
         M.keep_wire(True)
         wires = {}
         for st in steps:
@@ -87,6 +89,7 @@ def main():
                 gi, gd = wires.get(d, (np.zeros(0, np.int64), np.zeros(0)))
                 wire_ok &= np.array_equal(gi, wi) and gd.tobytes() == wd.tobytes()
         # one-sided remote read (operator(), :585-596) through CUDA IPC
+        M.materialize()  # no-op under the eager policy
         read_ok = True
         for _ in range(20):
             i, j = int(rng.integers(0, m)), int(rng.integers(0, n))

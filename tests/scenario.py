@@ -67,7 +67,7 @@ def run_checker(cfg, steps, kind="oracle", wire=False, threshold=None):
 
 
 def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, deterministic=False, device_api=False,
-             apply_kernel=0, exchange_mode=0):
+             apply_kernel=0, exchange_mode=0, apply_policy=0, defer_budget=0):
     """Execute on the GPU. P == 1 uses the process runtime, P > 1 the loopback transport
     (threads-as-ranks on one device). device_api=True feeds slices through
     cm_update_slice_device from torch tensors already resident in HBM."""
@@ -95,6 +95,8 @@ def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, determin
             M.set_apply_kernel(apply_kernel)
             if exchange_mode:
                 M.set_exchange_mode(exchange_mode)
+            if apply_policy:
+                M.set_apply_policy(apply_policy, defer_budget)
         run(setup)
         wires = {}
         for st in steps:

@@ -38,6 +38,8 @@ GROUPS = [
     "panels_wire_and_blocks",
     "panels_unsorted_masked_and_mixed_sources",
     "flag_barrier_commits",
+    "deferred_apply",
+    "deferred_apply_api",
 ]
 
 
