@@ -541,33 +541,38 @@ __device__ __forceinline__ bool mask_keep(int mask, long grow, long gcol) {
   return mask == 1 ? (grow <= gcol) : (grow > gcol);
 }
 
-template <typename T>
+// G = lanes that share one item: 32 (a warp per item) for ordinary items; 16 or 8 when the items of a
+// flush are tiny on average (a 32 x 32 update on a 4 x 2 grid leaves 8-row items), so that a warp
+// works on 2 or 4 items at a time instead of idling three quarters of its lanes.
+template <typename T, int G>
 __global__ void __launch_bounds__(256) k_apply_red(const ItemRec *__restrict__ recs, long nitems, T *__restrict__ local,
                                                    Geom g) {
+  constexpr int kPerWarp = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int sub = lane % G, grp = lane / G;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long t = warp; t < nitems; t += nwarps) {
+  for (long t = warp * kPerWarp + grp; t < nitems; t += nwarps * kPerWarp) {
     const ItemRec r = recs[t];
     T *__restrict__ dcol = local + (long)r.col * g.lld;
     const T *__restrict__ v = static_cast<const T *>(r.v);
     const int *__restrict__ lrow = r.lrow;
     const int mask = r.mask_flags & 0xff;
     if (mask == 0 && r.row_stride == 1) {
-      int a = lane;
+      int a = sub;
       // 4 independent value/index loads in flight per lane before the REDs
-      for (; a + 96 < r.n; a += 128) {
-        const T x0 = v[a], x1 = v[a + 32], x2 = v[a + 64], x3 = v[a + 96];
-        const int r0 = lrow[a], r1 = lrow[a + 32], r2 = lrow[a + 64], r3 = lrow[a + 96];
+      for (; a + 3 * G < r.n; a += 4 * G) {
+        const T x0 = v[a], x1 = v[a + G], x2 = v[a + 2 * G], x3 = v[a + 3 * G];
+        const int r0 = lrow[a], r1 = lrow[a + G], r2 = lrow[a + 2 * G], r3 = lrow[a + 3 * G];
         red_add(dcol + r0, x0);
         red_add(dcol + r1, x1);
         red_add(dcol + r2, x2);
         red_add(dcol + r3, x3);
       }
-      for (; a < r.n; a += 32) red_add(dcol + lrow[a], v[a]);
+      for (; a < r.n; a += G) red_add(dcol + lrow[a], v[a]);
     } else {
       const long gcol = global_index(r.col, g.nb, g.npcol, g.mypcol);
-      for (int a = lane; a < r.n; a += 32) {
+      for (int a = sub; a < r.n; a += G) {
         const int row = lrow[a];
         if (mask != 0 && !mask_keep(mask, global_index(row, g.mb, g.nprow, g.myprow), gcol)) continue;
         red_add(dcol + row, v[(long)a * r.row_stride]);
@@ -586,20 +591,33 @@ static int resident_blocks(K kernel, int threads, size_t smem) {
   return per_sm * kernel_sm_count();
 }
 
-template <typename T>
-static void launch_apply_red_t(const ItemRec *d_recs, long nitems, T *d_local, const Geom &g, cudaStream_t s) {
+template <typename T, int G>
+static void launch_apply_red_g(const ItemRec *d_recs, long nitems, T *d_local, const Geom &g, cudaStream_t s) {
   // exactly one resident wave: the strided item order is also the time order of the sweep
-  static const int resident = resident_blocks(k_apply_red<T>, 256, 0);
-  const long blocks = std::min((nitems + 7) / 8, (long)resident);
-  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_red<T>)(d_recs, nitems, d_local, g);
+  static const int resident = resident_blocks(k_apply_red<T, G>, 256, 0);
+  constexpr int kPerBlock = 8 * (32 / G);
+  const long blocks = std::min((nitems + kPerBlock - 1) / kPerBlock, (long)resident);
+  CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_red<T, G>)(d_recs, nitems, d_local, g);
 }
 
-void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_local, const Geom &g, cudaStream_t s) {
+template <typename T>
+static void launch_apply_red_t(const ItemRec *d_recs, long nitems, long elements, T *d_local, const Geom &g, cudaStream_t s) {
+  const long avg = elements / std::max(nitems, 1L);  // rows per item
+  if (avg <= 8)
+    launch_apply_red_g<T, 8>(d_recs, nitems, d_local, g, s);
+  else if (avg <= 16)
+    launch_apply_red_g<T, 16>(d_recs, nitems, d_local, g, s);
+  else
+    launch_apply_red_g<T, 32>(d_recs, nitems, d_local, g, s);
+}
+
+void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elements, void *d_local, const Geom &g,
+                      cudaStream_t s) {
   if (nitems <= 0) return;
   switch (dtype) {
-    case 0: launch_apply_red_t(d_recs, nitems, static_cast<double *>(d_local), g, s); break;
-    case 1: launch_apply_red_t(d_recs, nitems, static_cast<float *>(d_local), g, s); break;
-    default: launch_apply_red_t(d_recs, nitems, static_cast<int *>(d_local), g, s); break;
+    case 0: launch_apply_red_t(d_recs, nitems, elements, static_cast<double *>(d_local), g, s); break;
+    case 1: launch_apply_red_t(d_recs, nitems, elements, static_cast<float *>(d_local), g, s); break;
+    default: launch_apply_red_t(d_recs, nitems, elements, static_cast<int *>(d_local), g, s); break;
   }
 }
 

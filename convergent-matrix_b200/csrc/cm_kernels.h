@@ -68,7 +68,7 @@ int tile_count(int dtype, long m_local);  // column tiles stacked over the local
 void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, const uint64_t *d_items,
                        long nitems, ItemRec *d_recs, long n_local, long *d_col_start, cudaStream_t s);
 // (6a) scatter-add with RED.ADD, one warp per item (apply<T>, reference :178-187)
-void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, void *d_local, const Geom &g,
+void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elements, void *d_local, const Geom &g,
                       cudaStream_t s);
 // (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,

@@ -529,7 +529,7 @@ int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, lon
       launch_apply_tile(M->dtype, w.recs.as<ItemRec>(), w.col_start.as<long>(), nitems, M->d_local, M->n_local,
                         M->m_local, M->g, max_blocks_per_sm, tma_hint, st);
     else
-      launch_apply_red(M->dtype, w.recs.as<ItemRec>(), nitems, M->d_local, M->g, st);
+      launch_apply_red(M->dtype, w.recs.as<ItemRec>(), nitems, elements, M->d_local, M->g, st);
     M->stats.kernel_launches += 1;
     if (tile) M->stats.tile_launches += 1;
   }
