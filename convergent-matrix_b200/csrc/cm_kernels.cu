@@ -229,7 +229,9 @@ void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &
 constexpr int kPackThreads = 384;
 constexpr int kPackMaxDst = 1024;  // (k1 - k0) * P destinations per launch
 
-template <typename T>
+// NC = columns a thread keeps in flight (4; 8 = opt-in CM_B200_PACK_COLS=8: twice the bytes in flight per
+// thread, for when the kernel shares the SMs with a scatter-add and has fewer resident threads)
+template <typename T, int NC>
 __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1, PanelPlan pp,
                                                        Geom g, MapArenas ma, ScanArenas sa) {
   const int u = blockIdx.x;
@@ -280,26 +282,26 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
     T *const *brow = base + p * npcol;
     int kc = cbeg + (int)blockIdx.y;
     int gq = k0 * npcol;  // column group of the current column: only moves forward
-    // four columns in flight per thread
-    for (; kc + 3 * gy < cend; kc += 4 * gy) {
-      T x[4];
-      T *out[4];
-      int cp[4];
-      // the four source-column positions first (independent loads), then the four gathers that
-      // depend on them; the destination lookups (shared memory) fill the wait
+    // NC columns in flight per thread
+    for (; kc + (NC - 1) * gy < cend; kc += NC * gy) {
+      T x[NC];
+      T *out[NC];
+      int cp[NC];
+      // the source-column positions first (independent loads), then the gathers that depend on
+      // them; the destination lookups (shared memory) fill the wait
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cp[i] = cpos[kc + i * gy];
+      for (int i = 0; i < NC; ++i) cp[i] = cpos[kc + i * gy];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NC; ++i) {
         const int c = kc + i * gy;
         while (c >= coff[gq + 1]) ++gq;
         out[i] = brow[gdst[gq]] + (long)(c - coff[gq]) * stride + a;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = live ? data[srow + (long)cp[i] * src_cs] : T(0);
+      for (int i = 0; i < NC; ++i) x[i] = live ? data[srow + (long)cp[i] * src_cs] : T(0);
       if (live) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *out[i] = x[i];
+        for (int i = 0; i < NC; ++i) *out[i] = x[i];
       }
     }
     for (; kc < cend; kc += gy) {
@@ -361,10 +363,19 @@ void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, co
                  const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
   if (nupd <= 0 || k1 <= k0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
+  static const int ncols = getenv("CM_B200_PACK_COLS") ? atoi(getenv("CM_B200_PACK_COLS")) : 4;
+  if (ncols == 8) {
+    switch (dtype) {
+      case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    }
+    return;
+  }
   switch (dtype) {
-    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
   }
 }
 

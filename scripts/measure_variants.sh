@@ -36,6 +36,8 @@ run k1-batch CM_B200_PIPELINE=0 -- --steps 5 --warmup 3
 for AB in 1 2 3; do
   run k1-panels4-ab$AB CM_B200_PIPELINE=1 CM_B200_PIPELINE_APPLY_BLOCKS=$AB -- --steps 5 --warmup 3
 done
+run k1-batch-cols8 CM_B200_PIPELINE=0 CM_B200_PACK_COLS=8 -- --steps 5 --warmup 3
+run k1-panels4-ab2-cols8 CM_B200_PIPELINE=1 CM_B200_PIPELINE_APPLY_BLOCKS=2 CM_B200_PACK_COLS=8 -- --steps 5 --warmup 3
 run k1-panels2 CM_B200_PIPELINE=1 CM_B200_PANELS=2 -- --steps 5 --warmup 3
 run k1-panels4-flags CM_B200_PIPELINE=1 CM_B200_FLAG_BARRIER=1 -- --steps 5 --warmup 3
 
