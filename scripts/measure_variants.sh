@@ -24,6 +24,20 @@ parity() {  # parity <label> <env...>
   echo "rc=$?"
 }
 
+if [ "$N" = "1" ]; then
+  # single GPU: the suite, the default bench line, then (only after both exited 0) the two ncu passes of
+  # B200_PROFILING.md on the same command: launch list (shares of the step) and one full capture of the
+  # scatter-add kernel
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+  python bench.py --steps 5 --warmup 3 | tail -1 | tee gpurun_out/bench_k1_n1.json
+  B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --latency-reps 2"
+  $B > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 400 --csv \
+      --log-file gpurun_out/launches_k1_n1.csv $B > gpurun_out/ncu_launches.log 2>&1
+  $B > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_apply_tile -s 10 -c 2 \
+      -o gpurun_out/k_apply_tile_k1_n1 -f $B > gpurun_out/ncu_full.log 2>&1
+  exit 0
+fi
+
 # 1. parity of the new paths over real NVLink / NCCL first (small commits: thresholds lowered)
 parity baseline CM_B200_PIPELINE=0
 parity panels CM_B200_PIPELINE=1 CM_B200_PIPELINE_MIN_ELEMS=1
