@@ -267,3 +267,46 @@ def deferred_apply_api():
 
 
 CASES += [("deferred_apply", [(2, 0), (3, 0), (2, 40000), (2, 1)]), ("deferred_apply_api", [()])]
+
+
+def two_matrices_and_batch_api():
+    """two instances alive at once with interleaved updates and commits (arenas, flags and logs are per
+    instance), fed through the batch forms of the host and device APIs"""
+    cfgA = Cfg(cm.F64, 700, 500, 2, 2, 32, 32, 384)
+    cfgB = Cfg(cm.F32, 300, 900, 2, 2, 16, 64, 160)
+    rng = np.random.default_rng(161)
+    world = cm.LoopbackWorld(4, 0)
+    try:
+        A = world.run(lambda r: cm.Matrix(*cfgA.args()))
+        B = world.run(lambda r: cm.Matrix(*cfgB.args()))
+        world.run(lambda r: B[r].set_apply_policy(1))
+        stepsA, stepsB, keep = [], [], []
+        for rnd in range(3):
+            for r in range(4):
+                for cfg, mats, steps, device in ((cfgA, A, stepsA, False), (cfgB, B, stepsB, True)):
+                    cnt, m_u, n_u = 3, 40 + 10 * rnd, 30
+                    data = np.ascontiguousarray(rand_payload(rng, cfg.dtype, (cnt, n_u, m_u)))
+                    ix = np.ascontiguousarray(np.stack([sorted_unique(rng, cfg.m, m_u) for _ in range(cnt)]))
+                    jx = np.ascontiguousarray(np.stack([sorted_unique(rng, cfg.n, n_u) for _ in range(cnt)]))
+                    keep.append((data, ix, jx))
+                    for u in range(cnt):
+                        steps.append(("slice", r, data[u], m_u, n_u, m_u, False, ix[u], jx[u]))
+                    batch = cm.SliceBatch(cnt, m_u, n_u, data.ctypes.data, ix.ctypes.data, jx.ctypes.data, data.itemsize)
+                    world.on(r, lambda rr: mats[rr].update_batch(batch, device))
+            world.run(lambda r: A[r].commit())
+            stepsA.append(("commit",))
+            if rnd != 1:  # B commits less often than A
+                world.run(lambda r: B[r].commit())
+                stepsB.append(("commit",))
+        world.run(lambda r: B[r].commit())
+        stepsB.append(("commit",))
+        for cfg, mats, steps in ((cfgA, A, stepsA), (cfgB, B, stepsB)):
+            got = {"local": world.run(lambda r: mats[r].local()), "m_local": world.run(lambda r: mats[r].m_local),
+                   "n_local": world.run(lambda r: mats[r].n_local)}
+            assert_blocks_match(cfg, got, run_checker(cfg, steps))
+        world.run(lambda r: (A[r].destroy(), B[r].destroy()))
+    finally:
+        world.close()
+
+
+CASES += [("two_matrices_and_batch_api", [()])]

@@ -40,6 +40,7 @@ GROUPS = [
     "flag_barrier_commits",
     "deferred_apply",
     "deferred_apply_api",
+    "two_matrices_and_batch_api",
 ]
 
 
