@@ -627,6 +627,36 @@ StreamWaitValue32Fn stream_wait_value32() {
   return fn;
 }
 
+// flags of a flag wait: "greater or equal", plus — where the device supports it — a flush of outstanding
+// remote writes, so that data a peer stored BEFORE the flag is visible to the work behind the wait
+unsigned wait_value_flags() {
+  static const unsigned flags = [] {
+    int dev = 0, can = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&can, cudaDevAttrCanFlushRemoteWrites, dev) != cudaSuccess) {
+      cudaGetLastError();
+      can = 0;
+    }
+    return /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0u | (can == 1 ? /*CU_STREAM_WAIT_VALUE_FLUSH*/ (1u << 30) : 0u);
+  }();
+  return flags;
+}
+
+// stream-ordered wait until *(uint32_t *)addr >= value; 0 on success
+int wait_value_geq(cudaStream_t st, const void *addr, uint32_t value) {
+  StreamWaitValue32Fn wait32 = stream_wait_value32();
+  if (!wait32) return -1;
+  static bool flush_ok = true;  // a refused FLUSH flag is dropped for good (benign race: same value)
+  const unsigned flags = flush_ok ? wait_value_flags() : 0x0u;
+  int rc = wait32(st, (unsigned long long)(uintptr_t)addr, value, flags);
+  if (rc != 0 && flags != 0x0u) {
+    cudaGetLastError();
+    flush_ok = false;
+    rc = wait32(st, (unsigned long long)(uintptr_t)addr, value, 0x0u);
+  }
+  return rc;
+}
+
 // ---- barriers of a commit ------------------------------------------------------------------
 // stream-ordered: work enqueued on `st` afterwards starts only when every rank's stream has reached
 // its own call. Default: the transport's (a 1-element ncclAllReduce); opt-in: flags over peer memory.
@@ -642,7 +672,7 @@ int commit_stream_barrier(cm_matrix *M, cudaStream_t st) {
   const char *row = M->d_flags.as<char>() + 4 * (size_t)M->P;
   for (int r = 0; r < M->P; ++r) {
     if (r == M->me) continue;
-    const int rc = wait32(st, (unsigned long long)(uintptr_t)(row + 4 * (size_t)r), seq, /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0);
+    const int rc = wait_value_geq(st, row + 4 * (size_t)r, seq);
     if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
   }
   return CM_OK;
@@ -1088,11 +1118,9 @@ int commit_exchange(cm_matrix *M) {
       CM_TRY(tp->stream_barrier(M->xfer_stream[0]));
       return CM_OK;
     }
-    StreamWaitValue32Fn wait32 = stream_wait_value32();
     for (int r = 0; r < P; ++r) {
       if (r == me) continue;
-      const int rc = wait32(waiter, (unsigned long long)(uintptr_t)(M->d_flags.as<char>() + 4 * (size_t)r), seq,
-                            /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0);
+      const int rc = wait_value_geq(waiter, M->d_flags.as<char>() + 4 * (size_t)r, seq);
       if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
     }
     return CM_OK;

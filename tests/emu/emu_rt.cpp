@@ -272,7 +272,11 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
   p->minor = 0;
   return cudaSuccess;
 }
-cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) {
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
+  if (a != cudaDevAttrMultiProcessorCount) {
+    *v = 0;
+    return cudaSuccess;
+  }
   const char *e = getenv("CM_EMU_SMS");
   *v = e ? atoi(e) : 3;  // few "SMs": persistent kernels really loop, odd count exercises remainders
   return cudaSuccess;
