@@ -662,9 +662,8 @@ int wait_value_geq(cudaStream_t st, const void *addr, uint32_t value) {
 // its own call. Default: the transport's (a 1-element ncclAllReduce); opt-in: flags over peer memory.
 int commit_stream_barrier(cm_matrix *M, cudaStream_t st) {
   Transport *tp = M->ctx->tp;
-  StreamWaitValue32Fn wait32 = nullptr;
   const bool flags = M->P > 1 && M->p2p && M->flag_barrier > 0 && (M->flag_barrier > 1 || !tp->same_process()) &&
-                     (wait32 = stream_wait_value32()) != nullptr;
+                     stream_wait_value32() != nullptr;
   if (!flags) return tp->stream_barrier(st);
   const uint32_t seq = ++M->bar_seq;
   launch_signal_peers(M->d_peer_rows.as<uint32_t *>(), M->me, M->P, seq, st);
