@@ -221,6 +221,33 @@ void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &
 }
 
 // ------------------------------------------------------------------------------------
+// (2b) device-side layout: thread d walks owner d's arena in the order the host does (panel after
+// panel, source after source; cm_matrix.cu, commit_exchange) and notes where THIS rank's messages start.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_layout(const MsgCounts *__restrict__ counts, int P, int me, int esz, ArenaTable at,
+                                                void **__restrict__ dst_vals, char **__restrict__ dst_meta, int *overflow) {
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P; d += gridDim.x * blockDim.x) {
+    long ov = at.base_v[d], om = at.base_m[d];
+    for (int k = 0; k < kMaxChunks; ++k)
+      for (int src = 0; src < P; ++src) {
+        const MsgCounts c = counts[((long)src * kMaxChunks + k) * P + d];
+        if (src == me) {
+          dst_vals[k * P + d] = at.vals[d] + ov * esz;
+          dst_meta[k * P + d] = at.meta[d] + om;
+        }
+        ov += (c.nvals + 31) & ~31L;  // every message on a 256-byte boundary
+        om += meta_bytes(c.nseg, c.nidx);
+      }
+    if (ov * esz > at.cap_vals[d] || om > at.cap_meta[d]) atomicOr(overflow, 1);
+  }
+}
+
+void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, const ArenaTable &at, void **dst_vals,
+                   char **dst_meta, int *overflow, cudaStream_t s) {
+  CM_LAUNCH((nranks + 255) / 256, 256, 0, s, k_layout)(d_counts_all, nranks, me, esz, at, dst_vals, dst_meta, overflow);
+}
+
+// ------------------------------------------------------------------------------------
 // (3) pack. grid (nupd, ytiles): block (u, y) handles the grouped columns y, y+ytiles, ... of the
 // panels [k0, k1) of update u: for every owner row p it gathers the rows R_p of that column into
 // the (panel, p, q) segment — contiguous, coalesced stores; gathers hit every sector of the source
@@ -234,6 +261,7 @@ constexpr int kPackMaxDst = 1024;  // (k1 - k0) * P destinations per launch
 template <typename T, int NC>
 __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1, PanelPlan pp,
                                                        Geom g, MapArenas ma, ScanArenas sa) {
+  if (sa.overflow != nullptr && *sa.overflow != 0) return;  // speculative launch, an arena has to grow first
   const int u = blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;

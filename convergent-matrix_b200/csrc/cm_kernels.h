@@ -36,6 +36,17 @@ struct ScanArenas {
   MsgCounts *totals;  // [kMaxChunks * P], index panel * P + owner
   void **dst_vals;    // [kMaxChunks * P] where this rank's message (panel, owner) starts: values ...
   char **dst_meta;    // ... and metadata. May point into a PEER's receive arena (NVLink stores).
+  const int *overflow;  // device-side layout only (launch_layout): non-zero = some arena is too small, pack nothing
+};
+
+// what the device-side layout needs to know about every owner's receive arenas
+struct ArenaTable {
+  char *const *vals;    // [P] base of owner d's values arena as mapped on this rank
+  char *const *meta;    // [P] ... metadata arena
+  const long *cap_vals; // [P] capacities in bytes
+  const long *cap_meta;
+  const long *base_v;   // [P] first free element / byte (non-zero only while a deferred log is pending)
+  const long *base_m;
 };
 
 size_t dtype_size(int dtype);
@@ -46,6 +57,11 @@ void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const Pan
 // (2) per-owner scans over the staged updates (sizes of every message)
 void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
                  const long *d_coo_counts, cudaStream_t s);
+// (2b) device-side layout of this rank's messages inside the owners' receive arenas, from the
+// all-gathered counts [src][panel][dst] (same arithmetic as the host's): fills sa.dst_vals / dst_meta and
+// raises *overflow when any arena is too small. Lets the pack kernel start without a host round trip.
+void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, const ArenaTable &at, void **dst_vals,
+                   char **dst_meta, int *overflow, cudaStream_t s);
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
 // Packs the column panels [k0, k1) of every staged update.

@@ -280,6 +280,16 @@ struct cm_matrix {
   // every peer's number has arrived in its own row. Replaces the 1-element ncclAllReduce of a commit's
   // barriers; opt-in (CM_B200_FLAG_BARRIER=1) until measured. =2 also allows it between rank threads
   // of one process (kernel-logic tests only).
+  // Device-side layout (opt-in, CM_B200_DEVICE_LAYOUT=1; peer-to-peer stores, one-panel commits): a
+  // small kernel computes where this rank's messages go from the all-gathered counts and the pack
+  // kernel is launched right behind it, BEFORE the host has read the counts; the host's read-back of
+  // the counts (still needed for the owner side and for growth) overlaps the pack. If an arena turns
+  // out too small the speculative pack does nothing (same verdict on every rank) and the host path runs.
+  int device_layout = 0;
+  bool arena_tab_dirty = true;
+  DevBuf d_arena_tab;  // [6][P]: vals base, meta base, cap_vals, cap_meta, base_v, base_m
+  DevBuf d_overflow;
+  PinBuf h_overflow;
   int flag_barrier = 0;
   uint32_t bar_seq = 0;
   DevBuf d_peer_rows;  // [P] device pointers: peer r's barrier row
@@ -751,6 +761,7 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
     M->cap_vals[d] = grown(need_vals[d]);
     M->cap_meta[d] = grown(need_meta[d]);
   }
+  M->arena_tab_dirty = true;
   return CM_OK;
 }
 
@@ -814,6 +825,7 @@ int materialize_all(cm_matrix *M) {
   M->pend_applied = 0;
   std::fill(M->pend_v.begin(), M->pend_v.end(), 0L);
   std::fill(M->pend_m.begin(), M->pend_m.end(), 0L);
+  M->arena_tab_dirty = true;  // the device-side copy of the log offsets is stale now
   return CM_OK;
 }
 
@@ -868,6 +880,7 @@ int commit_exchange(cm_matrix *M) {
   sa.totals = M->d_totals.as<MsgCounts>();
   sa.dst_vals = M->d_dst_ptrs.as<void *>();
   sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
+  sa.overflow = nullptr;
   cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
   if (M->profiling) {
     ev_pack0 = get_event(M);
@@ -890,9 +903,51 @@ int commit_exchange(cm_matrix *M) {
   CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, per_rank, M->stream));
   CM_TRY(M->h_counts.ensure(per_rank * P + 8 * (size_t)P * P));
   MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][chunk][dst]
+  // -- device-side layout + speculative pack (opt-in): nothing below this point needs the host to know
+  // the counts before the pack kernel may run; the read-back overlaps it
+  const bool spec_pack = M->device_layout && P > 1 && M->p2p && !M->dma && pp.npanel == 1 && nupd > 0 &&
+                         !(M->dma ? M->pipeline != 0 : M->pipeline == 1);
+  if (spec_pack) {
+    const bool log_pending = M->apply_policy != 0;
+    CM_TRY(M->d_arena_tab.ensure(6 * 8 * (size_t)P));
+    CM_TRY(M->d_overflow.ensure(256));
+    CM_TRY(M->h_overflow.ensure(256));
+    if (M->arena_tab_dirty || log_pending) {
+      std::vector<long> tab(6 * (size_t)P);
+      for (int d = 0; d < P; ++d) {
+        tab[0 * P + d] = (long)(uintptr_t)M->peer_vals[d];
+        tab[1 * P + d] = (long)(uintptr_t)M->peer_meta[d];
+        tab[2 * P + d] = (long)M->cap_vals[d];
+        tab[3 * P + d] = (long)M->cap_meta[d];
+        tab[4 * P + d] = log_pending ? M->pend_v[d] : 0;
+        tab[5 * P + d] = log_pending ? M->pend_m[d] : 0;
+      }
+      CM_CUDA_TRY(cudaMemcpyAsync(M->d_arena_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, M->stream));
+      M->arena_tab_dirty = false;
+    }
+    const long *tab = M->d_arena_tab.as<long>();
+    ArenaTable at;
+    at.vals = reinterpret_cast<char *const *>(tab);
+    at.meta = reinterpret_cast<char *const *>(tab + P);
+    at.cap_vals = tab + 2 * P;
+    at.cap_meta = tab + 3 * P;
+    at.base_v = tab + 4 * P;
+    at.base_m = tab + 5 * P;
+    CM_CUDA_TRY(cudaMemsetAsync(M->d_overflow.p, 0, 4, M->stream));
+    launch_layout(M->d_counts_all.as<MsgCounts>(), P, me, (int)esz, at, sa.dst_vals, sa.dst_meta, M->d_overflow.as<int>(),
+                  M->stream);
+    sa.overflow = M->d_overflow.as<int>();
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, M->stream);
+    M->stats.kernel_launches += 2;
+    if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
+  }
   CM_CUDA_TRY(cudaMemcpyAsync(counts, M->d_counts_all.p, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
+  if (spec_pack) CM_CUDA_TRY(cudaMemcpyAsync(M->h_overflow.p, M->d_overflow.p, 4, cudaMemcpyDeviceToHost, M->stream));
   M->stats.d2h_bytes += (long)(per_rank * P);
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  // the speculative pack ran to completion unless the layout kernel found an arena too small
+  const bool packed = spec_pack && *static_cast<const int *>(M->h_overflow.p) == 0;
+  sa.overflow = nullptr;
   long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + per_rank * P);  // [src][dst]
   for (int src = 0; src < P; ++src)
     for (int d = 0; d < P; ++d) coo_counts[(size_t)src * P + d] = counts[cidx(src, 0, d)].ncoo;
@@ -996,8 +1051,9 @@ int commit_exchange(cm_matrix *M) {
         dst_ptrs[(size_t)K * P + i] = M->d_send_meta.as<char>() + s_meta_base[i];
       }
     }
-  CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
-                              M->stream));
+  if (!packed)
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                                M->stream));
 
   // -- COO blobs (elemental updates): [inds x n][vals x n] per owner, always via the transport --
   auto coo_blob = [esz](long n) { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); };
@@ -1150,12 +1206,12 @@ int commit_exchange(cm_matrix *M) {
 
   if (!pipelined) {
     // one batch: pack everything, (all-to-all-v), barrier, one scatter-add over all messages
-    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, M->stream);
-    M->stats.kernel_launches += nupd ? 1 : 0;
-    if (M->profiling) {
-      cudaEventRecord(ev_pack1, M->stream);
-      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+    if (!packed) {
+      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, M->stream);
+      M->stats.kernel_launches += nupd ? 1 : 0;
+      if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
     }
+    if (M->profiling) M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
     CM_CUDA_TRY(cudaGetLastError());
     CM_TRY(transport_lanes(0, K, true));
     if (M->dma && P > 1) {
@@ -1222,6 +1278,16 @@ int commit_exchange(cm_matrix *M) {
   if (M->keep_wire) {
     // what THIS rank sent to every owner, chunk after chunk, read back from wherever pack put it
     CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+    if (packed) {  // debug mode: the device-side layout must agree with the host's, pointer for pointer
+      std::vector<void *> dev_ptrs(dst_ptrs.size());
+      CM_CUDA_TRY(cudaMemcpy(dev_ptrs.data(), M->d_dst_ptrs.p, dev_ptrs.size() * sizeof(void *), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < K; ++k)
+        for (int d = 0; d < P; ++d)
+          if (counts[cidx(me, k, d)].nvals &&
+              (dev_ptrs[(size_t)k * P + d] != dst_ptrs[(size_t)k * P + d] ||
+               dev_ptrs[(size_t)K * P + (size_t)k * P + d] != dst_ptrs[(size_t)K * P + (size_t)k * P + d]))
+            return fail(CM_ERR_STATE, "device-side layout disagrees with the host layout (panel %d, owner %d)", k, d);
+    }
     M->dbg_msgs.clear();
     for (int d = 0; d < P; ++d)
       for (int k = 0; k < K; ++k) {
@@ -1630,6 +1696,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
     M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
+    if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
     if (M->P > 1 && M->p2p_possible) {
       std::vector<void *> rows(M->P);
       for (int r = 0; r < M->P; ++r) rows[r] = static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)M->P;
@@ -1675,6 +1742,9 @@ int cm_destroy(cm_matrix *M) {
   for (auto e : M->ev_xfer) cudaEventDestroy(e);
   M->d_flags.release();
   M->d_peer_rows.release();
+  M->d_arena_tab.release();
+  M->d_overflow.release();
+  M->h_overflow.release();
   M->h_seq.release();
   for (auto e : M->ev_chunk) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);
@@ -1984,6 +2054,7 @@ int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes) {
   if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the apply policy only with nothing staged");
   CM_TRY(materialize_all(M));
   M->apply_policy = policy;
+  M->arena_tab_dirty = true;
   if (budget_bytes > 0) M->defer_budget = (size_t)budget_bytes;
   return M->ctx->tp->barrier(M->stream);
 }
@@ -2016,6 +2087,7 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
     M->peer_vals[r] = M->peer_meta[r] = nullptr;
     M->cap_vals[r] = M->cap_meta[r] = 0;
   }
+  M->arena_tab_dirty = true;
   CM_TRY(M->ctx->tp->barrier(M->stream));
   M->d_recv_vals.release();
   M->d_recv_meta.release();

@@ -43,6 +43,7 @@ parity baseline CM_B200_PIPELINE=0
 parity panels CM_B200_PIPELINE=1 CM_B200_PIPELINE_MIN_ELEMS=1
 parity panels+flags CM_B200_PIPELINE=1 CM_B200_PIPELINE_MIN_ELEMS=1 CM_B200_FLAG_BARRIER=1
 parity flags CM_B200_FLAG_BARRIER=1
+parity devlayout CM_B200_DEVICE_LAYOUT=1
 parity deferred CM_TEST_APPLY_POLICY=1
 
 # 2. K1-weak: batch commit (round-1 default) against panel pipelining
@@ -66,3 +67,5 @@ run k3-panels CM_B200_PIPELINE=1 -- --workload K3 --steps 3 --warmup 3
 run k3-deferred CM_B200_PIPELINE=0 -- --workload K3 --steps 3 --warmup 3 --apply-policy deferred
 run k4-batch CM_B200_PIPELINE=0 -- --workload K4 --steps 3 --warmup 3
 run k4-flags CM_B200_FLAG_BARRIER=1 -- --workload K4 --steps 3 --warmup 3
+run k4-flags-devlayout CM_B200_FLAG_BARRIER=1 CM_B200_DEVICE_LAYOUT=1 -- --workload K4 --steps 3 --warmup 3
+run k2-devlayout CM_B200_PIPELINE=0 CM_B200_DEVICE_LAYOUT=1 -- --workload K2 --steps 3 --warmup 3

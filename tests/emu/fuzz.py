@@ -25,7 +25,8 @@ cm.LIB_PATH = os.environ.get("CM_EMU_LIB", os.path.join(HERE, "libcm_b200_emu.so
 from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,  # noqa: E402
                       sorted_unique)
 
-ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER")
+ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
+            "CM_B200_PACK_COLS")
 
 
 def index_set(rng, hi, k, style):
@@ -97,7 +98,8 @@ def make_scenario(rng):
     env = {}
     if cfg.P > 1 and rng.random() < 0.6:
         env = {"CM_B200_PIPELINE": str(int(rng.random() < 0.8)), "CM_B200_PIPELINE_MIN_ELEMS": str(int(rng.choice([1, 2000, 50000]))),
-               "CM_B200_PANELS": str(int(rng.integers(1, 5))), "CM_B200_FLAG_BARRIER": str(int(rng.choice([0, 2])))}
+               "CM_B200_PANELS": str(int(rng.integers(1, 5))), "CM_B200_FLAG_BARRIER": str(int(rng.choice([0, 2]))),
+               "CM_B200_DEVICE_LAYOUT": str(int(rng.random() < 0.5)), "CM_B200_PACK_COLS": str(int(rng.choice([4, 8])))}
     # stream comparison is defined for slice-only scenarios with panel-monotone index sets: elemental
     # updates travel in a lane of their own here (the reference interleaves them in the same bin) and
     # the symmetric update / fill_lower are masked on the owner

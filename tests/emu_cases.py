@@ -310,3 +310,28 @@ def two_matrices_and_batch_api():
 
 
 CASES += [("two_matrices_and_batch_api", [()])]
+
+
+def device_layout_speculative_pack():
+    """CM_B200_DEVICE_LAYOUT=1: the layout of a commit's messages is computed on the device and the pack
+    kernel is launched before the host has read the counts; growing arenas (the speculative pack backs
+    off), steady arenas, wire capture (which also cross-checks device and host layouts), both policies"""
+    from scenario import assert_wire_match, run_cuda
+    cfg = Cfg(cm.F64, 1000, 700, 2, 3, 16, 32, 512)
+    rng = np.random.default_rng(171)
+    steps = []
+    for k in (60, 60, 120, 40, 200, 200):  # arenas grow, then hold
+        for r in range(cfg.P):
+            ix, jx = sorted_unique(rng, cfg.m, k), sorted_unique(rng, cfg.n, k // 2)
+            steps.append(("slice", r, rand_payload(rng, cfg.dtype, (k // 2, k)), k, k // 2, k, False, ix, jx))
+        steps.append(("commit",))
+    want = run_checker(cfg, steps, wire=True, threshold=1 << 40)
+    with _Env(CM_B200_DEVICE_LAYOUT=1):
+        got = run_cuda(cfg, steps, wire=True, exchange_mode=2)
+        assert_wire_match(cfg, got, want)
+        assert_blocks_match(cfg, got, want)
+        assert_blocks_match(cfg, run_cuda(cfg, steps, exchange_mode=2, apply_policy=1), want)
+        assert_blocks_match(cfg, run_cuda(cfg, steps, exchange_mode=2, apply_policy=1, defer_budget=100000), want)
+
+
+CASES += [("device_layout_speculative_pack", [()])]

@@ -41,6 +41,7 @@ GROUPS = [
     "deferred_apply",
     "deferred_apply_api",
     "two_matrices_and_batch_api",
+    "device_layout_speculative_pack",
 ]
 
 
