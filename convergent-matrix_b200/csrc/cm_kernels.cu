@@ -1247,6 +1247,29 @@ __global__ void k_signal_peers(uint32_t *const *__restrict__ peer_rows, int me, 
   }
 }
 
+// The counts all-gather as peer stores: block r copies this rank's totals into rank r's table, fences,
+// and its first thread raises this rank's flag in rank r's arrival row.
+__global__ void __launch_bounds__(256) k_publish_counts(char *const *__restrict__ peer_bases, int me, int nranks,
+                                                        const MsgCounts *__restrict__ totals, long counts_off, long row_off,
+                                                        uint32_t seq) {
+  const int r = blockIdx.x;
+  const long words = (long)sizeof(MsgCounts) / 8 * kMaxChunks * nranks;  // my row, in 8-byte words
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(totals);
+  unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer_bases[r] + counts_off) + (long)me * words;
+  for (long w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && r != me) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(peer_bases[r] + row_off + 4 * (long)me) = seq;
+  }
+}
+
+void launch_publish_counts(char *const *d_peer_bases, int me, int nranks, const MsgCounts *d_totals, long counts_off,
+                           long row_off, uint32_t seq, cudaStream_t s) {
+  CM_LAUNCH(nranks, 256, 0, s, k_publish_counts)(d_peer_bases, me, nranks, d_totals, counts_off, row_off, seq);
+}
+
 void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s) {
   CM_LAUNCH((nranks + 127) / 128, 128, 0, s, k_signal_peers)(d_peer_rows, me, nranks, seq);
 }

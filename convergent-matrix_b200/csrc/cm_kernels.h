@@ -103,6 +103,12 @@ void launch_iota_global(long *d_out, long count, long blk, long np, long p, cuda
 // barrier over peer memory: flags[me] = seq in every peer's barrier row (system-scope release)
 void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s);
 
+// counts all-gather over peer memory: this rank's totals [kMaxChunks * P] go into row `me` of every
+// rank's table (at counts_off inside its peer-mapped block), then flags[me] = seq in every rank's
+// arrival row (at row_off)
+void launch_publish_counts(char *const *d_peer_bases, int me, int nranks, const MsgCounts *d_totals, long counts_off,
+                           long row_off, uint32_t seq, cudaStream_t s);
+
 int kernel_sm_count();
 
 }  // namespace cmb

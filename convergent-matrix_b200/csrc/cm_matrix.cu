@@ -293,6 +293,13 @@ struct cm_matrix {
   int flag_barrier = 0;
   uint32_t bar_seq = 0;
   DevBuf d_peer_rows;  // [P] device pointers: peer r's barrier row
+  // The peer-mapped block behind d_flags holds, per rank: row 0 arrival flags of mode 3, row 1 barrier
+  // numbers, row 2 "counts have arrived" numbers (4*P bytes each), then — 256-byte aligned — the table
+  // of all-gathered counts [src][panel][owner]. With the flag barrier on, the counts all-gather is peer
+  // stores too (k_publish_counts) instead of an ncclAllGather.
+  size_t counts_off = 0;       // byte offset of the counts table in the block
+  uint32_t counts_seq = 0;
+  DevBuf d_peer_bases;         // [P] device pointers: base of peer r's block
   unsigned seq_slot = 0;
   static constexpr int kXferStreams = 4;  // peers are spread over several streams = several copy engines
   cudaStream_t xfer_stream[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
@@ -670,11 +677,15 @@ int wait_value_geq(cudaStream_t st, const void *addr, uint32_t value) {
 // ---- barriers of a commit ------------------------------------------------------------------
 // stream-ordered: work enqueued on `st` afterwards starts only when every rank's stream has reached
 // its own call. Default: the transport's (a 1-element ncclAllReduce); opt-in: flags over peer memory.
+// flags in peer-mapped memory instead of NCCL for a commit's synchronisation (opt-in)
+bool flag_sync_enabled(cm_matrix *M) {
+  return M->P > 1 && M->p2p && M->flag_barrier > 0 && (M->flag_barrier > 1 || !M->ctx->tp->same_process()) &&
+         stream_wait_value32() != nullptr;
+}
+
 int commit_stream_barrier(cm_matrix *M, cudaStream_t st) {
   Transport *tp = M->ctx->tp;
-  const bool flags = M->P > 1 && M->p2p && M->flag_barrier > 0 && (M->flag_barrier > 1 || !tp->same_process()) &&
-                     stream_wait_value32() != nullptr;
-  if (!flags) return tp->stream_barrier(st);
+  if (!flag_sync_enabled(M)) return tp->stream_barrier(st);
   const uint32_t seq = ++M->bar_seq;
   launch_signal_peers(M->d_peer_rows.as<uint32_t *>(), M->me, M->P, seq, st);
   M->stats.kernel_launches += 1;
@@ -899,8 +910,31 @@ int commit_exchange(cm_matrix *M) {
 
   // -- counts: all-gather the totals, read them back (the one host sync of a commit) -----------
   const size_t per_rank = sizeof(MsgCounts) * (size_t)P * K;
-  CM_TRY(M->d_counts_all.ensure(per_rank * P));
-  CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, per_rank, M->stream));
+  void *counts_all = nullptr;  // device table [src][panel][owner]
+  const size_t table_off = M->counts_off + ((M->counts_seq + 1) & 1u) * per_rank * P;  // table of this commit
+  if (P > 1) {
+    counts_all = M->d_flags.as<char>() + table_off;
+  } else {
+    CM_TRY(M->d_counts_all.ensure(per_rank * P));
+    counts_all = M->d_counts_all.p;
+  }
+  if (flag_sync_enabled(M)) {
+    // every rank stores its row into every rank's table over NVLink and says so; the stream waits
+    // until every row of its own table has arrived (no NCCL call)
+    const uint32_t seq = ++M->counts_seq;
+    launch_publish_counts(M->d_peer_bases.as<char *>(), me, P, M->d_totals.as<MsgCounts>(), (long)table_off,
+                          2 * 4 * (long)P, seq, M->stream);
+    M->stats.kernel_launches += 1;
+    const char *row2 = M->d_flags.as<char>() + 2 * 4 * (size_t)P;
+    for (int r = 0; r < P; ++r) {
+      if (r == me) continue;
+      const int rc = wait_value_geq(M->stream, row2 + 4 * (size_t)r, seq);
+      if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
+    }
+  } else {
+    ++M->counts_seq;
+    CM_TRY(tp->allgather(M->d_totals.p, counts_all, per_rank, M->stream));
+  }
   CM_TRY(M->h_counts.ensure(per_rank * P + 8 * (size_t)P * P));
   MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][chunk][dst]
   // -- device-side layout + speculative pack (opt-in): nothing below this point needs the host to know
@@ -934,14 +968,14 @@ int commit_exchange(cm_matrix *M) {
     at.base_v = tab + 4 * P;
     at.base_m = tab + 5 * P;
     CM_CUDA_TRY(cudaMemsetAsync(M->d_overflow.p, 0, 4, M->stream));
-    launch_layout(M->d_counts_all.as<MsgCounts>(), P, me, (int)esz, at, sa.dst_vals, sa.dst_meta, M->d_overflow.as<int>(),
+    launch_layout(static_cast<const MsgCounts *>(counts_all), P, me, (int)esz, at, sa.dst_vals, sa.dst_meta, M->d_overflow.as<int>(),
                   M->stream);
     sa.overflow = M->d_overflow.as<int>();
     launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, M->stream);
     M->stats.kernel_launches += 2;
     if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
   }
-  CM_CUDA_TRY(cudaMemcpyAsync(counts, M->d_counts_all.p, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
+  CM_CUDA_TRY(cudaMemcpyAsync(counts, counts_all, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
   if (spec_pack) CM_CUDA_TRY(cudaMemcpyAsync(M->h_overflow.p, M->d_overflow.p, 4, cudaMemcpyDeviceToHost, M->stream));
   M->stats.d2h_bytes += (long)(per_rank * P);
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
@@ -1635,10 +1669,14 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->peer_flags.assign(M->P, nullptr);
   M->peer_flags_open.assign(M->P, false);
   if (M->P > 1) {
-    int rcf = M->d_flags.ensure(2 * 4 * (size_t)M->P);  // row 0: arrival flags of mode 3, row 1: barrier
+    M->counts_off = (3 * 4 * (size_t)M->P + 255) & ~(size_t)255;
+    // two tables, used alternately: a rank that leaves an (empty) commit early may already publish the
+    // next commit's counts while a slower rank is still reading this one's
+    const size_t block_bytes = M->counts_off + 2 * sizeof(MsgCounts) * (size_t)M->P * kMaxChunks * M->P;
+    int rcf = M->d_flags.ensure(block_bytes);
     if (rcf == CM_OK) rcf = M->h_seq.ensure(4 * 1024);
     if (rcf != CM_OK) return rcf;
-    cudaMemsetAsync(M->d_flags.p, 0, 2 * 4 * (size_t)M->P, M->stream);
+    cudaMemsetAsync(M->d_flags.p, 0, block_bytes, M->stream);
     cudaStreamSynchronize(M->stream);
     M->peer_flags[M->me] = M->d_flags.p;
     if (ctx->tp->same_process()) {
@@ -1701,8 +1739,10 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
       std::vector<void *> rows(M->P);
       for (int r = 0; r < M->P; ++r) rows[r] = static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)M->P;
       int rcr = M->d_peer_rows.ensure(sizeof(void *) * (size_t)M->P);
+      if (rcr == CM_OK) rcr = M->d_peer_bases.ensure(sizeof(void *) * (size_t)M->P);
       if (rcr != CM_OK) return rcr;
       cudaMemcpyAsync(M->d_peer_rows.p, rows.data(), sizeof(void *) * (size_t)M->P, cudaMemcpyHostToDevice, M->stream);
+      cudaMemcpyAsync(M->d_peer_bases.p, M->peer_flags.data(), sizeof(void *) * (size_t)M->P, cudaMemcpyHostToDevice, M->stream);
       cudaStreamSynchronize(M->stream);
     }
   }
@@ -1742,6 +1782,7 @@ int cm_destroy(cm_matrix *M) {
   for (auto e : M->ev_xfer) cudaEventDestroy(e);
   M->d_flags.release();
   M->d_peer_rows.release();
+  M->d_peer_bases.release();
   M->d_arena_tab.release();
   M->d_overflow.release();
   M->h_overflow.release();
