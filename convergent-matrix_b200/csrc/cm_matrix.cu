@@ -363,7 +363,7 @@ struct cm_matrix {
   DevBuf d_counts_all, d_dst_ptrs, d_coo_counts;
   ApplyWork work[kMaxChunks];
   cudaStream_t apply_stream = nullptr;  // scatter-add of panel k while panel k+1 is packed / exchanged
-  cudaEvent_t ev_chunk[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_panel[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
   int pipeline = -1;                    // panel-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
                                         // enables them in mode 2 too, =0 disables them everywhere
@@ -936,7 +936,7 @@ int commit_exchange(cm_matrix *M) {
     CM_TRY(tp->allgather(M->d_totals.p, counts_all, per_rank, M->stream));
   }
   CM_TRY(M->h_counts.ensure(per_rank * P + 8 * (size_t)P * P));
-  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][chunk][dst]
+  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][panel][dst]
   // -- device-side layout + speculative pack (opt-in): nothing below this point needs the host to know
   // the counts before the pack kernel may run; the read-back overlaps it
   const bool spec_pack = M->device_layout && P > 1 && M->p2p && !M->dma && pp.npanel == 1 && nupd > 0 &&
@@ -1109,7 +1109,7 @@ int commit_exchange(cm_matrix *M) {
   }
 
   // -- owner side of the panels [k0, k1): their messages -> one scatter-add
-  auto apply_chunks = [&](int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) -> int {
+  auto apply_panels = [&](int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) -> int {
     std::vector<MsgRef> msgs;
     long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
     for (int k = k0; k < k1; ++k)
@@ -1173,8 +1173,8 @@ int commit_exchange(cm_matrix *M) {
     return CM_OK;
   };
 
-  // -- mode 3: push chunks [k0, k1) to their owners with the copy engines, then tell every owner.
-  // `after` = event on the main stream behind the pack of those chunks; the owner-side wait for
+  // -- mode 3: push the panels [k0, k1) to their owners with the copy engines, then tell every owner.
+  // `after` = event on the main stream behind the pack of those panels; the owner-side wait for
   // all sources is enqueued on `waiter`.
   auto dma_push = [&](int k0, int k1, cudaEvent_t after, cudaStream_t waiter) -> int {
     constexpr int NS = cm_matrix::kXferStreams;
@@ -1194,7 +1194,7 @@ int commit_exchange(cm_matrix *M) {
         CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_meta[r]) + rbase_m[ridx(r, k, me)],
                                     dst_ptrs[(size_t)K * P + i], (size_t)meta_bytes(cs.nseg, cs.nidx), cudaMemcpyDefault, xs));
       }
-      if (!tp->same_process()) {  // tell owner r: everything of mine for these chunks has landed
+      if (!tp->same_process()) {  // tell owner r: everything of mine for these panels has landed
         uint32_t *slot = ring + (M->seq_slot++ % 1024);
         *slot = seq;
         CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)me, slot, 4, cudaMemcpyDefault, xs));
@@ -1268,9 +1268,9 @@ int commit_exchange(cm_matrix *M) {
         M->stats.kernel_launches += 1;
       }
       CM_CUDA_TRY(cudaEventRecord(M->ev_packed[k], M->stream));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_packed[k], 0));  // my own message of chunk k
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_packed[k], 0));  // my own message of panel k
       CM_TRY(dma_push(k, k + 1, M->ev_packed[k], M->apply_stream));
-      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, 0));
+      CM_TRY(apply_panels(k, k + 1, M->work[k], M->apply_stream, 0));
     }
     if (M->profiling) {
       cudaEventRecord(ev_pack1, M->stream);
@@ -1295,11 +1295,11 @@ int commit_exchange(cm_matrix *M) {
       }
       // "everybody's panel k has landed" is awaited on the apply stream: the main stream goes straight
       // on to the pack of panel k+1
-      CM_CUDA_TRY(cudaEventRecord(M->ev_chunk[k], M->stream));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_chunk[k], 0));
+      CM_CUDA_TRY(cudaEventRecord(M->ev_panel[k], M->stream));
+      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_panel[k], 0));
       CM_TRY(commit_stream_barrier(M, M->apply_stream));
-      // all but the last chunk's scatter-add share the SMs with the next chunk's pack kernel
-      CM_TRY(apply_chunks(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? M->pipeline_apply_blocks : 0));
+      // all but the last panel's scatter-add share the SMs with the next panel's pack kernel
+      CM_TRY(apply_panels(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? M->pipeline_apply_blocks : 0));
     }
     if (M->profiling) {
       cudaEventRecord(ev_pack1, M->stream);
@@ -1310,7 +1310,7 @@ int commit_exchange(cm_matrix *M) {
   }
 
   if (M->keep_wire) {
-    // what THIS rank sent to every owner, chunk after chunk, read back from wherever pack put it
+    // what THIS rank sent to every owner, panel after panel, read back from wherever pack put it
     CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
     if (packed) {  // debug mode: the device-side layout must agree with the host's, pointer for pointer
       std::vector<void *> dev_ptrs(dst_ptrs.size());
@@ -1356,7 +1356,7 @@ int commit_exchange(cm_matrix *M) {
       M->pend_m[d] = rbase_m[ridx(d, K - 1, P - 1) + 1];
     }
   } else if (!pipelined) {
-    CM_TRY(apply_chunks(0, K, M->work[0], M->stream, 0));
+    CM_TRY(apply_panels(0, K, M->work[0], M->stream, 0));
   }
   if (M->dma && P > 1 && !pipelined) {  // my pushes are complete before anyone may reuse the arenas
     for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
@@ -1606,7 +1606,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) {
-    // the scatter-add of chunk k must get SM slots while the pack kernel of chunk k+1 (launched
+    // the scatter-add of panel k must get SM slots while the pack kernel of panel k+1 (launched
     // earlier, thousands of short blocks) is running: give its stream the higher priority, so that
     // freed slots go to its pending blocks first
     int prio_lo = 0, prio_hi = 0;
@@ -1618,7 +1618,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_xfer[k], cudaEventDisableTiming);
   }
   for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_packed[k], cudaEventDisableTiming);
-  for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_chunk[k], cudaEventDisableTiming);
+  for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_panel[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_applied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->copy_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&M->d_local, M->local_elems * M->esz);
@@ -1787,7 +1787,7 @@ int cm_destroy(cm_matrix *M) {
   M->d_overflow.release();
   M->h_overflow.release();
   M->h_seq.release();
-  for (auto e : M->ev_chunk) cudaEventDestroy(e);
+  for (auto e : M->ev_panel) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
