@@ -46,7 +46,13 @@ parity flags CM_B200_FLAG_BARRIER=1
 parity devlayout CM_B200_DEVICE_LAYOUT=1
 parity deferred CM_TEST_APPLY_POLICY=1
 
-# 2. K1-weak: batch commit (round-1 default) against panel pipelining
+# 2. the whole variant matrix in ONE process per rank (cheap in box time): scripts/sweep.py
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+    --master-port $((PORT++)) scripts/sweep.py --gpus "$N" --workloads K1,K2,K3,K4 | grep '^{'
+[ "${FULL:-0}" = "1" ] || exit 0
+
+# 3. (FULL=1) the same comparisons through bench.py itself, one invocation per variant
+# K1-weak: batch commit (round-1 default) against panel pipelining
 run k1-batch CM_B200_PIPELINE=0 -- --steps 5 --warmup 3
 for AB in 1 2 3; do
   run k1-panels4-ab$AB CM_B200_PIPELINE=1 CM_B200_PIPELINE_APPLY_BLOCKS=$AB -- --steps 5 --warmup 3
