@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(256) k_build_direct(const UpdDesc *__restrict_
     s.flags = ma.uflags[u];
     segs[u] = s;
   }
+  if (keys == nullptr) return;  // Seg table only
   const int nch = (d.m + kRowChunk - 1) / kRowChunk;
   const long total = (long)d.n * nch;
   const long ib = item_base[u];
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(256) k_build_recv(const MsgRef *__restrict__ m
       s.flags = ws.flags;
       segs[sid] = s;
     }
+    if (keys == nullptr) continue;  // Seg table only
     const int nch = (ws.nr + kRowChunk - 1) / kRowChunk;
     const long total = (long)ws.nc * nch;
     const long ib = m.item_base + ws.item_off;
@@ -657,6 +659,50 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elemen
     case 0: launch_apply_red_t(d_recs, nitems, elements, static_cast<double *>(d_local), g, s); break;
     case 1: launch_apply_red_t(d_recs, nitems, elements, static_cast<float *>(d_local), g, s); break;
     default: launch_apply_red_t(d_recs, nitems, elements, static_cast<int *>(d_local), g, s); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// (6a') scatter-add straight from the Seg table: one warp per segment, lanes over its nr x nc
+// elements in column-major order (coalesced value loads), one RED per element. For flushes of
+// small segments — a 32 x 32 update on a 4 x 2 grid leaves 8 x 16 segments — where per-column items
+// (16 items of 8 rows) would cost more to build and sort than to apply.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_seg(const Seg *__restrict__ segs, long nsegs, T *__restrict__ local, Geom g) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long t = warp; t < nsegs; t += nwarps) {
+    const Seg s = segs[t];
+    if (s.nr <= 0 || s.nc <= 0) continue;
+    const T *__restrict__ v = static_cast<const T *>(s.vals);
+    const long total = (long)s.nr * s.nc;
+    int a = lane % s.nr, b = lane / s.nr;  // element e = a + b * nr
+    const int da = 32 % s.nr, db = 32 / s.nr;
+    for (long e = lane; e < total; e += 32) {
+      const int row = s.lrow[a], col = s.lcol[b];
+      bool keep = true;
+      if (s.mask != 0)
+        keep = mask_keep(s.mask, global_index(row, g.mb, g.nprow, g.myprow), global_index(col, g.nb, g.npcol, g.mypcol));
+      if (keep) red_add(local + (long)col * g.lld + row, v[(long)a * s.row_stride + (long)b * s.col_stride]);
+      a += da;
+      b += db;
+      if (a >= s.nr) {
+        a -= s.nr;
+        ++b;
+      }
+    }
+  }
+}
+
+void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, const Geom &g, cudaStream_t s) {
+  if (nsegs <= 0) return;
+  const long blocks = std::min((nsegs + 7) / 8, (long)kernel_sm_count() * 8);
+  switch (dtype) {
+    case 0: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<double>)(d_segs, nsegs, static_cast<double *>(d_local), g); break;
+    case 1: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<float>)(d_segs, nsegs, static_cast<float *>(d_local), g); break;
+    default: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<int>)(d_segs, nsegs, static_cast<int *>(d_local), g); break;
   }
 }
 

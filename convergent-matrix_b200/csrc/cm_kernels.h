@@ -68,6 +68,7 @@ void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, c
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp,
                  const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
+// d_keys == nullptr: the Seg table only (segment-wise scatter-add, launch_apply_seg)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,
                          const Geom &g, const MapArenas &ma, Seg *d_segs, uint32_t *d_keys,
                          uint64_t *d_items, cudaStream_t s);
@@ -86,6 +87,9 @@ void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, con
 // (6a) scatter-add with RED.ADD, one warp per item (apply<T>, reference :178-187)
 void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elements, void *d_local, const Geom &g,
                       cudaStream_t s);
+// (6a') scatter-add with RED straight from the Seg table, one warp per segment: for flushes of small
+// segments (tiny updates), where per-column items would be a handful of rows each
+void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, const Geom &g, cudaStream_t s);
 // (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
                        void *d_local, long n_local, long m_local, const Geom &g, int max_blocks_per_sm,

@@ -290,6 +290,7 @@ struct cm_matrix {
   DevBuf d_arena_tab;  // [6][P]: vals base, meta base, cap_vals, cap_meta, base_v, base_m
   DevBuf d_overflow;
   PinBuf h_overflow;
+  int seg_apply = 0;  // CM_B200_SEG_APPLY=1: flushes of small segments are scatter-added segment-wise (k_apply_seg)
   int flag_barrier = 0;
   uint32_t bar_seq = 0;
   DevBuf d_peer_rows;  // [P] device pointers: peer r's barrier row
@@ -509,6 +510,24 @@ MapArenas map_arenas(cm_matrix *M) {
   return ma;
 }
 
+// Segment-wise scatter-add (opt-in) instead of per-column items: for the flushes that would take the
+// unsorted RED path anyway (sparse and small) and whose segments are small on average.
+bool use_seg_apply(const cm_matrix *M, long elements, long nsegs) {
+  if (!M->seg_apply || M->deterministic || M->apply_kernel == 2 || nsegs <= 0) return false;
+  const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
+  if (M->apply_kernel == 0 && density >= M->tile_density) return false;  // tile kernel
+  if (M->sorted_sweep && elements >= (4L << 20)) return false;           // sorted RED sweep
+  return elements <= nsegs * 4096;
+}
+
+int seg_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nsegs, long elements) {
+  ScopedTimer t(M, 0, elements, st);
+  launch_apply_seg(M->dtype, w.segs.as<Seg>(), nsegs, M->d_local, M->g, st);
+  M->stats.kernel_launches += 1;
+  CM_CUDA_TRY(cudaGetLastError());
+  return CM_OK;
+}
+
 // sort (optional) + scatter-add over nitems (key,item) pairs sitting in w.keys0 / w.items0
 int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0,
                    bool tma_hint = false) {
@@ -605,15 +624,20 @@ int flush_direct(cm_matrix *M, bool sync = true) {
     CM_TRY(w.keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
     CM_TRY(w.items0.ensure(8 * (size_t)std::max(nitems, 1L)));
     const MapArenas ma = map_arenas(M);
+    const bool by_seg = use_seg_apply(M, M->staged_elems, nupd);
     {
       ScopedTimer t(M, 1, 0);
       launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, PanelPlan{1, 1}, ma, M->stream);
       launch_build_direct(M->dtype, M->d_descs.as<UpdDesc>(), M->d_item_base.as<long>(), nupd, M->g, ma,
-                          w.segs.as<Seg>(), w.keys0.as<uint32_t>(), w.items0.as<uint64_t>(), M->stream);
+                          w.segs.as<Seg>(), by_seg ? nullptr : w.keys0.as<uint32_t>(),
+                          by_seg ? nullptr : w.items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
     }
     // every staged payload is laid out so that its 256-row column chunks can be bulk-copied
-    CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0, M->staged_tma_ok));
+    if (by_seg)
+      CM_TRY(seg_apply(M, w, M->stream, nupd, M->staged_elems));
+    else
+      CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0, M->staged_tma_ok));
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
@@ -787,10 +811,14 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
   CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)seg_total));
   CM_TRY(w.keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
   CM_TRY(w.items0.ensure(8 * (size_t)std::max(item_total, 1L)));
-  launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
-                    w.items0.as<uint64_t>(), st);
+  const bool by_seg = use_seg_apply(M, elem_total, seg_total);
+  launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(),
+                    by_seg ? nullptr : w.keys0.as<uint32_t>(), by_seg ? nullptr : w.items0.as<uint64_t>(), st);
   M->stats.kernel_launches += 1;
-  CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
+  if (by_seg)
+    CM_TRY(seg_apply(M, w, st, seg_total, elem_total));
+  else
+    CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
   M->stats.elements_applied += elem_total;
   return CM_OK;
 }
@@ -1734,6 +1762,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
     M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
+    if (getenv("CM_B200_SEG_APPLY")) M->seg_apply = atoi(getenv("CM_B200_SEG_APPLY")) != 0 ? 1 : 0;
     if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
     if (M->P > 1 && M->p2p_possible) {
       std::vector<void *> rows(M->P);

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS",
-         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE")
+         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY")
 
 # name, workloads it applies to, env, harness options
 VARIANTS = [
@@ -37,6 +37,8 @@ VARIANTS = [
     ("flags", "*", {"CM_B200_FLAG_BARRIER": "1"}, {}),
     ("flags-devlayout", "*", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {}),
     ("devlayout", "K2,K4", {"CM_B200_DEVICE_LAYOUT": "1"}, {}),
+    ("segapply", "K4", {"CM_B200_SEG_APPLY": "1"}, {}),
+    ("segapply-flags-devlayout", "K4", {"CM_B200_SEG_APPLY": "1", "CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {}),
     ("deferred", "K2,K3,K4", {}, {"deferred": True}),
     ("deferred-flags-devlayout", "K2,K3,K4", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": True}),
     ("tile", "K3", {}, {"apply_kernel": 2}),
@@ -86,8 +88,8 @@ def main():
         for name, wls, env, opt in VARIANTS:
             if (wls != "*" and wl not in wls.split(",")) or (only and name not in only):
                 continue
-            if nranks == 1 and (env or opt.get("deferred")):
-                continue  # every knob concerns the exchange
+            if nranks == 1 and (any(k != "CM_B200_SEG_APPLY" for k in env) or opt.get("deferred")):
+                continue  # those knobs concern the exchange
             for k in KNOBS:
                 os.environ.pop(k, None)
             os.environ.update(env)

@@ -26,7 +26,7 @@ from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload,
                       sorted_unique)
 
 ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
-            "CM_B200_PACK_COLS")
+            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY")
 
 
 def index_set(rng, hi, k, style):
@@ -103,6 +103,8 @@ def make_scenario(rng):
     # stream comparison is defined for slice-only scenarios with panel-monotone index sets: elemental
     # updates travel in a lane of their own here (the reference interleaves them in the same bin) and
     # the symmetric update / fill_lower are masked on the owner
+    if rng.random() < 0.4:
+        env = dict(env, CM_B200_SEG_APPLY="1")
     wire = style != "unsorted" and all(s[0] in ("slice", "commit", "reset") for s in steps) and rng.random() < 0.8
     return cfg, steps, knobs, env, wire
 
