@@ -717,7 +717,8 @@ void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, c
 // sets), with an L2 prefetch of the value lines a few blocks further ahead. Items whose rows may
 // repeat, masked items (symmetric update / fill_lower) and strided payloads take a simple in-order
 // loop. Local blocks taller than a tile are cut into row bands (kMulti): every band's block walks the
-// same items and takes the rows that fall into its band. Finally the tile is added to HBM with
+// same items and takes the rows that fall into its band (a contiguous sub-range of the item, found
+// by binary search when the item is staged). Finally the tile is added to HBM with
 // 16-byte loads/stores, skipping pieces nobody touched. A tile has one owner and its items are
 // applied in a fixed order, so the result is bit-exact run to run (this is also the
 // deterministic-order mode). DRAM traffic is the compulsory s*E + 2*s*(touched pieces) instead of
@@ -757,9 +758,19 @@ __device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geo
 // registers are NOT touched here — not even to subtract the tile's first row — so the warp leaves
 // this phase with its loads still in flight and meets them again only in tile_add_block, after the
 // previous block's adds; `okmask` (bit i: thread has an element in item i) depends on shared memory only.
-template <typename T, bool kMulti, int BLK>
-__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int r0, int h, int (&row)[BLK],
-                                                T (&val)[BLK], unsigned &okmask) {
+// first position in the strictly increasing rows[0, n) whose value is >= key
+__device__ __forceinline__ int first_row_ge(const int *__restrict__ rows, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(rows + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename T, int BLK>
+__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int (&row)[BLK], T (&val)[BLK],
+                                                unsigned &okmask) {
   okmask = 0;
 #pragma unroll
   for (int i = 0; i < BLK; ++i) {
@@ -768,14 +779,7 @@ __device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, 
     const int aa = ok ? tid : 0;  // idle threads re-read element 0 (always valid memory)
     okmask |= (ok ? 1u : 0u) << i;
     row[i] = __ldg(t.rows + aa);
-    if (!kMulti) val[i] = __ldg(t.v + aa);
-  }
-  if (kMulti) {  // taller than one tile: fetch the value only if this tile owns the row
-#pragma unroll
-    for (int i = 0; i < BLK; ++i) {
-      const bool mine = ((okmask >> i) & 1u) && (unsigned)(row[i] - r0) < (unsigned)h;
-      val[i] = __ldg(it[i].v + (mine ? tid : 0));
-    }
+    val[i] = __ldg(t.v + aa);
   }
 }
 
@@ -806,7 +810,8 @@ __device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int 
   }
 }
 
-// kMulti: the local block is taller than one tile, so a block only owns part of each item's rows.
+// kMulti: the local block is taller than one tile, so a block only owns part of each item's rows
+// (staged items are trimmed to that part).
 // BLK: items a thread keeps in flight per register set (two sets); CTAS: resident blocks per SM
 // the register budget is sized for (3 x 6-item sets or 2 x 12-item sets).
 template <typename T, bool kMulti, int BLK, int CTAS>
@@ -840,6 +845,18 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         t.stride = r.row_stride;
         t.mf = tid < cnt ? r.mask_flags : 0;
         t.pad = 0;
+        if (kMulti && t.n > 0 && (t.mf >> 8) == 0) {
+          // taller than one tile: this block owns the rows [r0, r0 + h). An item's rows are strictly
+          // increasing, so the ones that fall into the band are a contiguous sub-range: keep only
+          // that (two binary searches per staged item instead of a range check per element, and
+          // the warps beyond the sub-range have nothing to load)
+          const int lo = first_row_ge(r.lrow, r.n, r0), hi = first_row_ge(r.lrow, r.n, r0 + h);
+          t.n = hi - lo;
+          if (t.n > 0) {  // (an empty sub-range keeps the item's own, valid, base addresses)
+            t.rows = r.lrow + lo;
+            t.v = static_cast<const T *>(r.v) + (long)lo * r.row_stride;
+          }
+        }
         sm.item[tid] = t;
         special = tid < cnt ? (r.mask_flags | (r.row_stride != 1)) : 0;
       }
@@ -852,16 +869,15 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         unsigned okA = 0, okB = 0;
         const int nblk = (cnt + BLK - 1) / BLK;  // staged padding covers up to kRecChunk
         const int kTilePrefetch = c_tile_prefetch;
-        if (!kMulti)
-          for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm.item + b * BLK, tid);
-        tile_load_block<T, kMulti, BLK>(sm.item, tid, r0, h, rowA, valA, okA);
+        for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm.item + b * BLK, tid);
+        tile_load_block<T, BLK>(sm.item, tid, rowA, valA, okA);
         for (int b = 0; b < nblk; b += 2) {
-          if (!kMulti && b + 1 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 1 + kTilePrefetch) * BLK, tid);
-          if (b + 1 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 1) * BLK, tid, r0, h, rowB, valB, okB);
+          if (b + 1 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 1 + kTilePrefetch) * BLK, tid);
+          if (b + 1 < nblk) tile_load_block<T, BLK>(sm.item + (b + 1) * BLK, tid, rowB, valB, okB);
           tile_add_block<T, BLK>(sm.acc, r0, h, rowA, valA, okA);
           if (b + 1 < nblk) {
-            if (!kMulti && b + 2 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 2 + kTilePrefetch) * BLK, tid);
-            if (b + 2 < nblk) tile_load_block<T, kMulti, BLK>(sm.item + (b + 2) * BLK, tid, r0, h, rowA, valA, okA);
+            if (b + 2 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 2 + kTilePrefetch) * BLK, tid);
+            if (b + 2 < nblk) tile_load_block<T, BLK>(sm.item + (b + 2) * BLK, tid, rowA, valA, okA);
             tile_add_block<T, BLK>(sm.acc, r0, h, rowB, valB, okB);
           }
         }

@@ -41,11 +41,14 @@ def index_set(rng, hi, k, style):
     return rng.integers(0, hi, size=k).astype(np.int64)  # unsorted, duplicates allowed
 
 
+TALL_P = 0.15  # share of scenarios whose local block is taller than one shared-memory tile (--tall)
+
+
 def make_scenario(rng):
     nprow, npcol = [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2), (1, 4), (2, 4), (4, 2)][int(rng.integers(0, 9))]
     mb, nb = int(rng.choice([1, 3, 8, 16, 64])), int(rng.choice([1, 4, 8, 16, 64]))
     dtype = int(rng.choice([cm.F64, cm.F64, cm.F32, cm.I32]))
-    tall = rng.random() < 0.15  # taller than one shared-memory tile (8192 fp64 / 16384 fp32 rows)
+    tall = rng.random() < TALL_P  # taller than one shared-memory tile (8192 fp64 / 16384 fp32 rows)
     m = int(rng.integers(9000, 20000)) * nprow if tall else int(rng.integers(max(mb * nprow, 2), 1500))
     n = int(rng.integers(max(nb * npcol, 2), max(nb * npcol, 2) + (200 if tall else 1200)))
     # every rank needs a non-empty local block (reference asserts, :422-427)
@@ -140,7 +143,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--count", type=int, default=50)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--tall", type=float, default=0.15, help="share of tall local blocks")
     a = ap.parse_args()
+    global TALL_P
+    TALL_P = a.tall
     fails = 0
     t0 = time.time()
     for s in range(a.seed, a.seed + a.count):
