@@ -24,6 +24,7 @@ import cm_b200 as cm  # noqa: E402
 cm.LIB_PATH = os.environ.get("CM_EMU_LIB", os.path.join(HERE, "libcm_b200_emu.so"))  # e.g. a sanitizer build  # explicit: the tests' library, not the product's
 
 import test_gpu_parity as T  # noqa: E402
+import test_gpu_variants as V  # noqa: E402
 import emu_cases as E  # noqa: E402
 
 
@@ -52,7 +53,8 @@ CASES = [
     (T, "test_empty_ragged_and_lopsided_inputs", [()]),
     (T, "test_contract_violations_fail_loudly", [()]),
     (T, "test_save_load_reference_file_format", [(1, None), (4, None)]),
-    (T, "test_flag_barrier_is_refused_between_rank_threads", [()]),
+    (V, "test_flag_barrier_is_refused_between_rank_threads", [()]),
+    (V, "test_segment_wise_scatter_add", [()]),
 ] + [(E, name, params) for name, params in E.CASES]
 
 NAMES = [name for _, name, _ in CASES]

@@ -462,25 +462,3 @@ def test_save_load_reference_file_format(P, tmp_path):
             world.close()
         else:
             cm.finalize()
-
-
-@pytest.mark.parametrize("grid,mode,npanel", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
-                                              ((3, 2, 8, 4, 96, 250, 150), 3, 3)])
-def test_column_panels_wire_bit_exact(grid, mode, npanel):
-    """commits cut into column panels (thresholds lowered through the environment so
-    that small commits are cut too): local blocks match the oracle and, index sets being sorted, the
-    per-owner wire streams are the reference's element for element"""
-    from emu_cases import panels_wire_and_blocks
-    panels_wire_and_blocks(grid, mode, npanel)
-
-
-def test_flag_barrier_is_refused_between_rank_threads():
-    """CM_B200_FLAG_BARRIER=1 applies to one-process-per-GPU runs only: rank threads sharing one GPU keep
-    the transport's barrier (mutually waiting streams of one device could deadlock), results unchanged"""
-    from emu_cases import _Env
-    cfg = Cfg(cm.F64, 600, 600, 2, 2, 64, 64, 512)
-    rng = np.random.default_rng(72)
-    steps = slice_steps(cfg, rng, 3, 100, 100, commit_every=2)
-    with _Env(CM_B200_FLAG_BARRIER=1):
-        got = run_cuda(cfg, steps, exchange_mode=2)
-    assert_blocks_match(cfg, got, run_checker(cfg, steps))

@@ -1,0 +1,63 @@
+"""-m gpu: the opt-in variants built after round 1's GPU time ran out, on the
+loopback transport (rank threads on one GPU). Kept in a file that sorts after the established GPU
+suites, so that `pytest -x` reaches those first. The same scenarios run on the kernel-logic library in
+the CPU suite (tests/test_kernel_logic_emu.py)."""
+import numpy as np
+import pytest
+
+import cm_b200 as cm
+from scenario import Cfg, assert_blocks_match, run_checker, run_cuda, slice_steps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("grid,mode,npanel", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
+                                              ((3, 2, 8, 4, 96, 250, 150), 3, 3)])
+def test_column_panels_wire_bit_exact(grid, mode, npanel):
+    """commits cut into column panels (thresholds lowered through the environment so
+    that small commits are cut too): local blocks match the oracle and, index sets being sorted, the
+    per-owner wire streams are the reference's element for element"""
+    from emu_cases import panels_wire_and_blocks
+    panels_wire_and_blocks(grid, mode, npanel)
+
+
+def test_flag_barrier_is_refused_between_rank_threads():
+    """CM_B200_FLAG_BARRIER=1 applies to one-process-per-GPU runs only: rank threads sharing one GPU keep
+    the transport's barrier (mutually waiting streams of one device could deadlock), results unchanged"""
+    from emu_cases import _Env
+    cfg = Cfg(cm.F64, 600, 600, 2, 2, 64, 64, 512)
+    rng = np.random.default_rng(72)
+    steps = slice_steps(cfg, rng, 3, 100, 100, commit_every=2)
+    with _Env(CM_B200_FLAG_BARRIER=1):
+        got = run_cuda(cfg, steps, exchange_mode=2)
+    assert_blocks_match(cfg, got, run_checker(cfg, steps))
+
+
+@pytest.mark.parametrize("mode,budget", [(2, 0), (3, 0), (2, 40000)])
+def test_deferred_scatter_add(mode, budget):
+    """cm_set_apply_policy(CM_APPLY_DEFERRED): commits deliver, the log is applied on read / over budget /
+    when an arena grows; same local blocks as the eager oracle"""
+    from emu_cases import deferred_apply
+    deferred_apply(mode, budget)
+
+
+def test_deferred_scatter_add_api():
+    from emu_cases import deferred_apply_api
+    deferred_apply_api()
+
+
+def test_device_layout_speculative_pack():
+    """CM_B200_DEVICE_LAYOUT=1: layout on the device, pack launched before the host has read the counts"""
+    from emu_cases import device_layout_speculative_pack
+    device_layout_speculative_pack()
+
+
+def test_segment_wise_scatter_add():
+    """CM_B200_SEG_APPLY=1 on tiny updates (K4-shaped: 32 x 32 on a 4 x 2 grid) and on one rank"""
+    from emu_cases import _Env
+    for cfg in (Cfg(cm.F32, 2048, 2048, 4, 2, 64, 64, 512), Cfg(cm.F64, 1024, 1024, 1, 1, 64, 64, 1024)):
+        rng = np.random.default_rng(181)
+        steps = slice_steps(cfg, rng, 6, 32, 32, commit_every=3)
+        with _Env(CM_B200_SEG_APPLY=1):
+            got = run_cuda(cfg, steps)
+        assert_blocks_match(cfg, got, run_checker(cfg, steps))

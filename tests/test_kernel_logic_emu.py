@@ -33,6 +33,7 @@ GROUPS = [
     "test_contract_violations_fail_loudly",
     "test_save_load_reference_file_format",
     "test_flag_barrier_is_refused_between_rank_threads",
+    "test_segment_wise_scatter_add",
     "device_api_single_rank",
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
