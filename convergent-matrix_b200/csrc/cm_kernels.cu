@@ -387,23 +387,37 @@ static int pick_ytiles(int nupd, long max_cols) {
   return (int)y;
 }
 
+// Block size of the pack kernel. Thread slot t <-> one row of the update (slots of one owner row padded
+// to 16), so an update of m_u rows has about m_u + 16 * NPROW slots. 384 threads (default, measured)
+// leave a third of the block idle on 256-row updates; CM_B200_PACK_THREADS=0 sizes the block to the
+// slots (a whole number of passes with few idle threads; more blocks resident per SM), any other
+// value is used as is.
+static int pack_threads(int cfg, long max_rows, long nprow) {
+  if (cfg > 0) return std::min(std::max((cfg + 31) & ~31, 32), kPackThreads);
+  const long slots = std::max(32L, max_rows + 16 * nprow);
+  const long passes = (slots + kPackThreads - 1) / kPackThreads;
+  const long per = (slots + passes - 1) / passes;
+  return (int)std::min<long>(std::max<long>((per + 31) & ~31L, 64), kPackThreads);
+}
+
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp, const Geom &g,
-                 const MapArenas &ma, const ScanArenas &sa, cudaStream_t s) {
+                 const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc, cudaStream_t s) {
   if (nupd <= 0 || k1 <= k0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
-  static const int ncols = getenv("CM_B200_PACK_COLS") ? atoi(getenv("CM_B200_PACK_COLS")) : 4;
+  const int threads = pack_threads(pc.threads, max_rows, g.nprow);
+  const int ncols = pc.cols;
   if (ncols == 8) {
     switch (dtype) {
-      case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      case 0: CM_LAUNCH(grid, threads, 0, s, k_pack<double, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      case 1: CM_LAUNCH(grid, threads, 0, s, k_pack<float, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      default: CM_LAUNCH(grid, threads, 0, s, k_pack<int, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
     }
     return;
   }
   switch (dtype) {
-    case 0: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<double, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    case 1: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<float, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    default: CM_LAUNCH(grid, kPackThreads, 0, s, k_pack<int, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 0: CM_LAUNCH(grid, threads, 0, s, k_pack<double, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 1: CM_LAUNCH(grid, threads, 0, s, k_pack<float, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    default: CM_LAUNCH(grid, threads, 0, s, k_pack<int, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
   }
 }
 

@@ -65,8 +65,14 @@ void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, c
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
 // Packs the column panels [k0, k1) of every staged update.
+// max_rows: largest m_u among the staged updates (sizes the block when pc.threads == 0).
+struct PackConfig {
+  int threads = 384;  // block size; 0 = sized to the update's rows (CM_B200_PACK_THREADS)
+  int cols = 4;       // columns a thread keeps in flight, 4 or 8 (CM_B200_PACK_COLS)
+};
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp,
-                 const Geom &g, const MapArenas &ma, const ScanArenas &sa, cudaStream_t s);
+                 const Geom &g, const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc,
+                 cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
 // d_keys == nullptr: the Seg table only (segment-wise scatter-add, launch_apply_seg)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,

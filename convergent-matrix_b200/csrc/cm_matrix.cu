@@ -290,6 +290,7 @@ struct cm_matrix {
   DevBuf d_arena_tab;  // [6][P]: vals base, meta base, cap_vals, cap_meta, base_v, base_m
   DevBuf d_overflow;
   PinBuf h_overflow;
+  PackConfig pack_cfg;  // CM_B200_PACK_THREADS / CM_B200_PACK_COLS
   int seg_apply = 0;  // CM_B200_SEG_APPLY=1: flushes of small segments are scatter-added segment-wise (k_apply_seg)
   int flag_barrier = 0;
   uint32_t bar_seq = 0;
@@ -902,6 +903,8 @@ int commit_exchange(cm_matrix *M) {
   // -- panel plan (a LOCAL decision of this source; owners cope with any mix): a source that stages
   // a large commit cuts its updates' columns into panels so that the owners can pipeline it
   const PanelPlan pp = plan_panels(M);
+  long max_rows = 0;
+  for (const UpdDesc &d : M->descs) max_rows = std::max<long>(max_rows, d.m);
 
   // -- source side: owner map + per-(panel, owner) sizes ---------------------------------------
   CM_TRY(upload_staged(M, pp.npanel));
@@ -999,7 +1002,7 @@ int commit_exchange(cm_matrix *M) {
     launch_layout(static_cast<const MsgCounts *>(counts_all), P, me, (int)esz, at, sa.dst_vals, sa.dst_meta, M->d_overflow.as<int>(),
                   M->stream);
     sa.overflow = M->d_overflow.as<int>();
-    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, M->stream);
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
     M->stats.kernel_launches += 2;
     if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
   }
@@ -1269,7 +1272,7 @@ int commit_exchange(cm_matrix *M) {
   if (!pipelined) {
     // one batch: pack everything, (all-to-all-v), barrier, one scatter-add over all messages
     if (!packed) {
-      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, M->stream);
+      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
       M->stats.kernel_launches += nupd ? 1 : 0;
       if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
     }
@@ -1292,7 +1295,7 @@ int commit_exchange(cm_matrix *M) {
     CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
     for (int k = 0; k < Kp; ++k) {
       if (panel_has_data(k)) {
-        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, M->stream);
+        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
         M->stats.kernel_launches += 1;
       }
       CM_CUDA_TRY(cudaEventRecord(M->ev_packed[k], M->stream));
@@ -1318,7 +1321,7 @@ int commit_exchange(cm_matrix *M) {
     CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
     for (int k = 0; k < Kp; ++k) {
       if (panel_has_data(k)) {
-        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, M->stream);
+        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
         M->stats.kernel_launches += 1;
       }
       // "everybody's panel k has landed" is awaited on the apply stream: the main stream goes straight
@@ -1762,6 +1765,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
     M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
+    if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
+    if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
     if (getenv("CM_B200_SEG_APPLY")) M->seg_apply = atoi(getenv("CM_B200_SEG_APPLY")) != 0 ? 1 : 0;
     if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
     if (M->P > 1 && M->p2p_possible) {
