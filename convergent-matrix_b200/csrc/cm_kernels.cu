@@ -864,11 +864,11 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
           // increasing, so the ones that fall into the band are a contiguous sub-range: keep only
           // that (two binary searches per staged item instead of a range check per element, and
           // the warps beyond the sub-range have nothing to load)
-          const int lo = first_row_ge(r.lrow, r.n, r0), hi = first_row_ge(r.lrow, r.n, r0 + h);
-          t.n = hi - lo;
+          const int a_lo = first_row_ge(r.lrow, r.n, r0), a_hi = first_row_ge(r.lrow, r.n, r0 + h);
+          t.n = a_hi - a_lo;
           if (t.n > 0) {  // (an empty sub-range keeps the item's own, valid, base addresses)
-            t.rows = r.lrow + lo;
-            t.v = static_cast<const T *>(r.v) + (long)lo * r.row_stride;
+            t.rows = r.lrow + a_lo;
+            t.v = static_cast<const T *>(r.v) + (long)a_lo * r.row_stride;
           }
         }
         sm.item[tid] = t;
