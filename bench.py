@@ -231,9 +231,9 @@ def bench_ours(args):
     M.set_apply_kernel({"auto": 0, "red": 1, "tile": 2}[args.apply_kernel])
     if nranks > 1:
         M.set_exchange_mode({"auto": 0, "nccl": 1, "p2p": 2, "dma": 3}[args.exchange])
-    spec["deferred"] = args.apply_policy == "deferred" and nranks > 1 and M.exchange_mode() != 1
+    spec["deferred"] = args.apply_policy != "eager" and nranks > 1 and M.exchange_mode() != 1
     if spec["deferred"]:
-        M.set_apply_policy(1, args.defer_budget_gib << 30)
+        M.set_apply_policy(2 if args.apply_policy == "background" else 1, args.defer_budget_gib << 30)
     data, ix, jx = gen_inputs(spec, rank, torch, device)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(M.stream(), device=device)
@@ -396,7 +396,7 @@ def bench_ours(args):
                        "l2": "inputs (payloads) per step are far larger than L2; no explicit flush",
                        "flush_threshold_elements": M.flush_threshold(), "sorted_sweep": not args.unsorted,
                        "deterministic": bool(args.deterministic), "apply_kernel": args.apply_kernel, "exchange": {1: "nccl", 2: "p2p", 3: "dma"}[M.exchange_mode()] if nranks > 1 else "none", "payload_bytes_per_rank_per_step": step_bytes,
-                       "apply_policy": "deferred (extension: commits deliver, ONE scatter-add per step inside the timed region)" if spec["deferred"] else "eager (reference semantics)",
+                       "apply_policy": (args.apply_policy + " (extension: commits deliver, the step ends with cm_materialize inside the timed region)") if spec["deferred"] else "eager (reference semantics)",
                        "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CM_B200_")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": st["kernel_launches"],
             "roofline": roof, "cpu_baseline": cpu,
@@ -495,8 +495,10 @@ def main():
     ap.add_argument("--apply-kernel", default="auto", choices=["auto", "red", "tile"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "dma"],
                     help="auto/p2p: the pack kernel stores into the owners' arenas over NVLink; nccl: grouped send/recv")
-    ap.add_argument("--apply-policy", default="eager", choices=["eager", "deferred"],
-                    help="deferred (N > 1, p2p/dma): commits only deliver, the step ends with cm_materialize (inside the timed region)")
+    ap.add_argument("--apply-policy", default="eager", choices=["eager", "deferred", "background"],
+                    help="deferred / background (N > 1, p2p/dma): commits only deliver (background: the logged messages are "
+                         "scatter-added on a second stream under the following commits), the step ends with cm_materialize "
+                         "(inside the timed region)")
     ap.add_argument("--defer-budget-gib", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-updates", type=int, default=0, help="updates per rank per e2e step (0 = all)")

@@ -330,7 +330,9 @@ struct cm_matrix {
     const void *vals;
     long nseg, nitems, nelems;
   };
-  int apply_policy = 0;               // CM_APPLY_EAGER / CM_APPLY_DEFERRED
+  int apply_policy = 0;               // CM_APPLY_EAGER / CM_APPLY_DEFERRED / CM_APPLY_BACKGROUND
+  bool bg_running = false;            // a background scatter-add of the log is (possibly) still on the apply stream
+  long bg_min_elems = 16L << 20;      // background policy: launch one when this many logged elements wait
   size_t defer_budget = 8ull << 30;   // bytes of logged values per owner before everybody materialises
   std::vector<PendMsg> pend;          // messages logged in MY arenas since the last collective materialise
   size_t pend_applied = 0;            // prefix of `pend` a local materialise has already applied
@@ -367,6 +369,7 @@ struct cm_matrix {
   cudaStream_t apply_stream = nullptr;  // scatter-add of panel k while panel k+1 is packed / exchanged
   cudaEvent_t ev_panel[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
+  cudaEvent_t ev_bg = nullptr;  // main stream -> apply stream dependency of a background scatter-add
   int pipeline = -1;                    // panel-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
                                         // enables them in mode 2 too, =0 disables them everywhere
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
@@ -430,7 +433,13 @@ struct ScopedTimer {
 
 // stream must be synchronised
 void resolve_timers(cm_matrix *M) {
+  std::vector<PendingTimer> keep;
   for (auto &t : M->timers) {
+    if (cudaEventQuery(t.b) == cudaErrorNotReady) {  // a background scatter-add still running on another stream
+      keep.push_back(t);
+      continue;
+    }
+    cudaGetLastError();
     float ms = 0;
     if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
       if (t.kind == 0) {
@@ -448,7 +457,7 @@ void resolve_timers(cm_matrix *M) {
     M->event_pool.push_back(t.a);
     M->event_pool.push_back(t.b);
   }
-  M->timers.clear();
+  M->timers.swap(keep);
 }
 
 int ceil_log2(long v) {
@@ -826,8 +835,17 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
 
 // deferred policy: apply what has been logged in my arenas and not applied yet (local, not collective;
 // the log itself is only truncated by materialize_all, because every rank tracks its length)
-int materialize_local(cm_matrix *M) {
-  if (M->pend_applied >= M->pend.size()) return CM_OK;
+// a background scatter-add (apply stream) must have finished before anything else touches the local
+// block or the work buffers it uses
+int wait_background(cm_matrix *M) {
+  if (!M->bg_running) return CM_OK;
+  CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
+  M->bg_running = false;
+  return CM_OK;
+}
+
+// the un-applied part of my log as one scatter-add on stream `st`
+int apply_log(cm_matrix *M, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
   std::vector<MsgRef> msgs;
   long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
   for (size_t i = M->pend_applied; i < M->pend.size(); ++i) {
@@ -843,11 +861,34 @@ int materialize_local(cm_matrix *M) {
     max_seg = std::max(max_seg, pm.nseg);
     msgs.push_back(m);
   }
-  CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, M->work[0], M->stream, 0));
+  CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm));
   M->pend_applied = M->pend.size();
   M->mirror_valid = false;
+  return CM_OK;
+}
+
+int materialize_local(cm_matrix *M) {
+  if (M->pend_applied >= M->pend.size() && !M->bg_running) return CM_OK;
+  CM_TRY(wait_background(M));
+  if (M->pend_applied < M->pend.size()) CM_TRY(apply_log(M, M->work[0], M->stream, 0));
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
   resolve_timers(M);
+  return CM_OK;
+}
+
+// background policy: start the scatter-add of what has been logged on the apply stream and return; the
+// pack / exchange of the following commits overlaps it (the log is append-only, nothing it reads changes)
+int start_background_apply(cm_matrix *M) {
+  long waiting = 0;
+  for (size_t i = M->pend_applied; i < M->pend.size(); ++i) waiting += M->pend[i].nelems;
+  if (waiting < M->bg_min_elems) return CM_OK;
+  // everything this stream has done so far (the delivery barrier included) precedes the scatter-add; an
+  // earlier background scatter-add precedes it in apply-stream order
+  CM_CUDA_TRY(cudaEventRecord(M->ev_bg, M->stream));
+  CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_bg, 0));
+  CM_TRY(apply_log(M, M->work[1], M->apply_stream, M->pipeline_apply_blocks));
+  CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
+  M->bg_running = true;
   return CM_OK;
 }
 
@@ -856,7 +897,7 @@ int commit_barrier(cm_matrix *M, cudaStream_t st);
 // COLLECTIVE: everybody applies its log, then the logs are truncated everywhere
 int materialize_all(cm_matrix *M) {
   if (M->P <= 1 || M->pend_v.empty()) return CM_OK;
-  bool any = !M->pend.empty();
+  bool any = false;  // from the global offsets only: every rank must take the same branch
   for (int d = 0; d < M->P; ++d) any = any || M->pend_v[d] != 0 || M->pend_m[d] != 0;
   if (!any) return CM_OK;  // same answer on every rank: the offsets are global knowledge
   CM_TRY(materialize_local(M));
@@ -1398,6 +1439,7 @@ int commit_exchange(cm_matrix *M) {
   for (int src = 0; src < P; ++src) {
     const long n = coo_counts[(size_t)src * P + me];
     if (!n) continue;
+    CM_TRY(wait_background(M));  // the tile kernel's write-back is not atomic: no RED into the block beside it
     const char *blob = src == me ? M->d_send_coo.as<char>() + s_coo_base[me] : M->d_recv_coo.as<char>() + r_coo_base[src];
     CM_TRY(apply_coo_blob(M, blob, n));
   }
@@ -1412,6 +1454,7 @@ int commit_exchange(cm_matrix *M) {
     bool over = false;  // same decision on every rank
     for (int d = 0; d < P; ++d) over = over || (size_t)M->pend_v[d] * esz > M->defer_budget;
     if (over) CM_TRY(materialize_all(M));
+    else if (M->apply_policy == CM_APPLY_BACKGROUND) CM_TRY(start_background_apply(M));
     return CM_OK;
   }
   // -- quiescence: everybody has applied everything (reference :737-741) --------------------
@@ -1651,6 +1694,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_packed[k], cudaEventDisableTiming);
   for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_panel[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_applied, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_bg, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->copy_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&M->d_local, M->local_elems * M->esz);
   if (e == cudaSuccess) e = cudaMemsetAsync(M->d_local, 0, M->local_elems * M->esz, M->stream);  // :431-432
@@ -1767,6 +1811,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
     if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
     if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
+    if (getenv("CM_B200_BG_MIN_ELEMS")) M->bg_min_elems = atol(getenv("CM_B200_BG_MIN_ELEMS"));
     if (getenv("CM_B200_SEG_APPLY")) M->seg_apply = atoi(getenv("CM_B200_SEG_APPLY")) != 0 ? 1 : 0;
     if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
     if (M->P > 1 && M->p2p_possible) {
@@ -1823,6 +1868,7 @@ int cm_destroy(cm_matrix *M) {
   M->h_seq.release();
   for (auto e : M->ev_panel) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);
+  cudaEventDestroy(M->ev_bg);
   M->h_counts.release();
   for (auto e : M->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(M->stream);
@@ -2124,8 +2170,8 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density) {
 }
 int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
-  if (policy != CM_APPLY_EAGER && policy != CM_APPLY_DEFERRED)
-    return fail(CM_ERR_INVALID, "apply policy must be CM_APPLY_EAGER (0) or CM_APPLY_DEFERRED (1)");
+  if (policy != CM_APPLY_EAGER && policy != CM_APPLY_DEFERRED && policy != CM_APPLY_BACKGROUND)
+    return fail(CM_ERR_INVALID, "apply policy must be CM_APPLY_EAGER (0), CM_APPLY_DEFERRED (1) or CM_APPLY_BACKGROUND (2)");
   if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the apply policy only with nothing staged");
   CM_TRY(materialize_all(M));
   M->apply_policy = policy;

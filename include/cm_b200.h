@@ -202,6 +202,10 @@ int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
  * unapplied updates: call cm_materialize first. budget_bytes <= 0 keeps the current budget (8 GiB). */
 #define CM_APPLY_EAGER 0
 #define CM_APPLY_DEFERRED 1
+/* CM_APPLY_BACKGROUND: as DEFERRED, but once enough elements are logged (16 Mi; CM_B200_BG_MIN_ELEMS) the
+ * owner starts their scatter-add on a second stream at the end of the commit and returns: it runs
+ * while the following commits pack and exchange. Same rules for readers as DEFERRED. */
+#define CM_APPLY_BACKGROUND 2
 int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes);
 int cm_get_apply_policy(const cm_matrix *M);
 /* COLLECTIVE: every rank applies its log, then a barrier; afterwards every local block is current. */

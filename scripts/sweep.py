@@ -41,8 +41,11 @@ VARIANTS = [
     ("devlayout", "K2,K4", {"CM_B200_DEVICE_LAYOUT": "1"}, {}),
     ("segapply", "K4", {"CM_B200_SEG_APPLY": "1"}, {}),
     ("segapply-flags-devlayout", "K4", {"CM_B200_SEG_APPLY": "1", "CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {}),
-    ("deferred", "K2,K3,K4", {}, {"deferred": True}),
-    ("deferred-flags-devlayout", "K2,K3,K4", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": True}),
+    ("deferred", "K2,K3,K4", {}, {"deferred": 1}),
+    ("background", "K2,K3", {}, {"deferred": 2}),
+    ("background-ab1", "K2,K3", {"CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {"deferred": 2}),
+    ("deferred-flags-devlayout", "K2,K3,K4", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 1}),
+    ("background-flags-devlayout", "K2,K3", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 2}),
     ("tile", "K3", {}, {"apply_kernel": 2}),
     ("dma", "K1,K2", {"CM_B200_EXCHANGE": "dma"}, {}),
 ]
@@ -101,7 +104,7 @@ def main():
             M.set_apply_kernel(opt.get("apply_kernel", 0))
             spec["deferred"] = bool(opt.get("deferred")) and nranks > 1 and M.exchange_mode() != 1
             if spec["deferred"]:
-                M.set_apply_policy(1, 16 << 30)
+                M.set_apply_policy(int(opt["deferred"]), 16 << 30)
             stream = torch.cuda.ExternalStream(M.stream(), device=device)
             batches = bench.make_batches(cm, spec, data.data_ptr(), ix.data_ptr(), jx.data_ptr(), esz, True)
             for _ in range(args.warmup):

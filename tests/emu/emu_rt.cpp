@@ -345,6 +345,7 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = (float)(b->t_ms - a->t_ms);
   return cudaSuccess;
 }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
   delete e;
   return cudaSuccess;

@@ -26,7 +26,7 @@ from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload,
                       sorted_unique)
 
 ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
-            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS")
+            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS")
 
 
 def index_set(rng, hi, k, style):
@@ -92,7 +92,7 @@ def make_scenario(rng):
     knobs = dict(apply_kernel=int(rng.choice([0, 1, 2])), sorted_sweep=bool(rng.random() < 0.8),
                  deterministic=bool(rng.random() < 0.25), exchange_mode=int(rng.choice([0, 1, 2, 3])))
     if cfg.P > 1 and knobs["exchange_mode"] != 1 and rng.random() < 0.35:  # deferred scatter-add (peer-to-peer modes)
-        knobs["apply_policy"] = 1
+        knobs["apply_policy"] = int(rng.choice([1, 2]))
         knobs["defer_budget"] = int(rng.choice([0, 1, 20000, 400000]))
     if cfg.P == 1:
         knobs["exchange_mode"] = 0
@@ -106,6 +106,8 @@ def make_scenario(rng):
     # stream comparison is defined for slice-only scenarios with panel-monotone index sets: elemental
     # updates travel in a lane of their own here (the reference interleaves them in the same bin) and
     # the symmetric update / fill_lower are masked on the owner
+    if knobs.get("apply_policy") == 2:
+        env = dict(env, CM_B200_BG_MIN_ELEMS=str(int(rng.choice([1, 5000]))))
     if rng.random() < 0.4:
         env = dict(env, CM_B200_SEG_APPLY="1")
     if rng.random() < 0.3:

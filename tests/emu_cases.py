@@ -193,7 +193,7 @@ CASES += [("flag_barrier_commits", [()])]
 
 
 # ---- deferred scatter-add (cm_set_apply_policy) ---------------------------------
-def deferred_apply(mode, budget):
+def deferred_apply(mode, budget, policy=1):
     """commit() only delivers; the log is applied when the block is read, when it outgrows its budget
     (budget small: every other commit) or when an arena has to grow; several rounds, elemental updates,
     the symmetric update, fill_lower and reset in between — same local blocks as the eager oracle"""
@@ -213,7 +213,8 @@ def deferred_apply(mode, budget):
     steps += [("fill_lower",), ("commit",), ("reset",)]
     steps += slice_steps(cfg, rng, 3, 80, 70, commit_every=1)
     want = run_checker(cfg, steps)
-    got = run_cuda(cfg, steps, exchange_mode=mode, apply_policy=1, defer_budget=budget)
+    with _Env(CM_B200_BG_MIN_ELEMS=1 if policy == 2 else 1 << 24):
+        got = run_cuda(cfg, steps, exchange_mode=mode, apply_policy=policy, defer_budget=budget)
     assert_blocks_match(cfg, got, want)
 
 
@@ -266,7 +267,8 @@ def deferred_apply_api():
         world.close()
 
 
-CASES += [("deferred_apply", [(2, 0), (3, 0), (2, 40000), (2, 1)]), ("deferred_apply_api", [()])]
+CASES += [("deferred_apply", [(2, 0), (3, 0), (2, 40000), (2, 1), (2, 0, 2), (3, 0, 2), (2, 40000, 2)]),
+          ("deferred_apply_api", [()])]
 
 
 def two_matrices_and_batch_api():

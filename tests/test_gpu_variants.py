@@ -33,12 +33,13 @@ def test_flag_barrier_is_refused_between_rank_threads():
     assert_blocks_match(cfg, got, run_checker(cfg, steps))
 
 
-@pytest.mark.parametrize("mode,budget", [(2, 0), (3, 0), (2, 40000)])
-def test_deferred_scatter_add(mode, budget):
-    """cm_set_apply_policy(CM_APPLY_DEFERRED): commits deliver, the log is applied on read / over budget /
-    when an arena grows; same local blocks as the eager oracle"""
+@pytest.mark.parametrize("mode,budget,policy", [(2, 0, 1), (3, 0, 1), (2, 40000, 1), (2, 0, 2), (2, 40000, 2)])
+def test_deferred_scatter_add(mode, budget, policy):
+    """cm_set_apply_policy(CM_APPLY_DEFERRED / CM_APPLY_BACKGROUND): commits deliver, the log is applied on
+    read / over budget / when an arena grows (policy 2: also in the background, on the apply stream,
+    while later commits pack); same local blocks as the eager oracle"""
     from emu_cases import deferred_apply
-    deferred_apply(mode, budget)
+    deferred_apply(mode, budget, policy)
 
 
 def test_deferred_scatter_add_api():
