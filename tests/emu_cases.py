@@ -337,3 +337,24 @@ def device_layout_speculative_pack():
 
 
 CASES += [("device_layout_speculative_pack", [()])]
+
+
+def deterministic_mode_under_variants():
+    """deterministic mode stays bit-exact run to run under column panels, the deferred and the background
+    policy (what is applied in which scatter-add depends only on the sequence of calls)"""
+    from scenario import run_cuda
+    cfg = Cfg(cm.F64, 640, 640, 2, 2, 32, 32, 320)
+    rng = np.random.default_rng(191)
+    steps = slice_steps(cfg, rng, 12, 200, 200, commit_every=3)  # ~2.3 hits per element per rank: order matters
+    want = run_checker(cfg, steps)
+    for env, kw in (({"CM_B200_PIPELINE": 1, "CM_B200_PIPELINE_MIN_ELEMS": 1}, {}),
+                    ({}, {"apply_policy": 1}), ({"CM_B200_BG_MIN_ELEMS": 1}, {"apply_policy": 2})):
+        with _Env(**env):
+            a = run_cuda(cfg, steps, exchange_mode=2, deterministic=True, **kw)
+            b = run_cuda(cfg, steps, exchange_mode=2, deterministic=True, **kw)
+        for r in range(cfg.P):
+            assert a["local"][r].tobytes() == b["local"][r].tobytes(), (env, kw, r)
+        assert_blocks_match(cfg, a, want)
+
+
+CASES += [("deterministic_mode_under_variants", [()])]

@@ -43,6 +43,7 @@ GROUPS = [
     "deferred_apply_api",
     "two_matrices_and_batch_api",
     "device_layout_speculative_pack",
+    "deterministic_mode_under_variants",
 ]
 
 
