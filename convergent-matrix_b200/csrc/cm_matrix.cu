@@ -290,6 +290,14 @@ struct cm_matrix {
   DevBuf d_arena_tab;  // [6][P]: vals base, meta base, cap_vals, cap_meta, base_v, base_m
   DevBuf d_overflow;
   PinBuf h_overflow;
+  // CM_B200_PINNED_DESCS=1: the descriptor table and the item offsets of a flush travel from two pinned
+  // staging slots used alternately (a truly asynchronous DMA) instead of straight from pageable vectors
+  // (which the driver may stage synchronously, behind whatever the stream still has to do)
+  int pinned_descs = 0;
+  PinBuf h_stage[2];
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  bool stage_used[2] = {false, false};
+  int stage_slot = 0;
   PackConfig pack_cfg;  // CM_B200_PACK_THREADS / CM_B200_PACK_COLS
   int seg_apply = 0;  // CM_B200_SEG_APPLY=1: flushes of small segments are scatter-added segment-wise (k_apply_seg)
   int flag_barrier = 0;
@@ -483,6 +491,37 @@ void clear_staged(cm_matrix *M) {
 
 int issue_merged_copy(cm_matrix *M);
 
+// host vector -> device buffer on the main stream, optionally through a pinned staging slot
+int upload_table(cm_matrix *M, void *d_dst, const void *h_src, size_t bytes, size_t slot_off) {
+  if (!bytes) return CM_OK;
+  if (!M->pinned_descs) {
+    CM_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, M->stream));
+    return CM_OK;
+  }
+  PinBuf &pb = M->h_stage[M->stage_slot];
+  char *h = static_cast<char *>(pb.p) + slot_off;
+  memcpy(h, h_src, bytes);
+  CM_CUDA_TRY(cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, M->stream));
+  return CM_OK;
+}
+
+// take the next staging slot for a flush holding `bytes` of tables: its previous DMA (two flushes ago) must be done
+int begin_stage(cm_matrix *M, size_t bytes) {
+  if (!M->pinned_descs) return CM_OK;
+  M->stage_slot ^= 1;
+  const int sl = M->stage_slot;
+  if (M->stage_used[sl]) CM_CUDA_TRY(cudaEventSynchronize(M->ev_stage[sl]));
+  if (!M->ev_stage[sl]) CM_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_stage[sl], cudaEventDisableTiming));
+  CM_TRY(M->h_stage[sl].ensure(bytes));
+  return CM_OK;
+}
+int end_stage(cm_matrix *M) {
+  if (!M->pinned_descs) return CM_OK;
+  CM_CUDA_TRY(cudaEventRecord(M->ev_stage[M->stage_slot], M->stream));
+  M->stage_used[M->stage_slot] = true;
+  return CM_OK;
+}
+
 int upload_staged(cm_matrix *M, int npanel = 1) {
   const int nupd = (int)M->descs.size();
   CM_TRY(issue_merged_copy(M));
@@ -493,9 +532,9 @@ int upload_staged(cm_matrix *M, int npanel = 1) {
   }
   CM_TRY(M->index_arena.upload(M->stream, &M->stats.h2d_bytes));
   CM_TRY(M->d_descs.ensure(sizeof(UpdDesc) * (size_t)std::max(nupd, 1)));
-  if (nupd)
-    CM_CUDA_TRY(cudaMemcpyAsync(M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, cudaMemcpyHostToDevice,
-                                M->stream));
+  // staging slot layout: [descriptors][item offsets (single-rank flush only)]
+  CM_TRY(begin_stage(M, (sizeof(UpdDesc) + 8) * (size_t)std::max(nupd, 1)));
+  CM_TRY(upload_table(M, M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, 0));
   const int npr = (int)M->g.nprow + 1, npc = (int)M->g.npcol * npanel + 1;
   CM_TRY(M->d_rl.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
   CM_TRY(M->d_rpos.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
@@ -628,7 +667,8 @@ int flush_direct(cm_matrix *M, bool sync = true) {
     CM_TRY(upload_staged(M));
     const long nitems = M->staged_items;
     CM_TRY(M->d_item_base.ensure(8 * (size_t)nupd));
-    CM_CUDA_TRY(cudaMemcpyAsync(M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, cudaMemcpyHostToDevice, M->stream));
+    CM_TRY(upload_table(M, M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, sizeof(UpdDesc) * (size_t)nupd));
+    CM_TRY(end_stage(M));
     ApplyWork &w = M->work[0];
     CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)nupd));
     CM_TRY(w.keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
@@ -949,6 +989,7 @@ int commit_exchange(cm_matrix *M) {
 
   // -- source side: owner map + per-(panel, owner) sizes ---------------------------------------
   CM_TRY(upload_staged(M, pp.npanel));
+  CM_TRY(end_stage(M));
   const size_t pu = (size_t)pp.npanel * P * std::max(nupd, 1);
   CM_TRY(M->d_valoff.ensure(8 * pu));
   CM_TRY(M->d_idxoff.ensure(8 * pu));
@@ -1809,6 +1850,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
     M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
+    if (getenv("CM_B200_PINNED_DESCS")) M->pinned_descs = atoi(getenv("CM_B200_PINNED_DESCS")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
     if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
     if (getenv("CM_B200_BG_MIN_ELEMS")) M->bg_min_elems = atol(getenv("CM_B200_BG_MIN_ELEMS"));
@@ -1859,6 +1901,10 @@ int cm_destroy(cm_matrix *M) {
   for (auto st : M->xfer_stream) cudaStreamDestroy(st);
   for (auto e : M->ev_packed) cudaEventDestroy(e);
   for (auto e : M->ev_xfer) cudaEventDestroy(e);
+  for (int k = 0; k < 2; ++k) {
+    M->h_stage[k].release();
+    if (M->ev_stage[k]) cudaEventDestroy(M->ev_stage[k]);
+  }
   M->d_flags.release();
   M->d_peer_rows.release();
   M->d_peer_bases.release();

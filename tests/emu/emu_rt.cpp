@@ -346,6 +346,7 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   return cudaSuccess;
 }
 cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) {
   delete e;
   return cudaSuccess;

@@ -170,6 +170,7 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventQuery(cudaEvent_t e);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
