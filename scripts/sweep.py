@@ -48,6 +48,9 @@ VARIANTS = [
     ("deferred-flags-devlayout", "K2,K3,K4", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 1}),
     ("background-flags-devlayout", "K2,K3", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 2}),
     ("tile", "K3", {}, {"apply_kernel": 2}),
+    ("flush-2^26", "K1", {}, {"flush_threshold": 1 << 26, "n1_only": True}),
+    ("flush-2^28", "K1", {}, {"flush_threshold": 1 << 28, "n1_only": True}),
+    ("flush-2^26-pinned-descs", "K1", {"CM_B200_PINNED_DESCS": "1"}, {"flush_threshold": 1 << 26, "n1_only": True}),
     ("dma", "K1,K2", {"CM_B200_EXCHANGE": "dma"}, {}),
 ]
 
@@ -96,6 +99,8 @@ def main():
                 continue
             if nranks == 1 and (any(k not in ("CM_B200_SEG_APPLY", "CM_B200_PINNED_DESCS") for k in env) or opt.get("deferred")):
                 continue  # those knobs concern the exchange
+            if opt.get("n1_only") and nranks > 1:
+                continue  # the flush threshold only bounds single-rank flushes
             for k in KNOBS:
                 os.environ.pop(k, None)
             os.environ.update(env)
@@ -103,6 +108,8 @@ def main():
             M = cm.Matrix(spec["dtype"], spec["m"], spec["n"], spec["nprow"], spec["npcol"], spec["mb"], spec["nb"], spec["lld"])
             M.set_profiling(True)
             M.set_apply_kernel(opt.get("apply_kernel", 0))
+            if opt.get("flush_threshold"):
+                M.set_flush_threshold(opt["flush_threshold"])
             spec["deferred"] = bool(opt.get("deferred")) and nranks > 1 and M.exchange_mode() != 1
             if spec["deferred"]:
                 M.set_apply_policy(int(opt["deferred"]), 16 << 30)
