@@ -30,6 +30,7 @@ if [ "$N" = "1" ]; then
   # scatter-add kernel
   python -m pytest tests -m gpu -x -q 2>&1 | tail -3
   python bench.py --steps 5 --warmup 3 | tail -1 | tee gpurun_out/bench_k1_n1.json
+  python scripts/sweep.py --gpus 1 --workloads K1,K4 | grep '^{' | tee gpurun_out/sweep_n1.jsonl
   B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --latency-reps 2"
   $B > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 400 --csv \
       --log-file gpurun_out/launches_k1_n1.csv $B > gpurun_out/ncu_launches.log 2>&1
