@@ -1245,10 +1245,19 @@ int commit_exchange(cm_matrix *M) {
 
   // -- exchange lanes of the transport (values + metadata only without p2p; COO always) ---------
   auto transport_lanes = [&](int k0, int k1, bool with_coo) -> int {
+    bool global_lane = false;  // every rank must take the same branch: decide from the global counts
+    for (int src = 0; src < P && !global_lane; ++src)
+      for (int d = 0; d < P && !global_lane; ++d) {
+        if (src == d) continue;
+        if (with_coo && coo_counts[(size_t)src * P + d]) global_lane = true;
+        if (!M->p2p)
+          for (int k = k0; k < k1; ++k)
+            if (counts[cidx(src, k, d)].nvals) global_lane = true;
+      }
+    if (!global_lane) return CM_OK;  // peer-to-peer modes without elemental updates: nothing rides on the transport
     const int nl = 2 * (k1 - k0) + 1;
     std::vector<std::vector<XferSpec>> sends(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
     std::vector<std::vector<XferSpec>> recvs(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
-    bool global_lane = false;  // every rank must take the same branch: decide from the global counts
     for (int r = 0; r < P; ++r) {
       if (r == me) continue;
       if (!M->p2p)  // NCCL mode only: values and metadata lanes
@@ -1271,15 +1280,7 @@ int commit_exchange(cm_matrix *M) {
           recvs[nl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r], (size_t)coo_blob(coo_counts[(size_t)r * P + me])};
       }
     }
-    for (int src = 0; src < P && !global_lane; ++src)
-      for (int d = 0; d < P && !global_lane; ++d) {
-        if (src == d) continue;
-        if (with_coo && coo_counts[(size_t)src * P + d]) global_lane = true;
-        if (!M->p2p)
-          for (int k = k0; k < k1; ++k)
-            if (counts[cidx(src, k, d)].nvals) global_lane = true;
-      }
-    if (global_lane) {
+    {
       ScopedTimer t(M, 2, 0);
       CM_TRY(tp->alltoallv(sends, recvs, M->stream));
     }
