@@ -62,3 +62,32 @@ def test_segment_wise_scatter_add():
         with _Env(CM_B200_SEG_APPLY=1):
             got = run_cuda(cfg, steps)
         assert_blocks_match(cfg, got, run_checker(cfg, steps))
+
+
+# ---- the same variants over real NVLink / NCCL, one process per GPU (skipped on single-GPU boxes) ----
+MP_VARIANTS = {
+    "panels": {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_MIN_ELEMS": "1"},
+    "panels+flags": {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_MIN_ELEMS": "1", "CM_B200_FLAG_BARRIER": "1"},
+    "flags+devlayout": {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"},
+    "deferred": {"CM_TEST_APPLY_POLICY": "1"},
+    "background+flags": {"CM_TEST_APPLY_POLICY": "2", "CM_B200_BG_MIN_ELEMS": "1", "CM_B200_FLAG_BARRIER": "1"},
+    "dma+panels": {"CM_TEST_EXCHANGE_MODE": "3", "CM_B200_PIPELINE_MIN_ELEMS": "1"},
+    "segapply+threads0": {"CM_B200_SEG_APPLY": "1", "CM_B200_PACK_THREADS": "0", "CM_B200_PINNED_DESCS": "1"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(MP_VARIANTS))
+@pytest.mark.parametrize("n", [2, 8])
+def test_multi_gpu_parity_of_variants(n, variant):
+    import os
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29750 + n * 10 + sorted(MP_VARIANTS).index(variant)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "mp_parity.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **MP_VARIANTS[variant]))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
