@@ -102,7 +102,7 @@ static_assert(sizeof(WireSeg) == 40, "wire segment layout");
 constexpr int kMaxChunks = 4;
 struct PanelPlan {
   int npanel;       // 1 .. kMaxChunks, and npanel * NPCOL <= kMaxGridDim
-  long panel_cols;  // local columns per panel (the last panel takes the rest)
+  long panel_cols;  // local columns per panel, a multiple of NB (the last panel takes the rest)
 };
 __host__ __device__ inline int panel_of(const PanelPlan &pp, long lcol) {
   if (pp.npanel <= 1) return 0;

@@ -82,7 +82,16 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
     }
     return;
   }
-  const bool panels = axis == 1 && pp.npanel > 1;
+  // Panels keep the reference's per-owner order (update after update, column after column, :605-613)
+  // only if this update's columns are non-decreasing in panel number — true for sorted jx, because
+  // panel_cols is a multiple of NB. An update whose columns are not goes into panel 0 as a whole.
+  bool panels = axis == 1 && pp.npanel > 1;
+  if (panels) {
+    int bad = 0;
+    for (int k = tid + 1; k < len; k += blockDim.x)
+      bad |= panel_of(pp, local_index(idx[k], blk, npo)) < panel_of(pp, local_index(idx[k - 1], blk, npo));
+    panels = __syncthreads_or(bad) == 0;
+  }
   auto group_of = [&](long gi) {
     int p = owner_coord(gi, blk, npo);
     if (panels) p += npo * panel_of(pp, local_index(gi, blk, npo));

@@ -962,8 +962,12 @@ PanelPlan plan_panels(cm_matrix *M) {
   const long ncols_max = cm_numroc(M->g.n, M->g.npcol, 0, M->g.nb);  // owner column 0 holds the most columns
   k = std::min(k, ncols_max);
   if (k <= 1) return pp;
-  pp.npanel = (int)k;
-  pp.panel_cols = (ncols_max + k - 1) / k;
+  // whole NB-blocks per panel: then a sorted jx is non-decreasing in panel number across ALL owners
+  // (global block B -> local block B / NPCOL -> panel), which is what keeps the wire order the reference's
+  const long nb = M->g.nb;
+  pp.panel_cols = (((ncols_max + k - 1) / k + nb - 1) / nb) * nb;
+  pp.npanel = (int)std::min<long>(k, (ncols_max + pp.panel_cols - 1) / pp.panel_cols);
+  if (pp.npanel <= 1) return PanelPlan{1, 1};
   return pp;
 }
 
@@ -1839,6 +1843,17 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (rc0 != CM_OK) return rc0;
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
+    // CM_B200_PROFILE=fast switches on the opt-in protocol variants together (every one of them can still be
+    // overridden by its own variable below); "measured" (default) is the configuration of BASELINE.md section 5
+    if (const char *prof = getenv("CM_B200_PROFILE")) {
+      if (!strcmp(prof, "fast")) {
+        M->pipeline = 1;
+        M->flag_barrier = 1;
+        M->device_layout = 1;
+        M->pinned_descs = 1;
+        M->seg_apply = 1;
+      }
+    }
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PIPELINE_APPLY_BLOCKS")) M->pipeline_apply_blocks = std::max(0, atoi(getenv("CM_B200_PIPELINE_APPLY_BLOCKS")));
     if (getenv("CM_B200_PANELS")) M->npanel_cfg = std::max(1, atoi(getenv("CM_B200_PANELS")));
@@ -2301,9 +2316,9 @@ int cm_debug_keep_wire(cm_matrix *M, int on) {
 
 // expands the compact messages to owner `dst` into the reference's (inds, data) stream; pass null
 // outputs to count only. The reference appends update after update to the owner's bin (:611), so the
-// panels of a commit are walked update-major: all panels of update 0, then of update 1, ... (equal to
-// the reference's order whenever an update's column indices are non-decreasing in panel number,
-// e.g. sorted jx; always equal for a one-panel commit).
+// panels of a commit are walked update-major: all panels of update 0, then of update 1, ... — the
+// reference's order, because the grouping kernel only cuts an update into panels when its column
+// indices are non-decreasing in panel number.
 static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *data_out) {
   const Geom &g = M->g;
   const size_t esz = M->esz;

@@ -22,11 +22,12 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS",
-         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS")
+         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PROFILE")
 
 # name, workloads it applies to, env, harness options
 VARIANTS = [
     ("batch", "*", {}, {}),
+    ("profile-fast", "*", {"CM_B200_PROFILE": "fast"}, {}),
     ("batch-pinned-descs", "*", {"CM_B200_PINNED_DESCS": "1"}, {}),
     ("batch-cols8", "K1,K2", {"CM_B200_PACK_COLS": "8"}, {}),
     ("batch-threads-auto", "K1,K2,K4", {"CM_B200_PACK_THREADS": "0"}, {}),
@@ -97,7 +98,7 @@ def main():
         for name, wls, env, opt in VARIANTS:
             if (wls != "*" and wl not in wls.split(",")) or (only and name not in only):
                 continue
-            if nranks == 1 and (any(k not in ("CM_B200_SEG_APPLY", "CM_B200_PINNED_DESCS") for k in env) or opt.get("deferred")):
+            if nranks == 1 and (any(k not in ("CM_B200_SEG_APPLY", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE") for k in env) or opt.get("deferred")):
                 continue  # those knobs concern the exchange
             if opt.get("n1_only") and nranks > 1:
                 continue  # the flush threshold only bounds single-rank flushes

@@ -26,7 +26,7 @@ from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload,
                       sorted_unique)
 
 ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
-            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PINNED_DESCS")
+            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE")
 
 
 def index_set(rng, hi, k, style):
@@ -114,7 +114,8 @@ def make_scenario(rng):
         env = dict(env, CM_B200_SEG_APPLY="1")
     if rng.random() < 0.3:
         env = dict(env, CM_B200_PACK_THREADS=str(int(rng.choice([0, 32, 96, 256]))))
-    wire = style != "unsorted" and all(s[0] in ("slice", "commit", "reset") for s in steps) and rng.random() < 0.8
+    # (any index style, panels or not: an update whose columns are not panel-monotone stays in panel 0)
+    wire = all(s[0] in ("slice", "commit", "reset") for s in steps) and rng.random() < 0.8
     return cfg, steps, knobs, env, wire
 
 

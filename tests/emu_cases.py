@@ -44,7 +44,7 @@ def _pipelined(mode, env):
     the thresholds are lowered through the environment so that it stays small enough for fibers"""
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
-    cfg = Cfg(cm.F32, 256, 256, 2, 2, 64, 64, 128)
+    cfg = Cfg(cm.F32, 256, 256, 2, 2, 16, 16, 128)  # 128 local columns = 8 blocks of NB: four 2-block panels
     world = cm.LoopbackWorld(4, 0)
     try:
         mats = world.run(lambda r: cm.Matrix(*cfg.args()))
@@ -71,8 +71,8 @@ def _pipelined(mode, env):
         for r, (blk, st) in enumerate(out):
             blk = blk.reshape(-1, cfg.lld)
             pr, pc = r // 2, r % 2
-            gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(128)])
-            gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(128)])
+            gi = np.array([(l // 16) * 32 + pr * 16 + l % 16 for l in range(128)])
+            gj = np.array([(l // 16) * 32 + pc * 16 + l % 16 for l in range(128)])
             assert np.array_equal(blk[:128, :128], want[np.ix_(gj, gi)]), f"rank {r}"
             assert st["apply_launches"] == 4, st["apply_launches"]  # one scatter-add per chunk
         world.run(lambda r: mats[r].destroy())
