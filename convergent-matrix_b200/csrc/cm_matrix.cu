@@ -1869,6 +1869,10 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (getenv("CM_B200_PINNED_DESCS")) M->pinned_descs = atoi(getenv("CM_B200_PINNED_DESCS")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
     if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
+    if (const char *pol = getenv("CM_B200_APPLY_POLICY")) {  // default policy of new matrices: eager | deferred | background
+      if (!strcmp(pol, "deferred")) M->apply_policy = CM_APPLY_DEFERRED;
+      if (!strcmp(pol, "background")) M->apply_policy = CM_APPLY_BACKGROUND;
+    }
     if (getenv("CM_B200_BG_MIN_ELEMS")) M->bg_min_elems = atol(getenv("CM_B200_BG_MIN_ELEMS"));
     if (getenv("CM_B200_SEG_APPLY")) M->seg_apply = atoi(getenv("CM_B200_SEG_APPLY")) != 0 ? 1 : 0;
     if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
