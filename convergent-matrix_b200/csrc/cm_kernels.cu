@@ -833,11 +833,33 @@ __device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int 
   }
 }
 
+// Write-back of a tile by the TMA unit (opt-in, CM_B200_TILE_BULKRED=1): one bulk reduce-add
+// (cp.reduce.async.bulk, SASS UBLKRED) adds the whole shared-memory tile to its column in global memory —
+// no thread waits on a dependent global load. Needs 16-byte aligned ends; adds zeros where nothing was hit.
+#ifndef CM_EMU
+__device__ __forceinline__ unsigned tile_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_reduce_add(double *gdst, const double *ssrc, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(tile_smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add(float *gdst, const float *ssrc, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(tile_smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add(int *gdst, const int *ssrc, unsigned bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(tile_smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+#endif
+
 // kMulti: the local block is taller than one tile, so a block only owns part of each item's rows
 // (staged items are trimmed to that part).
 // BLK: items a thread keeps in flight per register set (two sets); CTAS: resident blocks per SM
 // the register budget is sized for (3 x 6-item sets or 2 x 12-item sets).
-template <typename T, bool kMulti, int BLK, int CTAS>
+template <typename T, bool kMulti, int BLK, int CTAS, bool kBulk>
 __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
                                                        long ncols, int ntiles, long m_local, T *local, Geom g) {
   CM_DYN_SMEM(smem_raw);
@@ -928,11 +950,23 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         }
       }
     }
+#ifndef CM_EMU
+    if (kBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my tile writes -> async proxy
+#endif
     __syncthreads();
 
     // write-back: local[c, r0 + i] += acc[i], 16 bytes per thread step, untouched pieces skipped
     T *dcol = local + c * g.lld + r0;
     constexpr int kPer = 16 / (int)sizeof(T);
+#ifndef CM_EMU
+    if (kBulk && (reinterpret_cast<uintptr_t>(dcol) & 15) == 0 && ((h * (int)sizeof(T)) & 15) == 0) {
+      if (tid == 0) {
+        bulk_reduce_add(dcol, sm.acc, (unsigned)(h * (int)sizeof(T)));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile has been read: it may be re-zeroed
+      }
+    } else
+#endif
     if ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) {
       const int hv = h / kPer;
 #pragma unroll 4
@@ -961,6 +995,9 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
     }
     __syncthreads();  // the next unit re-zeroes acc
   }
+#ifndef CM_EMU
+  if (kBulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reductions performed
+#endif
 }
 
 // ------------------------------------------------------------------------------------
@@ -1162,7 +1199,7 @@ static void launch_tile_tma(const ItemRec *d_recs, const long *d_col_start, long
 
 #endif  // CM_EMU
 
-template <typename T, bool kMulti, int BLK, int CTAS>
+template <typename T, bool kMulti, int BLK, int CTAS, bool kBulk = false>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
                                 T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
@@ -1172,14 +1209,14 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
       const int pf = atoi(getenv("CM_B200_TILE_PREFETCH"));
       cudaMemcpyToSymbol(c_tile_prefetch, &pf, sizeof(int));
     }
-    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
+    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS, kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS, kBulk>, 256, smem);
   }
   const long nunits = n_local * ntiles;
   // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
   // the next chunk in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS>)(
+  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS, kBulk>)(
       d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
 }
 
@@ -1199,6 +1236,17 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   }
 #else
   (void)tma_mode;
+#endif
+#ifndef CM_EMU
+  // opt-in: write-back by one bulk reduce-add per tile (default item sets only)
+  static const int bulk_red = getenv("CM_B200_TILE_BULKRED") ? atoi(getenv("CM_B200_TILE_BULKRED")) : 0;
+  if (bulk_red) {
+    if (ntiles == 1)
+      launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    else
+      launch_tile_variant<T, true, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    return;
+  }
 #endif
   // variant 0 (default): 6-item sets, 3 blocks per SM; variant 1: 12-item sets, 2 blocks per SM
   static const int variant = getenv("CM_B200_TILE_VARIANT") ? atoi(getenv("CM_B200_TILE_VARIANT")) : 0;

@@ -23,6 +23,7 @@ import bench  # noqa: E402
 
 KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS",
          "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PROFILE")
+# CM_B200_TILE_BULKRED is read once per process: time it with a separate invocation (--only batch, variable exported)
 
 # name, workloads it applies to, env, harness options
 VARIANTS = [
