@@ -265,6 +265,48 @@ void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, c
 constexpr int kPackThreads = 384;
 constexpr int kPackMaxDst = 1024;  // (k1 - k0) * P destinations per launch
 
+// wire metadata of update u for the panels [k0, k1): header (first update only), WireSeg, index lists.
+// Called by the y == 0 block of an update with the block's shared roff / coff tables.
+__device__ __forceinline__ void pack_write_meta(const UpdDesc &d, int u, int nupd, int k0, int k1, int nprow, int npcol,
+                                                const int *roff, const int *coff, const MapArenas &ma, const ScanArenas &sa) {
+  const int tid = threadIdx.x, P = nprow * npcol;
+  const int *__restrict__ rl = ma.rl + d.rbase;
+  const int *__restrict__ cl = ma.cl + d.cbase;
+  for (int k = k0; k < k1; ++k)
+    for (int dst = 0; dst < P; ++dst) {
+      const MsgCounts c = sa.totals[k * P + dst];
+      if (c.nvals == 0) continue;  // empty message: nothing was reserved for it
+      const int p = dst / npcol, q = dst % npcol, gq = k * npcol + q;
+      const int nr = roff[p + 1] - roff[p], nc = coff[gq + 1] - coff[gq];
+      char *mb = sa.dst_meta[k * P + dst];
+      if (u == 0 && tid == 0) {  // message header
+        WireHdr *h = reinterpret_cast<WireHdr *>(mb);
+        h->nseg = c.nseg;
+        h->nvals = c.nvals;
+        h->nidx = c.nidx;
+        h->nitems = c.nitems;
+      }
+      WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
+      const bool empty = (long)nr * nc == 0;
+      const long obase = ((long)k * P + dst) * nupd + u;
+      const long ioff = sa.idxoff[obase];
+      if (tid == 0) {
+        ws->nr = empty ? 0 : nr;
+        ws->nc = empty ? 0 : nc;
+        ws->mask = d.mask;
+        ws->flags = ma.uflags[u];
+        ws->val_off = sa.valoff[obase];
+        ws->idx_off = ioff;
+        ws->item_off = sa.itemoff[obase];
+      }
+      if (!empty) {
+        int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nupd * sizeof(WireSeg)) + ioff;
+        for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
+        for (int cc = tid; cc < nc; cc += blockDim.x) iw[nr + cc] = cl[coff[gq] + cc];
+      }
+    }
+}
+
 // NC = columns a thread keeps in flight (4; 8 = opt-in CM_B200_PACK_COLS=8: twice the bytes in flight per
 // thread, for when the kernel shares the SMs with a scatter-add and has fewer resident threads)
 template <typename T, int NC>
@@ -347,43 +389,138 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
     }
   }
 
-  if (blockIdx.y == 0) {
-    const int *__restrict__ rl = ma.rl + d.rbase;
-    const int *__restrict__ cl = ma.cl + d.cbase;
-    for (int k = k0; k < k1; ++k)
-      for (int dst = 0; dst < P; ++dst) {
-        const MsgCounts c = sa.totals[k * P + dst];
-        if (c.nvals == 0) continue;  // empty message: nothing was reserved for it
-        const int p = dst / npcol, q = dst % npcol, gq = k * npcol + q;
-        const int nr = roff[p + 1] - roff[p], nc = coff[gq + 1] - coff[gq];
-        char *mb = sa.dst_meta[k * P + dst];
-        if (u == 0 && tid == 0) {  // message header
-          WireHdr *h = reinterpret_cast<WireHdr *>(mb);
-          h->nseg = c.nseg;
-          h->nvals = c.nvals;
-          h->nidx = c.nidx;
-          h->nitems = c.nitems;
-        }
-        WireSeg *ws = reinterpret_cast<WireSeg *>(mb + sizeof(WireHdr)) + u;
-        const bool empty = (long)nr * nc == 0;
-        const long obase = ((long)k * P + dst) * nupd + u;
-        const long ioff = sa.idxoff[obase];
-        if (tid == 0) {
-          ws->nr = empty ? 0 : nr;
-          ws->nc = empty ? 0 : nc;
-          ws->mask = d.mask;
-          ws->flags = ma.uflags[u];
-          ws->val_off = sa.valoff[obase];
-          ws->idx_off = ioff;
-          ws->item_off = sa.itemoff[obase];
-        }
-        if (!empty) {
-          int *iw = reinterpret_cast<int *>(mb + sizeof(WireHdr) + (long)nupd * sizeof(WireSeg)) + ioff;
-          for (int a = tid; a < nr; a += blockDim.x) iw[a] = rl[roff[p] + a];
-          for (int cc = tid; cc < nc; cc += blockDim.x) iw[nr + cc] = cl[coff[gq] + cc];
+  if (blockIdx.y == 0) pack_write_meta(d, u, nupd, k0, k1, nprow, npcol, roff, coff, ma, sa);
+}
+
+// ------------------------------------------------------------------------------------
+// (3') pack with bulk stores (opt-in, CM_B200_PACK_BULK=1). Same segments, same message layout as
+// k_pack, but a column's run of rows for one owner row is first gathered into shared memory and then
+// leaves the SM as ONE bulk copy (cp.async.bulk.global.shared::cta, 1-2 KB) instead of 128-byte
+// stores by half-warps: larger write requests towards NVLink, no store instructions on the SM. Eight
+// columns per stage, two stages: the gathers of stage g+1 overlap the bulk copies of stage g. Owner
+// rows whose runs are short (< 64 rows: dense, unaligned segments) or not a multiple of 16 bytes keep
+// the per-thread stores. Needs an update's thread slots (rows + 16 per owner row) to fit kBulkSlots.
+// ------------------------------------------------------------------------------------
+constexpr int kBulkThreads = 256;
+constexpr int kBulkCols = 8;
+constexpr int kBulkSlots = 544;
+
+#ifdef CM_EMU
+#define CM_BULK_STORE(dst, src, bytes) memcpy(dst, src, bytes)
+#define CM_BULK_COMMIT() ((void)0)
+#define CM_BULK_WAIT_READ_1() ((void)0)
+#define CM_BULK_WAIT_ALL() ((void)0)
+#define CM_FENCE_ASYNC_SMEM() ((void)0)
+#else
+#define CM_BULK_STORE(dst, src, bytes)                                                                         \
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),                       \
+               "r"((unsigned)__cvta_generic_to_shared(src)), "r"((unsigned)(bytes))                            \
+               : "memory")
+#define CM_BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
+#define CM_BULK_WAIT_READ_1() asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory")
+#define CM_BULK_WAIT_ALL() asm volatile("cp.async.bulk.wait_group 0;" ::: "memory")
+#define CM_FENCE_ASYNC_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(kBulkThreads) k_pack_bulk(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1,
+                                                            PanelPlan pp, Geom g, MapArenas ma, ScanArenas sa) {
+  if (sa.overflow != nullptr && *sa.overflow != 0) return;
+  CM_DYN_SMEM(smem_raw);
+  T(*stage)[kBulkCols][kBulkSlots] = reinterpret_cast<T(*)[kBulkCols][kBulkSlots]>(smem_raw);  // [2][cols][slots]
+  const int u = blockIdx.x;
+  const UpdDesc d = descs[u];
+  const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
+  const int ncg = npcol * pp.npanel;
+  __shared__ int roff[kMaxGridDim + 1];
+  __shared__ int coff[kMaxGridDim + 1];
+  __shared__ int tstart[kMaxGridDim + 1];
+  __shared__ int gdst[kMaxGridDim];
+  __shared__ T *base[kPackMaxDst];
+  const int tid = threadIdx.x;
+  if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
+  if (tid <= ncg) coff[tid] = ma.coff[(long)u * (ncg + 1) + tid];
+  if (tid < ncg) gdst[tid] = (tid / npcol - k0) * P + tid % npcol;
+  for (int i = tid; i < (k1 - k0) * P; i += blockDim.x) {
+    const int k = k0 + i / P, dst = i % P;
+    base[i] = static_cast<T *>(sa.dst_vals[k * P + dst]) + sa.valoff[((long)k * P + dst) * nupd + u];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int p = 0; p < nprow; ++p) {
+      tstart[p] = acc;
+      acc += (roff[p + 1] - roff[p] + kSegAlign - 1) & ~(kSegAlign - 1);
+    }
+    tstart[nprow] = acc;
+  }
+  __syncthreads();
+  const T *__restrict__ data = static_cast<const T *>(d.data);
+  const int *__restrict__ rpos = ma.rpos + d.rbase;
+  const int *__restrict__ cpos = ma.cpos + d.cbase;
+  const long src_rs = d.trans ? d.ld : 1, src_cs = d.trans ? 1 : d.ld;
+  const int cbeg = coff[k0 * npcol], cend = coff[k1 * npcol];
+  const int gy = (int)gridDim.y;
+  const int nslots = tstart[nprow];  // <= kBulkSlots (the launcher checks)
+
+  // the issuing thread j handles (column i of the stage, owner row p): j = i * nprow + p
+  const bool issuer = tid < kBulkCols * nprow;
+  const int my_i = tid / nprow, my_p = tid % nprow;
+  int ngroups = 0;
+  for (int kc0 = cbeg + (int)blockIdx.y; kc0 < cend; kc0 += kBulkCols * gy, ++ngroups) {
+    const int sidx = ngroups & 1;
+    // stage sidx was last used two groups ago: its bulk copies must have read it
+    if (issuer) CM_BULK_WAIT_READ_1();
+    __syncthreads();
+    // gather: slot t of column i -> stage[sidx][i][t]; owner rows that cannot go by bulk copy store directly
+    for (int t = tid; t < nslots; t += blockDim.x) {
+      int p = 0;
+      while (t >= tstart[p + 1]) ++p;
+      const int a = t - tstart[p];
+      const int nr = roff[p + 1] - roff[p];
+      if (a >= nr) continue;
+      const bool by_bulk = nr >= 64 && ((nr * (int)sizeof(T)) & 15) == 0;
+      const int stride = seg_col_stride(nr);
+      const long srow = (long)rpos[roff[p] + a] * src_rs;
+      int cp[kBulkCols];
+      T x[kBulkCols];
+#pragma unroll
+      for (int i = 0; i < kBulkCols; ++i) {
+        const int c = kc0 + i * gy;
+        cp[i] = c < cend ? cpos[c] : -1;
+      }
+#pragma unroll
+      for (int i = 0; i < kBulkCols; ++i) x[i] = cp[i] >= 0 ? data[srow + (long)cp[i] * src_cs] : T(0);
+      if (by_bulk) {
+#pragma unroll
+        for (int i = 0; i < kBulkCols; ++i) stage[sidx][i][t] = x[i];
+      } else {
+        int gq = k0 * npcol;
+#pragma unroll
+        for (int i = 0; i < kBulkCols; ++i) {
+          const int c = kc0 + i * gy;
+          if (c >= cend) break;
+          while (c >= coff[gq + 1]) ++gq;
+          base[gdst[gq] + p * npcol][(long)(c - coff[gq]) * stride + a] = x[i];
         }
       }
+    }
+    CM_FENCE_ASYNC_SMEM();  // my shared-memory writes become visible to the bulk-copy engine
+    __syncthreads();
+    if (issuer) {
+      const int c = kc0 + my_i * gy;
+      const int nr = roff[my_p + 1] - roff[my_p];
+      if (c < cend && nr >= 64 && ((nr * (int)sizeof(T)) & 15) == 0) {
+        int gq = k0 * npcol;
+        while (c >= coff[gq + 1]) ++gq;
+        T *dst = base[gdst[gq] + my_p * npcol] + (long)(c - coff[gq]) * seg_col_stride(nr);
+        CM_BULK_STORE(dst, &stage[sidx][my_i][tstart[my_p]], nr * (int)sizeof(T));
+      }
+      CM_BULK_COMMIT();  // one group per stage and issuing thread, empty or not
+    }
   }
+  if (issuer) CM_BULK_WAIT_ALL();
+  if (blockIdx.y == 0) pack_write_meta(d, u, nupd, k0, k1, nprow, npcol, roff, coff, ma, sa);
 }
 
 static int pick_ytiles(int nupd, long max_cols) {
@@ -413,6 +550,22 @@ void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, co
                  const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc, cudaStream_t s) {
   if (nupd <= 0 || k1 <= k0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
+  if (pc.bulk && max_rows + 16 * g.nprow <= kBulkSlots && kBulkCols * g.nprow <= kBulkThreads) {
+    const size_t smem = 2 * (size_t)kBulkCols * kBulkSlots * dtype_size(dtype);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_pack_bulk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 8));
+      cudaFuncSetAttribute(k_pack_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 4));
+      cudaFuncSetAttribute(k_pack_bulk<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 4));
+      attr_set = true;
+    }
+    switch (dtype) {
+      case 0: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<double>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      case 1: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<float>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+      default: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<int>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    }
+    return;
+  }
   const int threads = pack_threads(pc.threads, max_rows, g.nprow);
   const int ncols = pc.cols;
   if (ncols == 8) {

@@ -69,6 +69,7 @@ void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, c
 struct PackConfig {
   int threads = 384;  // block size; 0 = sized to the update's rows (CM_B200_PACK_THREADS)
   int cols = 4;       // columns a thread keeps in flight, 4 or 8 (CM_B200_PACK_COLS)
+  int bulk = 0;       // 1: runs of rows leave the SM as bulk copies from shared memory (CM_B200_PACK_BULK)
 };
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp,
                  const Geom &g, const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc,

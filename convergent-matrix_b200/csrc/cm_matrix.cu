@@ -1868,6 +1868,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
     if (getenv("CM_B200_PINNED_DESCS")) M->pinned_descs = atoi(getenv("CM_B200_PINNED_DESCS")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
+    if (getenv("CM_B200_PACK_BULK")) M->pack_cfg.bulk = atoi(getenv("CM_B200_PACK_BULK")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
     if (const char *pol = getenv("CM_B200_APPLY_POLICY")) {  // default policy of new matrices: eager | deferred | background
       if (!strcmp(pol, "deferred")) M->apply_policy = CM_APPLY_DEFERRED;

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS",
-         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PROFILE")
+         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PROFILE", "CM_B200_PACK_BULK")
 # CM_B200_TILE_BULKRED is read once per process: time it with a separate invocation (--only batch, variable exported)
 
 # name, workloads it applies to, env, harness options
@@ -31,6 +31,8 @@ VARIANTS = [
     ("profile-fast", "*", {"CM_B200_PROFILE": "fast"}, {}),
     ("batch-pinned-descs", "*", {"CM_B200_PINNED_DESCS": "1"}, {}),
     ("batch-cols8", "K1,K2", {"CM_B200_PACK_COLS": "8"}, {}),
+    ("batch-bulk", "K1,K2", {"CM_B200_PACK_BULK": "1"}, {}),
+    ("panels4-ab2-bulk", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_PACK_BULK": "1"}, {}),
     ("batch-threads-auto", "K1,K2,K4", {"CM_B200_PACK_THREADS": "0"}, {}),
     ("batch-threads-auto-cols8", "K1,K2", {"CM_B200_PACK_THREADS": "0", "CM_B200_PACK_COLS": "8"}, {}),
     ("panels4-ab1", "K1,K2,K3", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {}),

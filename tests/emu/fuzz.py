@@ -26,7 +26,7 @@ from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload,
                       sorted_unique)
 
 ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
-            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE")
+            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE", "CM_B200_PACK_BULK")
 
 
 def index_set(rng, hi, k, style):
@@ -110,6 +110,8 @@ def make_scenario(rng):
         env = dict(env, CM_B200_BG_MIN_ELEMS=str(int(rng.choice([1, 5000]))))
     if rng.random() < 0.3:
         env = dict(env, CM_B200_PINNED_DESCS="1")
+    if rng.random() < 0.3:
+        env = dict(env, CM_B200_PACK_BULK="1")
     if rng.random() < 0.4:
         env = dict(env, CM_B200_SEG_APPLY="1")
     if rng.random() < 0.3:

@@ -55,6 +55,7 @@ CASES = [
     (T, "test_save_load_reference_file_format", [(1, None), (4, None)]),
     (V, "test_flag_barrier_is_refused_between_rank_threads", [()]),
     (V, "test_segment_wise_scatter_add", [()]),
+    (V, "test_pack_with_bulk_stores", [()]),
 ] + [(E, name, params) for name, params in E.CASES]
 
 NAMES = [name for _, name, _ in CASES]

@@ -34,6 +34,7 @@ GROUPS = [
     "test_save_load_reference_file_format",
     "test_flag_barrier_is_refused_between_rank_threads",
     "test_segment_wise_scatter_add",
+    "test_pack_with_bulk_stores",
     "device_api_single_rank",
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
