@@ -32,7 +32,7 @@ if [ "$N" = "1" ]; then
   python bench.py --steps 5 --warmup 3 | tail -1 | tee gpurun_out/bench_k1_n1.json
   python scripts/sweep.py --gpus 1 --workloads K1,K4 | grep '^{' | tee gpurun_out/sweep_n1.jsonl
   # the bulk reduce-add write-back is chosen once per process
-  CM_B200_TILE_BULKRED=1 python -m pytest tests/test_gpu_variants.py -q -m gpu -k bulk_reduce --runxfail 2>&1 | tail -3
+  CM_B200_TEST_PTX_VARIANTS=1 timeout 900 python -m pytest tests/test_gpu_variants.py -q -m gpu -k "bulk_reduce or bulk_stores_child" 2>&1 | tail -3
   CM_B200_TILE_BULKRED=1 python scripts/sweep.py --gpus 1 --workloads K1 --only batch | grep '^{' | tee gpurun_out/sweep_n1_bulkred.jsonl
   B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --latency-reps 2"
   $B > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 400 --csv \

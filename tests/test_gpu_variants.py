@@ -93,7 +93,14 @@ def test_multi_gpu_parity_of_variants(n, variant):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
 
 
-@pytest.mark.xfail(reason="inline-PTX variant (cp.reduce.async.bulk write-back) that has not had its first GPU run yet", strict=False)
+# The two inline-PTX variants below have not had their first GPU run yet: they only run when asked for
+# (CM_B200_TEST_PTX_VARIANTS=1, scripts/measure_variants.sh does), in child processes, so that an untested
+# instruction sequence cannot take the established suite down with it.
+PTX_VARIANTS = pytest.mark.skipif(not __import__("os").environ.get("CM_B200_TEST_PTX_VARIANTS"),
+                                  reason="unmeasured inline-PTX variant: set CM_B200_TEST_PTX_VARIANTS=1")
+
+
+@PTX_VARIANTS
 def test_tile_write_back_by_bulk_reduce_add():
     """CM_B200_TILE_BULKRED=1: a tile is added to its column by ONE bulk reduce-add of the TMA unit
     instead of 16-byte load/add/store steps (read once per process: child process)"""
@@ -118,12 +125,27 @@ def test_tile_write_back_by_bulk_reduce_add():
     assert p.returncode == 0 and "VARIANT_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
 
 
-@pytest.mark.xfail(reason="inline-PTX variant (cp.async.bulk stores from shared memory) that has not had its first GPU run yet",
-                   strict=False)
+@PTX_VARIANTS
+def test_pack_with_bulk_stores_child_process():
+    """test_pack_with_bulk_stores in a child process with a timeout"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys\nsys.path.insert(0, 'tests')\nimport test_gpu_variants as V\n"
+            "V.test_pack_with_bulk_stores()\nprint('VARIANT_OK')\n")
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "VARIANT_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
+
+
 def test_pack_with_bulk_stores():
     """CM_B200_PACK_BULK=1: a column's run of rows for one owner row leaves the SM as one bulk copy;
     wire streams bit-exact, local blocks within tolerance (runs of >= 64 rows take the bulk path,
-    shorter ones and odd byte counts the per-thread stores)"""
+    shorter ones and odd byte counts the per-thread stores). On a GPU only through the child-process
+    wrapper above; the kernel-logic suite calls it directly."""
+    import os
+    if not os.environ.get("CM_EMU_LIB") and not cm.LIB_PATH.endswith("_emu.so") and not os.environ.get("CM_B200_TEST_PTX_VARIANTS"):
+        pytest.skip("unmeasured inline-PTX variant: set CM_B200_TEST_PTX_VARIANTS=1")
     from emu_cases import _Env
     from scenario import assert_wire_match
     for cfg, m_u, n_u in ((Cfg(cm.F64, 2000, 1000, 2, 2, 64, 64, 1024), 500, 300), (Cfg(cm.F32, 1500, 900, 2, 3, 16, 32, 768), 391, 200),
