@@ -8,7 +8,7 @@ import cm_b200 as cm
 from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,
                       slice_steps, sorted_unique)
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1200)]  # a hang must become a failure (pytest-timeout)
 
 
 @pytest.mark.parametrize("dtype", [cm.F64, cm.F32, cm.I32])
