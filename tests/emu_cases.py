@@ -358,3 +358,39 @@ def deterministic_mode_under_variants():
 
 
 CASES += [("deterministic_mode_under_variants", [()])]
+
+
+def k1_full_size_properties():
+    """BASELINE K1 geometry at full size (N = 8192, 256 x 256 all-ones updates, device API, asynchronous
+    threshold flushes through both scatter-add kernels): every element lands exactly once, per-row hit
+    counts, exact cancellation by the negated updates (tests/test_gpu_parity.py::test_full_size_properties_k1
+    restated with numpy)"""
+    cm.init(0, 1, 0)
+    try:
+        M = cm.Matrix(cm.F64, 8192, 8192, 1, 1, 64, 64, 8192)
+        rng = np.random.default_rng(1)
+        U = 512
+        ones = np.ones((256, 256))
+        ix = np.stack([np.sort(rng.choice(8192, 256, replace=False)) for _ in range(U)]).astype(np.int64)
+        jx = np.stack([np.sort(rng.choice(8192, 256, replace=False)) for _ in range(U)]).astype(np.int64)
+        M.set_flush_threshold(1 << 24)  # 257 updates per threshold flush: density just above / below 0.25
+        for sign in (ones, -ones):
+            for u in range(U):
+                M.update_device(_ptr(sign), 256, 256, 256, False, _ptr(ix[u]), _ptr(jx[u]))
+            M.commit()
+            blk = M.local().reshape(8192, 8192)
+            if sign is ones:
+                assert blk.sum() == U * 256 * 256
+                rows = np.zeros(8192)
+                np.add.at(rows, ix.reshape(-1), 256.0)
+                assert np.array_equal(blk.sum(axis=0), rows)
+                st = M.stats()
+                assert st["tile_launches"] >= 1 and st["flushes"] >= 2
+            else:
+                assert not blk.any()
+        M.destroy()
+    finally:
+        cm.finalize()
+
+
+CASES += [("k1_full_size_properties", [()])]

@@ -45,6 +45,7 @@ GROUPS = [
     "two_matrices_and_batch_api",
     "device_layout_speculative_pack",
     "deterministic_mode_under_variants",
+    "k1_full_size_properties",
 ]
 
 
