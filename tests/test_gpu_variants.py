@@ -9,7 +9,7 @@ import cm_b200 as cm
 from scenario import Cfg, assert_blocks_match, run_checker, run_cuda, slice_steps
 
 # a disagreement between rank threads would be a hang, not a failure: bound every test (pytest-timeout)
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.mark.parametrize("grid,mode,npanel", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
