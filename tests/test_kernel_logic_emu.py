@@ -94,3 +94,6 @@ def test_product_library_is_not_the_emulator():
         assert "emu" not in f.read()
     with open(os.path.join(ROOT, "convergent-matrix_b200", "csrc", "Makefile")) as f:
         assert "CM_EMU" not in f.read()
+    if os.path.exists(cm.LIB_PATH):  # no fiber scheduler, no runtime stubs inside the product library
+        blob = open(cm.LIB_PATH, "rb").read()
+        assert b"cmemu" not in blob and b"cm emu" not in blob
