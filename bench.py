@@ -361,6 +361,14 @@ def bench_ours(args):
                 "launches": st["apply_launches"], "avg_launch_ms": st["apply_ms"] / max(1, st["apply_launches"]),
                 "elements_per_launch": st["apply_elements"] // max(1, st["apply_launches"]),
                 "kernel_share_of_step": st["apply_ms"] / ms}
+        # roofline of the whole step: the slower of the HBM term (3*s bytes per owned
+        # s-byte element) and the NVLink term (s*(P-1)/P bytes per sourced element at 770 GB/s per direction),
+        # uniform owners assumed; value is aggregate payload GB/s
+        hbm_ceiling = peak / 3.0
+        nvl_ceiling = 770.0 * nranks / (nranks - 1) if nranks > 1 else float("inf")
+        roof["step"] = {"bound": "nvlink" if nvl_ceiling < hbm_ceiling else "hbm",
+                        "ceiling_GBps_per_gpu": min(hbm_ceiling, nvl_ceiling),
+                        "frac": value / (min(hbm_ceiling, nvl_ceiling) * nranks), "assumes": "uniform owners"}
         if nranks > 1:
             xm = M.exchange_mode()
             p2p = xm == 2
