@@ -394,3 +394,47 @@ def k1_full_size_properties():
 
 
 CASES += [("k1_full_size_properties", [()])]
+
+
+def bench_step_helpers():
+    """bench.py's workload plumbing (make_batches / run_step, eager and deferred with the final
+    cm_materialize) on a scaled-down K2-shaped spec, against a dense numpy sum"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    spec = dict(name="mini-K2", dtype=0, m=1024, n=1024, nprow=2, npcol=2, mb=64, nb=64, lld=512, m_u=96, n_u=80, U=12,
+                commit_every=4)
+    rng = np.random.default_rng(211)
+    for deferred in (False, True):
+        world = cm.LoopbackWorld(4, 0)
+        try:
+            mats = world.run(lambda r: cm.Matrix(spec["dtype"], spec["m"], spec["n"], spec["nprow"], spec["npcol"], spec["mb"],
+                                                 spec["nb"], spec["lld"]))
+            sp = dict(spec, deferred=deferred)
+            if deferred:
+                world.run(lambda r: mats[r].set_apply_policy(1, 1 << 30))
+            dense = np.zeros((spec["n"], spec["m"]))
+            inputs = []
+            for r in range(4):
+                data = np.ascontiguousarray(rng.uniform(-1, 1, size=(spec["U"], spec["n_u"], spec["m_u"])))
+                ix = np.ascontiguousarray(np.stack([sorted_unique(rng, spec["m"], spec["m_u"]) for _ in range(spec["U"])]))
+                jx = np.ascontiguousarray(np.stack([sorted_unique(rng, spec["n"], spec["n_u"]) for _ in range(spec["U"])]))
+                for u in range(spec["U"]):
+                    dense[np.ix_(jx[u], ix[u])] += data[u]
+                inputs.append((data, ix, jx))
+            batches = [bench.make_batches(cm, sp, _ptr(d), _ptr(i), _ptr(j), 8, True) for d, i, j in inputs]
+            assert len(batches[0]) == 3  # commit every 4 of 12 updates
+            world.run(lambda r: bench.run_step(mats[r], batches[r], sp))
+            blocks = world.run(lambda r: mats[r].local())
+            for r in range(4):
+                pr, pc = r // 2, r % 2
+                gi = np.array([(l // 64) * 128 + pr * 64 + l % 64 for l in range(512)])
+                gj = np.array([(l // 64) * 128 + pc * 64 + l % 64 for l in range(512)])
+                got = blocks[r].reshape(-1, spec["lld"])[:512, :512]
+                assert np.linalg.norm(got - dense[np.ix_(gj, gi)]) <= 1e-12 * np.linalg.norm(dense), (deferred, r)
+            world.run(lambda r: mats[r].destroy())
+        finally:
+            world.close()
+
+
+CASES += [("bench_step_helpers", [()])]

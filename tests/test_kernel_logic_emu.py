@@ -46,6 +46,7 @@ GROUPS = [
     "device_layout_speculative_pack",
     "deterministic_mode_under_variants",
     "k1_full_size_properties",
+    "bench_step_helpers",
 ]
 
 
