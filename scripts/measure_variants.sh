@@ -13,13 +13,13 @@ run() {  # run <label> <env...> -- <bench args...>
   while [ "$1" != "--" ]; do envs+=("$1"); shift; done
   shift
   echo "=== $label: ${envs[*]:-} bench.py $*"
-  env "${envs[@]}" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+  env "${envs[@]}" timeout -k 15 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port $((PORT++)) bench.py --gpus "$N" --no-e2e --no-cpu-baseline --latency-reps 50 "$@" | tail -1
 }
 parity() {  # parity <label> <env...>
   local label=$1; shift
   echo "=== parity $label: $*"
-  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+  env "$@" timeout -k 15 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port $((PORT++)) tests/mp_parity.py | tail -4
   echo "rc=$?"
 }
@@ -51,7 +51,7 @@ parity devlayout CM_B200_DEVICE_LAYOUT=1
 parity deferred CM_TEST_APPLY_POLICY=1
 
 # 2. the whole variant matrix in ONE process per rank (cheap in box time): scripts/sweep.py
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+timeout -k 15 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
     --master-port $((PORT++)) scripts/sweep.py --gpus "$N" --workloads K1,K2,K3,K4 | grep '^{'
 [ "${FULL:-0}" = "1" ] || exit 0
 
