@@ -21,7 +21,7 @@ parity() {  # parity <label> <env...>
   echo "=== parity $label: $*"
   env "$@" timeout -k 15 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port $((PORT++)) tests/mp_parity.py | tail -4
-  echo "rc=$?"
+  echo "rc=${PIPESTATUS[0]}"
 }
 
 if [ "$N" = "1" ]; then
