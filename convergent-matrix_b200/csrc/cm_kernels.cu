@@ -894,29 +894,29 @@ void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, c
 // repeat, masked items (symmetric update / fill_lower) and strided payloads take a simple in-order
 // loop. Local blocks taller than a tile are cut into row bands (kMulti): every band's block walks the
 // same items and takes the rows that fall into its band (a contiguous sub-range of the item, found
-// by binary search when the item is staged). Finally the tile is added to HBM with
-// 16-byte loads/stores, skipping pieces nobody touched. A tile has one owner and its items are
-// applied in a fixed order, so the result is bit-exact run to run (this is also the
-// deterministic-order mode). DRAM traffic is the compulsory s*E + 2*s*(touched pieces) instead of
-// one sector round trip per element. Best when the flush hits the local block densely.
+// by binary search when the item is staged). Finally the tile is added to its column in HBM by ONE
+// bulk reduce-add of the TMA unit (cp.reduce.async.bulk .add, SASS UBLKRED.G.S.ADD): no thread waits
+// on a dependent global load for the write-back (B200, K1: 2.07 ms against 2.76 ms per step with a
+// per-thread load / add / store write-back). Columns that are not 16-byte aligned fall back to
+// per-thread 16-byte loads / stores. A tile has one owner and its items are applied in a fixed
+// order, so the result is bit-exact run to run (this is also the deterministic-order mode). DRAM
+// traffic is the compulsory s*E + 2*s*(touched columns) instead of one sector round trip per
+// element. Best when the flush hits the local block densely.
 // ------------------------------------------------------------------------------------
 constexpr int kRecChunk = 144;  // items of a run staged in shared memory at a time (multiple of 2*BLK)
 
-template <typename T>
-struct TileItem {  // one staged item, 32 bytes
-  const T *v;       // first value
-  const int *rows;  // row indices
-  int n;            // rows (0 for padding / serially applied items)
-  int stride;       // elements between rows in v
-  int mf;           // mask | flags << 8
-  int pad;
-};
-
+// The staged items of a chunk, one array per field: a thread fetches the fields of BLK consecutive
+// items with a few 16-byte broadcast loads instead of one 32-byte record per item (the shared-memory
+// pipe is the busiest unit of this kernel: every wavefront saved on bookkeeping goes to the tile).
 template <typename T>
 struct TileSmem {
   static constexpr int kTileRows = 65536 / (int)sizeof(T);
-  T acc[kTileRows];             // 64 KiB: the tile (one column x kTileRows rows)
-  TileItem<T> item[kRecChunk];  // 4 KiB
+  alignas(128) T acc[kTileRows];       // 64 KiB: the tile (one column x kTileRows rows)
+  alignas(16) const T *v[kRecChunk];   // first value of each staged item
+  alignas(16) const int *rows[kRecChunk];  // its row indices
+  alignas(16) int n[kRecChunk];        // rows (0 for padding)
+  int stride[kRecChunk];               // elements between rows in v   (in-order path only)
+  int mf[kRecChunk];                   // mask | flags << 8            (in-order path only)
 };
 
 // largest local row whose global row index is <= gcol (-1 if none): with it the triangular
@@ -930,10 +930,6 @@ __device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geo
   return (int)lo - 1;
 }
 
-// fetch element `tid` of the BLK items starting at `it` (plain items: stride 1). The loaded
-// registers are NOT touched here — not even to subtract the tile's first row — so the warp leaves
-// this phase with its loads still in flight and meets them again only in tile_add_block, after the
-// previous block's adds; `okmask` (bit i: thread has an element in item i) depends on shared memory only.
 // first position in the strictly increasing rows[0, n) whose value is >= key
 __device__ __forceinline__ int first_row_ge(const int *__restrict__ rows, int n, int key) {
   int lo = 0, hi = n;
@@ -944,33 +940,60 @@ __device__ __forceinline__ int first_row_ge(const int *__restrict__ rows, int n,
   return lo;
 }
 
+template <typename P>
+struct alignas(16) Pair16 {  // two pointers, one 16-byte shared-memory load
+  P x, y;
+};
+struct alignas(8) Pair8 {
+  int x, y;
+};
+
+// fetch element `tid` of the BLK staged items starting at index `j0` (plain items: stride 1; j0 is a
+// multiple of BLK, BLK is even, so the field arrays are read 16 / 8 bytes at a time). The loaded
+// registers are NOT touched here — not even to subtract the tile's first row — so the warp leaves
+// this phase with its loads still in flight and meets them again only in tile_add_block, after the
+// previous block's adds; `okmask` (bit i: thread has an element in item i) depends on shared memory only.
 template <typename T, int BLK>
-__device__ __forceinline__ void tile_load_block(const TileItem<T> *it, int tid, int (&row)[BLK], T (&val)[BLK],
+__device__ __forceinline__ void tile_load_block(const TileSmem<T> &sm, int j0, int tid, int (&row)[BLK], T (&val)[BLK],
                                                 unsigned &okmask) {
+  static_assert(BLK % 2 == 0, "items are fetched two at a time");
+  const T *vp[BLK];
+  const int *rp[BLK];
+  int nn[BLK];
+#pragma unroll
+  for (int i = 0; i < BLK; i += 2) {
+    const Pair16<const T *> a = *reinterpret_cast<const Pair16<const T *> *>(&sm.v[j0 + i]);
+    const Pair16<const int *> b = *reinterpret_cast<const Pair16<const int *> *>(&sm.rows[j0 + i]);
+    const Pair8 c = *reinterpret_cast<const Pair8 *>(&sm.n[j0 + i]);
+    vp[i] = a.x;
+    vp[i + 1] = a.y;
+    rp[i] = b.x;
+    rp[i + 1] = b.y;
+    nn[i] = c.x;
+    nn[i + 1] = c.y;
+  }
   okmask = 0;
 #pragma unroll
   for (int i = 0; i < BLK; ++i) {
-    const TileItem<T> t = it[i];
-    const bool ok = tid < t.n;
+    const bool ok = tid < nn[i];
     const int aa = ok ? tid : 0;  // idle threads re-read element 0 (always valid memory)
     okmask |= (ok ? 1u : 0u) << i;
-    row[i] = __ldg(t.rows + aa);
-    val[i] = __ldg(t.v + aa);
+    row[i] = __ldg(rp[i] + aa);
+    val[i] = __ldg(vp[i] + aa);
   }
 }
 
-// L2 prefetch of the value lines of the BLK items starting at `it` (item i: threads 16*i .. 16*i+15,
-// one 128-byte line each): issued kTilePrefetch blocks ahead, so that the register loads that
+// L2 prefetch of the value lines of the BLK items starting at `j0` (item i: threads 16*i .. 16*i+15,
+// one 128-byte line each): issued c_tile_prefetch blocks ahead, so that the register loads that
 // follow later find their data in L2 instead of waiting a full DRAM round trip behind a barrier
 __constant__ int c_tile_prefetch = 2;  // blocks ahead (CM_B200_TILE_PREFETCH)
 template <typename T, int BLK>
-__device__ __forceinline__ void tile_prefetch_block(const TileItem<T> *it, int tid) {
+__device__ __forceinline__ void tile_prefetch_block(const TileSmem<T> &sm, int j0, int tid) {
   const int i = tid >> 4, line = tid & 15;
   if (i < BLK) {
-    const TileItem<T> t = it[i];
 #ifndef CM_EMU
-    if (line * 128 < t.n * (int)sizeof(T))
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(t.v) + line * 128));
+    if (line * 128 < sm.n[j0 + i] * (int)sizeof(T))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(sm.v[j0 + i]) + line * 128));
 #endif
   }
 }
@@ -986,9 +1009,9 @@ __device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int 
   }
 }
 
-// Write-back of a tile by the TMA unit (opt-in, CM_B200_TILE_BULKRED=1): one bulk reduce-add
-// (cp.reduce.async.bulk, SASS UBLKRED) adds the whole shared-memory tile to its column in global memory —
-// no thread waits on a dependent global load. Needs 16-byte aligned ends; adds zeros where nothing was hit.
+// Write-back of a tile by the TMA unit: one bulk reduce-add (cp.reduce.async.bulk, SASS UBLKRED) adds the
+// whole shared-memory tile to its column in global memory. Needs 16-byte aligned ends; adds zeros where
+// nothing was hit.
 #ifndef CM_EMU
 __device__ __forceinline__ unsigned tile_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_reduce_add(double *gdst, const double *ssrc, unsigned bytes) {
@@ -1008,13 +1031,19 @@ __device__ __forceinline__ void bulk_reduce_add(int *gdst, const int *ssrc, unsi
 }
 #endif
 
+template <typename T>
+struct alignas(16) Vec16 {
+  T x[16 / sizeof(T)];
+};
+
 // kMulti: the local block is taller than one tile, so a block only owns part of each item's rows
 // (staged items are trimmed to that part).
 // BLK: items a thread keeps in flight per register set (two sets); CTAS: resident blocks per SM
-// the register budget is sized for (3 x 6-item sets or 2 x 12-item sets).
-template <typename T, bool kMulti, int BLK, int CTAS, bool kBulk>
+// bulk: write the tile back with one bulk reduce-add (0: per-thread loads / stores; the kernel-logic
+// build and misaligned columns always take those)
+template <typename T, bool kMulti, int BLK, int CTAS>
 __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
-                                                       long ncols, int ntiles, long m_local, T *local, Geom g) {
+                                                       long ncols, int ntiles, long m_local, T *local, Geom g, int bulk) {
   CM_DYN_SMEM(smem_raw);
   TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
   constexpr int kTileRows = TileSmem<T>::kTileRows;
@@ -1027,7 +1056,13 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
     if (lo == hi) continue;  // uniform: nothing for this column in this flush
     const int r0 = tile * kTileRows;
     const int h = (int)min((long)kTileRows, m_local - r0);
-    for (int i = tid; i < h; i += 256) sm.acc[i] = T(0);
+    {
+      Vec16<T> z;
+#pragma unroll
+      for (int k = 0; k < (int)(16 / sizeof(T)); ++k) z.x[k] = T(0);
+      Vec16<T> *acc16 = reinterpret_cast<Vec16<T> *>(sm.acc);
+      for (int i = tid; i < (h * (int)sizeof(T) + 15) / 16; i += 256) acc16[i] = z;
+    }
 
     for (long base = lo; base < hi; base += kRecChunk) {
       const int cnt = (int)min((long)kRecChunk, hi - base);
@@ -1036,26 +1071,27 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
       if (tid < kRecChunk) {
         // padding entries (tid >= cnt) alias item 0 with n = 0: loads stay in bounds, nothing is added
         const ItemRec r = recs[base + (tid < cnt ? tid : 0)];
-        TileItem<T> t;
-        t.v = static_cast<const T *>(r.v);
-        t.rows = r.lrow;
-        t.n = tid < cnt ? r.n : 0;
-        t.stride = r.row_stride;
-        t.mf = tid < cnt ? r.mask_flags : 0;
-        t.pad = 0;
-        if (kMulti && t.n > 0 && (t.mf >> 8) == 0) {
+        const T *v = static_cast<const T *>(r.v);
+        const int *rows = r.lrow;
+        int n = tid < cnt ? r.n : 0;
+        const int mf = tid < cnt ? r.mask_flags : 0;
+        if (kMulti && n > 0 && (mf >> 8) == 0) {
           // taller than one tile: this block owns the rows [r0, r0 + h). An item's rows are strictly
           // increasing, so the ones that fall into the band are a contiguous sub-range: keep only
           // that (two binary searches per staged item instead of a range check per element, and
           // the warps beyond the sub-range have nothing to load)
           const int a_lo = first_row_ge(r.lrow, r.n, r0), a_hi = first_row_ge(r.lrow, r.n, r0 + h);
-          t.n = a_hi - a_lo;
-          if (t.n > 0) {  // (an empty sub-range keeps the item's own, valid, base addresses)
-            t.rows = r.lrow + a_lo;
-            t.v = static_cast<const T *>(r.v) + (long)a_lo * r.row_stride;
+          n = a_hi - a_lo;
+          if (n > 0) {  // (an empty sub-range keeps the item's own, valid, base addresses)
+            rows = r.lrow + a_lo;
+            v = static_cast<const T *>(r.v) + (long)a_lo * r.row_stride;
           }
         }
-        sm.item[tid] = t;
+        sm.v[tid] = v;
+        sm.rows[tid] = rows;
+        sm.n[tid] = n;
+        sm.stride[tid] = r.row_stride;
+        sm.mf[tid] = mf;
         special = tid < cnt ? (r.mask_flags | (r.row_stride != 1)) : 0;
       }
       const bool plain = __syncthreads_or(special) == 0;  // no mask, no repeated rows, unit stride
@@ -1067,15 +1103,15 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         unsigned okA = 0, okB = 0;
         const int nblk = (cnt + BLK - 1) / BLK;  // staged padding covers up to kRecChunk
         const int kTilePrefetch = c_tile_prefetch;
-        for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm.item + b * BLK, tid);
-        tile_load_block<T, BLK>(sm.item, tid, rowA, valA, okA);
+        for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm, b * BLK, tid);
+        tile_load_block<T, BLK>(sm, 0, tid, rowA, valA, okA);
         for (int b = 0; b < nblk; b += 2) {
-          if (b + 1 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 1 + kTilePrefetch) * BLK, tid);
-          if (b + 1 < nblk) tile_load_block<T, BLK>(sm.item + (b + 1) * BLK, tid, rowB, valB, okB);
+          if (b + 1 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm, (b + 1 + kTilePrefetch) * BLK, tid);
+          if (b + 1 < nblk) tile_load_block<T, BLK>(sm, (b + 1) * BLK, tid, rowB, valB, okB);
           tile_add_block<T, BLK>(sm.acc, r0, h, rowA, valA, okA);
           if (b + 1 < nblk) {
-            if (b + 2 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm.item + (b + 2 + kTilePrefetch) * BLK, tid);
-            if (b + 2 < nblk) tile_load_block<T, BLK>(sm.item + (b + 2) * BLK, tid, rowA, valA, okA);
+            if (b + 2 + kTilePrefetch < nblk) tile_prefetch_block<T, BLK>(sm, (b + 2 + kTilePrefetch) * BLK, tid);
+            if (b + 2 < nblk) tile_load_block<T, BLK>(sm, (b + 2) * BLK, tid, rowA, valA, okA);
             tile_add_block<T, BLK>(sm.acc, r0, h, rowB, valB, okB);
           }
         }
@@ -1083,61 +1119,63 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         // masked (symmetric update / fill_lower), strided or repeated-row items: simple in-order loop
         const int thr = mask_threshold(global_index(c, g.nb, g.npcol, g.mypcol), m_local, g);
         for (int j = 0; j < cnt; ++j) {
-          const TileItem<T> t = sm.item[j];
-          const int mask = t.mf & 0xff;
-          if (t.mf >> 8) {
+          const T *v = sm.v[j];
+          const int *rows = sm.rows[j];
+          const int n = sm.n[j], stride = sm.stride[j], mf = sm.mf[j];
+          const int mask = mf & 0xff;
+          if (mf >> 8) {
             if (tid == 0) {  // rows may repeat: one thread applies the item serially
-              for (int a = 0; a < t.n; ++a) {
-                const int rr = t.rows[a] - r0;
+              for (int a = 0; a < n; ++a) {
+                const int rr = rows[a] - r0;
                 if ((unsigned)rr >= (unsigned)h) continue;
                 if (mask != 0 && (mask == 1) != (rr + r0 <= thr)) continue;
-                sm.acc[rr] += t.v[(long)a * t.stride];
+                sm.acc[rr] += v[(long)a * stride];
               }
             }
-          } else if (tid < t.n) {
-            const int rr = __ldg(t.rows + tid) - r0;
+          } else if (tid < n) {
+            const int rr = __ldg(rows + tid) - r0;
             if ((unsigned)rr < (unsigned)h && (mask == 0 || (mask == 1) == (rr + r0 <= thr)))
-              sm.acc[rr] += __ldg(t.v + (long)tid * t.stride);
+              sm.acc[rr] += __ldg(v + (long)tid * stride);
           }
           __syncthreads();
         }
       }
     }
-#ifndef CM_EMU
-    if (kBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my tile writes -> async proxy
-#endif
-    __syncthreads();
 
-    // write-back: local[c, r0 + i] += acc[i], 16 bytes per thread step, untouched pieces skipped
+    // write-back: local[c, r0 + i] += acc[i]
     T *dcol = local + c * g.lld + r0;
-    constexpr int kPer = 16 / (int)sizeof(T);
+    const bool aligned = (reinterpret_cast<uintptr_t>(dcol) & 15) == 0;
 #ifndef CM_EMU
-    if (kBulk && (reinterpret_cast<uintptr_t>(dcol) & 15) == 0 && ((h * (int)sizeof(T)) & 15) == 0) {
+    if (bulk && aligned && ((h * (int)sizeof(T)) & 15) == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my tile writes -> async proxy
+      __syncthreads();
       if (tid == 0) {
         bulk_reduce_add(dcol, sm.acc, (unsigned)(h * (int)sizeof(T)));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile has been read: it may be re-zeroed
       }
-    } else
+      __syncthreads();  // the next unit re-zeroes acc
+      continue;
+    }
 #endif
-    if ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) {
+    __syncthreads();
+    constexpr int kPer = 16 / (int)sizeof(T);
+    if (aligned) {
+      // 16 bytes per thread step (LDS.128 / LDG.128 / STG.128), untouched pieces skipped
       const int hv = h / kPer;
+      const Vec16<T> *acc16 = reinterpret_cast<const Vec16<T> *>(sm.acc);
+      Vec16<T> *d16 = reinterpret_cast<Vec16<T> *>(dcol);
 #pragma unroll 4
       for (int i = tid; i < hv; i += 256) {
-        T a[kPer];
+        const Vec16<T> a = acc16[i];
         bool any = false;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          a[k] = sm.acc[i * kPer + k];
-          any |= a[k] != T(0);
-        }
+        for (int k = 0; k < kPer; ++k) any |= a.x[k] != T(0);
         if (any) {
-          T *p = dcol + (long)i * kPer;
-          T q[kPer];
+          Vec16<T> q = d16[i];
 #pragma unroll
-          for (int k = 0; k < kPer; ++k) q[k] = p[k];
-#pragma unroll
-          for (int k = 0; k < kPer; ++k) p[k] = q[k] + a[k];
+          for (int k = 0; k < kPer; ++k) q.x[k] += a.x[k];
+          d16[i] = q;
         }
       }
       for (int i = hv * kPer + tid; i < h; i += 256)
@@ -1149,282 +1187,51 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
     __syncthreads();  // the next unit re-zeroes acc
   }
 #ifndef CM_EMU
-  if (kBulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reductions performed
+  if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reductions performed
 #endif
 }
 
-// ------------------------------------------------------------------------------------
-// (6c) column-tile scatter-add, TMA variant. Same ownership and ordering as k_apply_tile, but the
-// values (n*s bytes, contiguous) and row indices (n*4 bytes) of each item are brought into a
-// kTmaStages-deep shared-memory ring by 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that one
-// thread issues and that complete on per-stage mbarriers: a dozen items are in flight per block at
-// no register cost. Eligible items are 16-byte aligned with n % 4 == 0 (always true for the
-// payloads of K1-shaped updates); other items fall back to per-thread loads inside the same loop.
-// ------------------------------------------------------------------------------------
-#ifndef CM_EMU  // inline PTX (mbarrier, cp.async.bulk): not part of the host-compiled logic tests
-constexpr int kTmaStages = 12;
-
-template <typename T>
-struct TileSmemTma {
-  static constexpr int kTileRows = 65536 / (int)sizeof(T);
-  T acc[kTileRows];
-  alignas(16) T vals[kTmaStages][256];
-  alignas(16) int rows[kTmaStages][256];
-  TileItem<T> item[kRecChunk];
-  alignas(8) unsigned long long full[kTmaStages];
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 2) k_apply_tile_tma(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
-                                                           long ncols, long m_local, T *local, Geom g) {
-  CM_DYN_SMEM(smem_raw);
-  TileSmemTma<T> &sm = *reinterpret_cast<TileSmemTma<T> *>(smem_raw);
-  const int tid = threadIdx.x;
-  const int h = (int)m_local;  // one tile covers all local rows (the launcher guarantees it)
-  if (tid == 0) {
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&sm.full[s], 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  unsigned phase = 0;  // bit s = parity the next wait on stage s expects (identical in every thread)
-
-  // thread 0: start the bulk copies of staged item j into its ring stage (or just arrive)
-  auto fill = [&](int j) {
-    const TileItem<T> t = sm.item[j];
-    const int s = j % kTmaStages;
-    if (t.pad) {
-      mbar_arrive_expect_tx(&sm.full[s], (unsigned)t.n * (unsigned)(sizeof(T) + 4));
-      tma_load_1d(sm.vals[s], t.v, (unsigned)t.n * (unsigned)sizeof(T), &sm.full[s]);
-      tma_load_1d(sm.rows[s], t.rows, (unsigned)t.n * 4u, &sm.full[s]);
-    } else {
-      mbar_arrive(&sm.full[s]);
-    }
-  };
-
-  for (long c = blockIdx.x; c < ncols; c += gridDim.x) {
-    const long lo = col_start[c], hi = col_start[c + 1];
-    if (lo == hi) continue;  // uniform: nothing for this column in this flush
-    for (int i = tid; i < h; i += 256) sm.acc[i] = T(0);
-
-    for (long base = lo; base < hi; base += kRecChunk) {
-      const int cnt = (int)min((long)kRecChunk, hi - base);
-      __syncthreads();  // previous chunk fully consumed; acc zeroed
-      int special = 0;
-      if (tid < cnt) {
-        const ItemRec r = recs[base + tid];
-        TileItem<T> t;
-        t.v = static_cast<const T *>(r.v);
-        t.rows = r.lrow;
-        t.n = r.n;
-        t.stride = r.row_stride;
-        t.mf = r.mask_flags;
-        // bulk-copy eligible: unit stride, 16-byte aligned sources, sizes multiples of 16 bytes
-        t.pad = (r.row_stride == 1 && (r.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(r.v) & 15) == 0) &&
-                 ((reinterpret_cast<uintptr_t>(r.lrow) & 15) == 0))
-                    ? 1
-                    : 0;
-        sm.item[tid] = t;
-        special = r.mask_flags | (r.row_stride != 1);
-      }
-      const bool plain = __syncthreads_or(special) == 0;  // no mask, no repeated rows, unit stride
-      if (plain) {
-        if (tid == 0)
-          for (int j = 0; j < min(cnt, kTmaStages); ++j) fill(j);
-        for (int k = 0; k < cnt; ++k) {
-          const int s = k % kTmaStages;
-          mbar_wait(&sm.full[s], (phase >> s) & 1u);
-          phase ^= 1u << s;
-          const TileItem<T> t = sm.item[k];
-          if (tid < t.n) {
-            int rr;
-            T x;
-            if (t.pad) {
-              rr = sm.rows[s][tid];
-              x = sm.vals[s][tid];
-            } else {
-              rr = __ldg(t.rows + tid);
-              x = __ldg(t.v + tid);
-            }
-            if ((unsigned)rr < (unsigned)h) sm.acc[rr] += x;
-          }
-          __syncthreads();  // items strictly in order; stage s is free again
-          if (tid == 0 && k + kTmaStages < cnt) fill(k + kTmaStages);
-        }
-      } else {
-        // masked (symmetric update / fill_lower), strided or repeated-row items: simple in-order loop
-        const int thr = mask_threshold(global_index(c, g.nb, g.npcol, g.mypcol), m_local, g);
-        for (int j = 0; j < cnt; ++j) {
-          const TileItem<T> t = sm.item[j];
-          const int mask = t.mf & 0xff;
-          if (t.mf >> 8) {
-            if (tid == 0) {  // rows may repeat: one thread applies the item serially
-              for (int a = 0; a < t.n; ++a) {
-                const int rr = t.rows[a];
-                if ((unsigned)rr >= (unsigned)h) continue;
-                if (mask != 0 && (mask == 1) != (rr <= thr)) continue;
-                sm.acc[rr] += t.v[(long)a * t.stride];
-              }
-            }
-          } else if (tid < t.n) {
-            const int rr = __ldg(t.rows + tid);
-            if ((unsigned)rr < (unsigned)h && (mask == 0 || (mask == 1) == (rr <= thr)))
-              sm.acc[rr] += __ldg(t.v + (long)tid * t.stride);
-          }
-          __syncthreads();
-        }
-      }
-    }
-    __syncthreads();
-
-    // write-back: local[c, i] += acc[i], 16 bytes per thread step, untouched pieces skipped
-    T *dcol = local + c * g.lld;
-    constexpr int kPer = 16 / (int)sizeof(T);
-    if ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) {
-      const int hv = h / kPer;
-#pragma unroll 4
-      for (int i = tid; i < hv; i += 256) {
-        T a[kPer];
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          a[k] = sm.acc[i * kPer + k];
-          any |= a[k] != T(0);
-        }
-        if (any) {
-          T *p = dcol + (long)i * kPer;
-          T q[kPer];
-#pragma unroll
-          for (int k = 0; k < kPer; ++k) q[k] = p[k];
-#pragma unroll
-          for (int k = 0; k < kPer; ++k) p[k] = q[k] + a[k];
-        }
-      }
-      for (int i = hv * kPer + tid; i < h; i += 256)
-        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
-    } else {
-      for (int i = tid; i < h; i += 256)
-        if (sm.acc[i] != T(0)) dcol[i] += sm.acc[i];
-    }
-    __syncthreads();  // the next column re-zeroes acc
-  }
-}
-
-template <typename T>
-static void launch_tile_tma(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                            const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
-  const size_t smem = sizeof(TileSmemTma<T>);
-  static int resident = 0;
-  if (resident == 0) {
-    cudaFuncSetAttribute(k_apply_tile_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resident = resident_blocks(k_apply_tile_tma<T>, 256, smem);
-  }
-  const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  CM_LAUNCH((unsigned)std::min({n_local, (long)resident, cap}), 256, smem, s, k_apply_tile_tma<T>)(d_recs, d_col_start, n_local,
-                                                                                       m_local, d_local, g);
-}
-
-#endif  // CM_EMU
-
-template <typename T, bool kMulti, int BLK, int CTAS, bool kBulk = false>
+template <typename T, bool kMulti, int BLK, int CTAS>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
                                 T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
   static int resident = 0;
+  static int bulk = 1;
   if (resident == 0) {
     if (getenv("CM_B200_TILE_PREFETCH")) {
       const int pf = atoi(getenv("CM_B200_TILE_PREFETCH"));
       cudaMemcpyToSymbol(c_tile_prefetch, &pf, sizeof(int));
     }
-    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS, kBulk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS, kBulk>, 256, smem);
+    if (getenv("CM_B200_TILE_BULKRED")) bulk = atoi(getenv("CM_B200_TILE_BULKRED")) != 0;  // 0: per-thread write-back
+    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
   }
   const long nunits = n_local * ntiles;
   // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
-  // the next chunk in a pipelined commit)
+  // the next panel in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS, kBulk>)(
-      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g);
+  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS>)(
+      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, bulk);
 }
 
 template <typename T>
 static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                                const Geom &g, int max_blocks_per_sm, bool tma_hint, cudaStream_t s) {
+                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
-  // TMA ring variant: opt-in (CM_B200_TILE_TMA=1 when the caller knows the items are bulk-copy
-  // eligible, =2 always). Measured on K1 (B200) it is slower than the register-prefetch kernel,
-  // 0.97 vs 0.61 ms per 131 M elements: two 1-2 KiB bulk copies per item keep the SM's TMA unit
-  // busy ~550 cycles per item, more than the whole register path costs.
-  static const int tma_mode = getenv("CM_B200_TILE_TMA") ? atoi(getenv("CM_B200_TILE_TMA")) : 0;  // 0 never, 1 hint, 2 always
-#ifndef CM_EMU
-  if (ntiles == 1 && (tma_mode == 2 || (tma_mode == 1 && tma_hint))) {
-    launch_tile_tma<T>(d_recs, d_col_start, n_local, m_local, d_local, g, max_blocks_per_sm, s);
-    return;
-  }
-#else
-  (void)tma_mode;
-#endif
-#ifndef CM_EMU
-  // opt-in: write-back by one bulk reduce-add per tile (default item sets only)
-  static const int bulk_red = getenv("CM_B200_TILE_BULKRED") ? atoi(getenv("CM_B200_TILE_BULKRED")) : 0;
-  if (bulk_red) {
-    if (ntiles == 1)
-      launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-    else
-      launch_tile_variant<T, true, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-    return;
-  }
-#endif
-  // variant 0 (default): 6-item sets, 3 blocks per SM; variant 1: 12-item sets, 2 blocks per SM
-  static const int variant = getenv("CM_B200_TILE_VARIANT") ? atoi(getenv("CM_B200_TILE_VARIANT")) : 0;
-  if (ntiles == 1) {
-    if (variant == 1)
-      launch_tile_variant<T, false, 12, 2>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-    else if (variant == 2)
-      launch_tile_variant<T, false, 8, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-    else
-      launch_tile_variant<T, false, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-  } else {
-    if (variant == 1)
-      launch_tile_variant<T, true, 12, 2>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-    else
-      launch_tile_variant<T, true, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
-  }
+  // 6-item register sets, 3 blocks per SM (measured best on B200; 8- and 12-item sets spill or lose residency)
+  if (ntiles == 1)
+    launch_tile_variant<T, false, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+  else
+    launch_tile_variant<T, true, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
-                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, bool tma_hint, cudaStream_t s) {
+                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   if (nitems <= 0) return;
   switch (dtype) {
-    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
-    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
-    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, tma_hint, s); break;
+    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, s); break;
+    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, s); break;
+    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, s); break;
   }
 }
 

@@ -100,7 +100,7 @@ void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, c
 // (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
                        void *d_local, long n_local, long m_local, const Geom &g, int max_blocks_per_sm,
-                       bool tma_hint, cudaStream_t s);
+                       cudaStream_t s);
 // COO path for elemental updates: local[inds[k]] += vals[k]
 void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local,
                       cudaStream_t s);

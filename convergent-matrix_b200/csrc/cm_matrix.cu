@@ -359,7 +359,6 @@ struct cm_matrix {
   std::vector<long> item_base;  // single-rank path: first item of each update
   long staged_elems = 0, staged_rows = 0, staged_cols = 0, staged_items = 0;
   bool borrowed_pending = false;  // device-API payloads staged since the last flush
-  bool staged_tma_ok = true;      // all staged payloads are 16-byte aligned, unit stride, m % 4 == 0, even ld
   DevArena payload_arena{64ull << 20};
   MirrorArena index_arena{4ull << 20};
   std::vector<CooBin> coo;  // [owner]
@@ -479,7 +478,6 @@ void clear_staged(cm_matrix *M) {
   M->item_base.clear();
   M->staged_elems = M->staged_rows = M->staged_cols = M->staged_items = 0;
   M->borrowed_pending = false;
-  M->staged_tma_ok = true;
   M->payload_arena.reset();
   M->index_arena.reset();
   for (auto &b : M->coo) {
@@ -578,8 +576,7 @@ int seg_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nsegs, long elem
 }
 
 // sort (optional) + scatter-add over nitems (key,item) pairs sitting in w.keys0 / w.items0
-int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0,
-                   bool tma_hint = false) {
+int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0) {
   if (nitems <= 0) return CM_OK;
   const uint64_t *items = w.items0.as<uint64_t>();
   const uint32_t *keys = w.keys0.as<uint32_t>();
@@ -612,7 +609,7 @@ int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, lon
     ScopedTimer t(M, 0, elements, st);
     if (tile)
       launch_apply_tile(M->dtype, w.recs.as<ItemRec>(), w.col_start.as<long>(), nitems, M->d_local, M->n_local,
-                        M->m_local, M->g, max_blocks_per_sm, tma_hint, st);
+                        M->m_local, M->g, max_blocks_per_sm, st);
     else
       launch_apply_red(M->dtype, w.recs.as<ItemRec>(), nitems, elements, M->d_local, M->g, st);
     M->stats.kernel_launches += 1;
@@ -683,11 +680,10 @@ int flush_direct(cm_matrix *M, bool sync = true) {
                           by_seg ? nullptr : w.items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
     }
-    // every staged payload is laid out so that its 256-row column chunks can be bulk-copied
     if (by_seg)
       CM_TRY(seg_apply(M, w, M->stream, nupd, M->staged_elems));
     else
-      CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0, M->staged_tma_ok));
+      CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0));
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
@@ -1551,8 +1547,6 @@ int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, in
   d.rbase = M->staged_rows;
   d.cbase = M->staged_cols;
   M->descs.push_back(d);
-  M->staged_tma_ok = M->staged_tma_ok && !trans && (m_u & 3) == 0 && ((ld * (long)M->esz) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(d_data) & 15) == 0 && mask == 0;
   M->item_base.push_back(M->staged_items);
   M->staged_rows += m_u;
   M->staged_cols += n_u;

@@ -171,7 +171,7 @@ int cm_dtype(const cm_matrix *M);
 
 /* bin_flush_threshold, :507-514 — number of staged update ELEMENTS above which update()
  * triggers a local flush (strict '>', :346). Default CM_DEFAULT_FLUSH_THRESHOLD. */
-#define CM_DEFAULT_FLUSH_THRESHOLD (1L << 27)
+#define CM_DEFAULT_FLUSH_THRESHOLD (1L << 30)
 long cm_get_flush_threshold(const cm_matrix *M);
 int cm_set_flush_threshold(cm_matrix *M, long elements);
 /* progress_interval, :529-545 — stored for API compatibility; there is no progress engine. */

@@ -353,9 +353,11 @@ void cmref_wire_clear(void *h) {
 // all ranks released together by a barrier. If pin != 0, rank r is pinned to core
 // (r % ncores). out_secs[0] = max total, out_secs[1] = max time inside update() calls
 // (binning + threshold flushes), out_secs[2] = max time inside commit().
+// data_period > 0: update u reads payload (u % data_period) — the index sets are all distinct, the
+// payload buffers of a bounded sample are cycled (payload values do not influence the time).
 void cmref_bench_slices(void *h, const void *const *data, const long *const *ix,
                         const long *const *jx, long nupd, long m_u, long n_u,
-                        long commit_every, int pin, double *out_secs) {
+                        long commit_every, int pin, double *out_secs, long data_period) {
   Session *s = static_cast<Session *>(h);
   const size_t esz = dtype_size(s->dtype);
   std::vector<double> t_total(s->P), t_upd(s->P), t_commit(s->P);
@@ -370,7 +372,8 @@ void cmref_bench_slices(void *h, const void *const *data, const long *const *ix,
     double upd = 0, com = 0;
     for (long u = 0; u < nupd; ++u) {
       const auto a = clk::now();
-      M->update_slice(d + (size_t)u * m_u * n_u * esz, m_u, n_u, m_u, 0,
+      const long du = data_period > 0 ? u % data_period : u;
+      M->update_slice(d + (size_t)du * m_u * n_u * esz, m_u, n_u, m_u, 0,
                       const_cast<long *>(ix[r] + u * m_u), const_cast<long *>(jx[r] + u * n_u));
       const auto b = clk::now();
       upd += std::chrono::duration<double>(b - a).count();

@@ -54,6 +54,8 @@ VARIANTS = [
     ("tile", "K3", {}, {"apply_kernel": 2}),
     ("flush-2^26", "K1", {}, {"flush_threshold": 1 << 26, "n1_only": True}),
     ("flush-2^28", "K1", {}, {"flush_threshold": 1 << 28, "n1_only": True}),
+    ("flush-2^29", "K1", {}, {"flush_threshold": 1 << 29, "n1_only": True}),
+    ("flush-2^30", "K1", {}, {"flush_threshold": 1 << 30, "n1_only": True}),
     ("flush-2^26-pinned-descs", "K1", {"CM_B200_PINNED_DESCS": "1"}, {"flush_threshold": 1 << 26, "n1_only": True}),
     ("dma", "K1,K2", {"CM_B200_EXCHANGE": "dma"}, {}),
 ]

@@ -211,7 +211,7 @@ class RefShim:
             L.cmref_wire_copy.argtypes = [_vp, _i, _i, _lp, _vp]
             L.cmref_wire_clear.argtypes = [_vp]
             L.cmref_bench_slices.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_lp), C.POINTER(_lp),
-                                             _l, _l, _l, _l, _i, C.POINTER(C.c_double)]
+                                             _l, _l, _l, _l, _i, C.POINTER(C.c_double), _l]
             cls._lib = L
         return cls._lib
 
@@ -305,14 +305,15 @@ class RefShim:
     def wire_clear(self):
         self.L.cmref_wire_clear(self.h)
 
-    def bench_slices(self, data, ix, jx, m_u, n_u, commit_every=0, pin=True):
+    def bench_slices(self, data, ix, jx, m_u, n_u, commit_every=0, pin=True, data_period=0):
         """data/ix/jx: per-rank lists of contiguous arrays ([nupd, n_u, m_u] payloads stored
-        column-major per update, [nupd, m_u], [nupd, n_u]). Returns (total_s, update_s, commit_s)."""
+        column-major per update, [nupd, m_u], [nupd, n_u]). Returns (total_s, update_s, commit_s).
+        data_period > 0: data holds only that many payloads per rank, cycled over the nupd updates."""
         P = self.P
         nupd = ix[0].shape[0]
         dptr = (_vp * P)(*[_ptr(d) for d in data])
         iptr = (_lp * P)(*[_lptr(a) for a in ix])
         jptr = (_lp * P)(*[_lptr(a) for a in jx])
         out = (C.c_double * 3)()
-        self.L.cmref_bench_slices(self.h, dptr, iptr, jptr, nupd, m_u, n_u, commit_every, int(pin), out)
+        self.L.cmref_bench_slices(self.h, dptr, iptr, jptr, nupd, m_u, n_u, commit_every, int(pin), out, data_period)
         return out[0], out[1], out[2]

@@ -267,7 +267,7 @@ def test_accessors_descriptor_host_mirror_and_knobs():
         M = cm.Matrix(*cfg.args())
         assert (M.m, M.n, M.m_local, M.n_local, M.lld, M.pgrid_row, M.pgrid_col) == (2000, 1000, 2000, 1000, 2048, 0, 0)
         assert M.descinit(3) == [1, 3, 2000, 1000, 64, 64, 0, 0, 2048]
-        assert M.flush_threshold() == 1 << 27 and M.progress_interval() == 1
+        assert M.flush_threshold() == 1 << 30 and M.progress_interval() == 1
         M.set_flush_threshold(12345)
         M.set_progress_interval(0)
         assert M.flush_threshold() == 12345 and M.progress_interval() == 0
