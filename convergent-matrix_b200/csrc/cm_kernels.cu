@@ -230,33 +230,6 @@ void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &
 }
 
 // ------------------------------------------------------------------------------------
-// (2b) device-side layout: thread d walks owner d's arena in the order the host does (panel after
-// panel, source after source; cm_matrix.cu, commit_exchange) and notes where THIS rank's messages start.
-// ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_layout(const MsgCounts *__restrict__ counts, int P, int me, int esz, ArenaTable at,
-                                                void **__restrict__ dst_vals, char **__restrict__ dst_meta, int *overflow) {
-  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P; d += gridDim.x * blockDim.x) {
-    long ov = at.base_v[d], om = at.base_m[d];
-    for (int k = 0; k < kMaxChunks; ++k)
-      for (int src = 0; src < P; ++src) {
-        const MsgCounts c = counts[((long)src * kMaxChunks + k) * P + d];
-        if (src == me) {
-          dst_vals[k * P + d] = at.vals[d] + ov * esz;
-          dst_meta[k * P + d] = at.meta[d] + om;
-        }
-        ov += (c.nvals + 31) & ~31L;  // every message on a 256-byte boundary
-        om += meta_bytes(c.nseg, c.nidx);
-      }
-    if (ov * esz > at.cap_vals[d] || om > at.cap_meta[d]) atomicOr(overflow, 1);
-  }
-}
-
-void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, const ArenaTable &at, void **dst_vals,
-                   char **dst_meta, int *overflow, cudaStream_t s) {
-  CM_LAUNCH((nranks + 255) / 256, 256, 0, s, k_layout)(d_counts_all, nranks, me, esz, at, dst_vals, dst_meta, overflow);
-}
-
-// ------------------------------------------------------------------------------------
 // (3) pack. grid (nupd, ytiles): block (u, y) handles the grouped columns y, y+ytiles, ... of the
 // panels [k0, k1) of update u: for every owner row p it gathers the rows R_p of that column into
 // the (panel, p, q) segment — contiguous, coalesced stores; gathers hit every sector of the source
@@ -307,12 +280,11 @@ __device__ __forceinline__ void pack_write_meta(const UpdDesc &d, int u, int nup
     }
 }
 
-// NC = columns a thread keeps in flight (4; 8 = opt-in CM_B200_PACK_COLS=8: twice the bytes in flight per
-// thread, for when the kernel shares the SMs with a scatter-add and has fewer resident threads)
-template <typename T, int NC>
+constexpr int kPackCols = 4;  // columns a thread keeps in flight (8 measured no faster: NVLink-bound)
+template <typename T>
 __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1, PanelPlan pp,
                                                        Geom g, MapArenas ma, ScanArenas sa) {
-  if (sa.overflow != nullptr && *sa.overflow != 0) return;  // speculative launch, an arena has to grow first
+  constexpr int NC = kPackCols;
   const int u = blockIdx.x;
   const UpdDesc d = descs[u];
   const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
@@ -392,137 +364,6 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(const UpdDesc *__restrict
   if (blockIdx.y == 0) pack_write_meta(d, u, nupd, k0, k1, nprow, npcol, roff, coff, ma, sa);
 }
 
-// ------------------------------------------------------------------------------------
-// (3') pack with bulk stores (opt-in, CM_B200_PACK_BULK=1). Same segments, same message layout as
-// k_pack, but a column's run of rows for one owner row is first gathered into shared memory and then
-// leaves the SM as ONE bulk copy (cp.async.bulk.global.shared::cta, 1-2 KB) instead of 128-byte
-// stores by half-warps: larger write requests towards NVLink, no store instructions on the SM. Eight
-// columns per stage, two stages: the gathers of stage g+1 overlap the bulk copies of stage g. Owner
-// rows whose runs are short (< 64 rows: dense, unaligned segments) or not a multiple of 16 bytes keep
-// the per-thread stores. Needs an update's thread slots (rows + 16 per owner row) to fit kBulkSlots.
-// ------------------------------------------------------------------------------------
-constexpr int kBulkThreads = 256;
-constexpr int kBulkCols = 8;
-constexpr int kBulkSlots = 544;
-
-#ifdef CM_EMU
-#define CM_BULK_STORE(dst, src, bytes) memcpy(dst, src, bytes)
-#define CM_BULK_COMMIT() ((void)0)
-#define CM_BULK_WAIT_READ_1() ((void)0)
-#define CM_BULK_WAIT_ALL() ((void)0)
-#define CM_FENCE_ASYNC_SMEM() ((void)0)
-#else
-#define CM_BULK_STORE(dst, src, bytes)                                                                         \
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),                       \
-               "r"((unsigned)__cvta_generic_to_shared(src)), "r"((unsigned)(bytes))                            \
-               : "memory")
-#define CM_BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
-#define CM_BULK_WAIT_READ_1() asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory")
-#define CM_BULK_WAIT_ALL() asm volatile("cp.async.bulk.wait_group 0;" ::: "memory")
-#define CM_FENCE_ASYNC_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
-#endif
-
-template <typename T>
-__global__ void __launch_bounds__(kBulkThreads) k_pack_bulk(const UpdDesc *__restrict__ descs, int nupd, int k0, int k1,
-                                                            PanelPlan pp, Geom g, MapArenas ma, ScanArenas sa) {
-  if (sa.overflow != nullptr && *sa.overflow != 0) return;
-  CM_DYN_SMEM(smem_raw);
-  T(*stage)[kBulkCols][kBulkSlots] = reinterpret_cast<T(*)[kBulkCols][kBulkSlots]>(smem_raw);  // [2][cols][slots]
-  const int u = blockIdx.x;
-  const UpdDesc d = descs[u];
-  const int nprow = (int)g.nprow, npcol = (int)g.npcol, P = nprow * npcol;
-  const int ncg = npcol * pp.npanel;
-  __shared__ int roff[kMaxGridDim + 1];
-  __shared__ int coff[kMaxGridDim + 1];
-  __shared__ int tstart[kMaxGridDim + 1];
-  __shared__ int gdst[kMaxGridDim];
-  __shared__ T *base[kPackMaxDst];
-  const int tid = threadIdx.x;
-  if (tid <= nprow) roff[tid] = ma.roff[(long)u * (nprow + 1) + tid];
-  if (tid <= ncg) coff[tid] = ma.coff[(long)u * (ncg + 1) + tid];
-  if (tid < ncg) gdst[tid] = (tid / npcol - k0) * P + tid % npcol;
-  for (int i = tid; i < (k1 - k0) * P; i += blockDim.x) {
-    const int k = k0 + i / P, dst = i % P;
-    base[i] = static_cast<T *>(sa.dst_vals[k * P + dst]) + sa.valoff[((long)k * P + dst) * nupd + u];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int p = 0; p < nprow; ++p) {
-      tstart[p] = acc;
-      acc += (roff[p + 1] - roff[p] + kSegAlign - 1) & ~(kSegAlign - 1);
-    }
-    tstart[nprow] = acc;
-  }
-  __syncthreads();
-  const T *__restrict__ data = static_cast<const T *>(d.data);
-  const int *__restrict__ rpos = ma.rpos + d.rbase;
-  const int *__restrict__ cpos = ma.cpos + d.cbase;
-  const long src_rs = d.trans ? d.ld : 1, src_cs = d.trans ? 1 : d.ld;
-  const int cbeg = coff[k0 * npcol], cend = coff[k1 * npcol];
-  const int gy = (int)gridDim.y;
-  const int nslots = tstart[nprow];  // <= kBulkSlots (the launcher checks)
-
-  // the issuing thread j handles (column i of the stage, owner row p): j = i * nprow + p
-  const bool issuer = tid < kBulkCols * nprow;
-  const int my_i = tid / nprow, my_p = tid % nprow;
-  int ngroups = 0;
-  for (int kc0 = cbeg + (int)blockIdx.y; kc0 < cend; kc0 += kBulkCols * gy, ++ngroups) {
-    const int sidx = ngroups & 1;
-    // stage sidx was last used two groups ago: its bulk copies must have read it
-    if (issuer) CM_BULK_WAIT_READ_1();
-    __syncthreads();
-    // gather: slot t of column i -> stage[sidx][i][t]; owner rows that cannot go by bulk copy store directly
-    for (int t = tid; t < nslots; t += blockDim.x) {
-      int p = 0;
-      while (t >= tstart[p + 1]) ++p;
-      const int a = t - tstart[p];
-      const int nr = roff[p + 1] - roff[p];
-      if (a >= nr) continue;
-      const bool by_bulk = nr >= 64 && ((nr * (int)sizeof(T)) & 15) == 0;
-      const int stride = seg_col_stride(nr);
-      const long srow = (long)rpos[roff[p] + a] * src_rs;
-      int cp[kBulkCols];
-      T x[kBulkCols];
-#pragma unroll
-      for (int i = 0; i < kBulkCols; ++i) {
-        const int c = kc0 + i * gy;
-        cp[i] = c < cend ? cpos[c] : -1;
-      }
-#pragma unroll
-      for (int i = 0; i < kBulkCols; ++i) x[i] = cp[i] >= 0 ? data[srow + (long)cp[i] * src_cs] : T(0);
-      if (by_bulk) {
-#pragma unroll
-        for (int i = 0; i < kBulkCols; ++i) stage[sidx][i][t] = x[i];
-      } else {
-        int gq = k0 * npcol;
-#pragma unroll
-        for (int i = 0; i < kBulkCols; ++i) {
-          const int c = kc0 + i * gy;
-          if (c >= cend) break;
-          while (c >= coff[gq + 1]) ++gq;
-          base[gdst[gq] + p * npcol][(long)(c - coff[gq]) * stride + a] = x[i];
-        }
-      }
-    }
-    CM_FENCE_ASYNC_SMEM();  // my shared-memory writes become visible to the bulk-copy engine
-    __syncthreads();
-    if (issuer) {
-      const int c = kc0 + my_i * gy;
-      const int nr = roff[my_p + 1] - roff[my_p];
-      if (c < cend && nr >= 64 && ((nr * (int)sizeof(T)) & 15) == 0) {
-        int gq = k0 * npcol;
-        while (c >= coff[gq + 1]) ++gq;
-        T *dst = base[gdst[gq] + my_p * npcol] + (long)(c - coff[gq]) * seg_col_stride(nr);
-        CM_BULK_STORE(dst, &stage[sidx][my_i][tstart[my_p]], nr * (int)sizeof(T));
-      }
-      CM_BULK_COMMIT();  // one group per stage and issuing thread, empty or not
-    }
-  }
-  if (issuer) CM_BULK_WAIT_ALL();
-  if (blockIdx.y == 0) pack_write_meta(d, u, nupd, k0, k1, nprow, npcol, roff, coff, ma, sa);
-}
-
 static int pick_ytiles(int nupd, long max_cols) {
   const int target = kernel_sm_count() * 8;
   long y = (target + nupd - 1) / nupd;
@@ -534,12 +375,10 @@ static int pick_ytiles(int nupd, long max_cols) {
 }
 
 // Block size of the pack kernel. Thread slot t <-> one row of the update (slots of one owner row padded
-// to 16), so an update of m_u rows has about m_u + 16 * NPROW slots. 384 threads (default, measured)
-// leave a third of the block idle on 256-row updates; CM_B200_PACK_THREADS=0 sizes the block to the
-// slots (a whole number of passes with few idle threads; more blocks resident per SM), any other
-// value is used as is.
-static int pack_threads(int cfg, long max_rows, long nprow) {
-  if (cfg > 0) return std::min(std::max((cfg + 31) & ~31, 32), kPackThreads);
+// to 16), so an update of m_u rows has about m_u + 16 * NPROW slots: the block is sized to a whole number
+// of passes over the slots with few idle threads (B200, 8 GPUs: K4's 32-row updates 36.0 -> 31.5 ms per
+// step against a fixed 384-thread block; neutral on 256- and 512-row updates, which are NVLink-bound).
+static int pack_threads(long max_rows, long nprow) {
   const long slots = std::max(32L, max_rows + 16 * nprow);
   const long passes = (slots + kPackThreads - 1) / kPackThreads;
   const long per = (slots + passes - 1) / passes;
@@ -547,39 +386,14 @@ static int pack_threads(int cfg, long max_rows, long nprow) {
 }
 
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp, const Geom &g,
-                 const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc, cudaStream_t s) {
+                 const MapArenas &ma, const ScanArenas &sa, long max_rows, cudaStream_t s) {
   if (nupd <= 0 || k1 <= k0) return;
   const dim3 grid(nupd, pick_ytiles(nupd, 4096));
-  if (pc.bulk && max_rows + 16 * g.nprow <= kBulkSlots && kBulkCols * g.nprow <= kBulkThreads) {
-    const size_t smem = 2 * (size_t)kBulkCols * kBulkSlots * dtype_size(dtype);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_pack_bulk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 8));
-      cudaFuncSetAttribute(k_pack_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 4));
-      cudaFuncSetAttribute(k_pack_bulk<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kBulkCols * kBulkSlots * 4));
-      attr_set = true;
-    }
-    switch (dtype) {
-      case 0: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<double>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      case 1: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<float>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      default: CM_LAUNCH(grid, kBulkThreads, smem, s, k_pack_bulk<int>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    }
-    return;
-  }
-  const int threads = pack_threads(pc.threads, max_rows, g.nprow);
-  const int ncols = pc.cols;
-  if (ncols == 8) {
-    switch (dtype) {
-      case 0: CM_LAUNCH(grid, threads, 0, s, k_pack<double, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      case 1: CM_LAUNCH(grid, threads, 0, s, k_pack<float, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-      default: CM_LAUNCH(grid, threads, 0, s, k_pack<int, 8>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    }
-    return;
-  }
+  const int threads = pack_threads(max_rows, g.nprow);
   switch (dtype) {
-    case 0: CM_LAUNCH(grid, threads, 0, s, k_pack<double, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    case 1: CM_LAUNCH(grid, threads, 0, s, k_pack<float, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
-    default: CM_LAUNCH(grid, threads, 0, s, k_pack<int, 4>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 0: CM_LAUNCH(grid, threads, 0, s, k_pack<double>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    case 1: CM_LAUNCH(grid, threads, 0, s, k_pack<float>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
+    default: CM_LAUNCH(grid, threads, 0, s, k_pack<int>)(d_descs, nupd, k0, k1, pp, g, ma, sa); break;
   }
 }
 
@@ -839,50 +653,6 @@ void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elemen
 }
 
 // ------------------------------------------------------------------------------------
-// (6a') scatter-add straight from the Seg table: one warp per segment, lanes over its nr x nc
-// elements in column-major order (coalesced value loads), one RED per element. For flushes of
-// small segments — a 32 x 32 update on a 4 x 2 grid leaves 8 x 16 segments — where per-column items
-// (16 items of 8 rows) would cost more to build and sort than to apply.
-// ------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_apply_seg(const Seg *__restrict__ segs, long nsegs, T *__restrict__ local, Geom g) {
-  const int lane = threadIdx.x & 31;
-  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long t = warp; t < nsegs; t += nwarps) {
-    const Seg s = segs[t];
-    if (s.nr <= 0 || s.nc <= 0) continue;
-    const T *__restrict__ v = static_cast<const T *>(s.vals);
-    const long total = (long)s.nr * s.nc;
-    int a = lane % s.nr, b = lane / s.nr;  // element e = a + b * nr
-    const int da = 32 % s.nr, db = 32 / s.nr;
-    for (long e = lane; e < total; e += 32) {
-      const int row = s.lrow[a], col = s.lcol[b];
-      bool keep = true;
-      if (s.mask != 0)
-        keep = mask_keep(s.mask, global_index(row, g.mb, g.nprow, g.myprow), global_index(col, g.nb, g.npcol, g.mypcol));
-      if (keep) red_add(local + (long)col * g.lld + row, v[(long)a * s.row_stride + (long)b * s.col_stride]);
-      a += da;
-      b += db;
-      if (a >= s.nr) {
-        a -= s.nr;
-        ++b;
-      }
-    }
-  }
-}
-
-void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, const Geom &g, cudaStream_t s) {
-  if (nsegs <= 0) return;
-  const long blocks = std::min((nsegs + 7) / 8, (long)kernel_sm_count() * 8);
-  switch (dtype) {
-    case 0: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<double>)(d_segs, nsegs, static_cast<double *>(d_local), g); break;
-    case 1: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<float>)(d_segs, nsegs, static_cast<float *>(d_local), g); break;
-    default: CM_LAUNCH((unsigned)blocks, 256, 0, s, k_apply_seg<int>)(d_segs, nsegs, static_cast<int *>(d_local), g); break;
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // (6b) column-tile scatter-add. One block owns one tile of the local block — one column x up to
 // kTileRows rows (64 KiB) — in shared memory. It walks the column's run of items in sorted order;
 // thread t owns element t of every item (an item is at most kRowChunk = 256 rows of one segment
@@ -984,9 +754,9 @@ __device__ __forceinline__ void tile_load_block(const TileSmem<T> &sm, int j0, i
 }
 
 // L2 prefetch of the value lines of the BLK items starting at `j0` (item i: threads 16*i .. 16*i+15,
-// one 128-byte line each): issued c_tile_prefetch blocks ahead, so that the register loads that
+// one 128-byte line each): issued kTilePrefetchBlocks blocks ahead, so that the register loads that
 // follow later find their data in L2 instead of waiting a full DRAM round trip behind a barrier
-__constant__ int c_tile_prefetch = 2;  // blocks ahead (CM_B200_TILE_PREFETCH)
+constexpr int kTilePrefetchBlocks = 2;  // blocks ahead (B200, K1: 0 -> 2.30, 1 -> 2.16, 2 -> 2.10, 3 -> 2.16 ms per step)
 template <typename T, int BLK>
 __device__ __forceinline__ void tile_prefetch_block(const TileSmem<T> &sm, int j0, int tid) {
   const int i = tid >> 4, line = tid & 15;
@@ -1102,7 +872,7 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         T valA[BLK], valB[BLK];
         unsigned okA = 0, okB = 0;
         const int nblk = (cnt + BLK - 1) / BLK;  // staged padding covers up to kRecChunk
-        const int kTilePrefetch = c_tile_prefetch;
+        constexpr int kTilePrefetch = kTilePrefetchBlocks;
         for (int b = 1; b <= kTilePrefetch && b < nblk; ++b) tile_prefetch_block<T, BLK>(sm, b * BLK, tid);
         tile_load_block<T, BLK>(sm, 0, tid, rowA, valA, okA);
         for (int b = 0; b < nblk; b += 2) {
@@ -1196,13 +966,8 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
                                 T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
   static int resident = 0;
-  static int bulk = 1;
+  const int bulk = 1;  // (0: per-thread write-back everywhere; kept for misaligned columns and the kernel-logic build)
   if (resident == 0) {
-    if (getenv("CM_B200_TILE_PREFETCH")) {
-      const int pf = atoi(getenv("CM_B200_TILE_PREFETCH"));
-      cudaMemcpyToSymbol(c_tile_prefetch, &pf, sizeof(int));
-    }
-    if (getenv("CM_B200_TILE_BULKRED")) bulk = atoi(getenv("CM_B200_TILE_BULKRED")) != 0;  // 0: per-thread write-back
     cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
   }
@@ -1327,44 +1092,6 @@ void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, lon
                                                            static_cast<int *>(d_local));
       break;
   }
-}
-
-// One half of the flag barrier (cm_matrix.cu, commit_stream_barrier): every earlier kernel of this
-// stream has completed — its stores into the peers' arenas included — when this one starts; the
-// fence orders the flag behind them at system scope, the store crosses NVLink into the peer's row.
-__global__ void k_signal_peers(uint32_t *const *__restrict__ peer_rows, int me, int nranks, uint32_t seq) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < nranks && r != me) {
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(peer_rows[r] + me) = seq;
-  }
-}
-
-// The counts all-gather as peer stores: block r copies this rank's totals into rank r's table, fences,
-// and its first thread raises this rank's flag in rank r's arrival row.
-__global__ void __launch_bounds__(256) k_publish_counts(char *const *__restrict__ peer_bases, int me, int nranks,
-                                                        const MsgCounts *__restrict__ totals, long counts_off, long row_off,
-                                                        uint32_t seq) {
-  const int r = blockIdx.x;
-  const long words = (long)sizeof(MsgCounts) / 8 * kMaxChunks * nranks;  // my row, in 8-byte words
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(totals);
-  unsigned long long *dst = reinterpret_cast<unsigned long long *>(peer_bases[r] + counts_off) + (long)me * words;
-  for (long w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0 && r != me) {
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(peer_bases[r] + row_off + 4 * (long)me) = seq;
-  }
-}
-
-void launch_publish_counts(char *const *d_peer_bases, int me, int nranks, const MsgCounts *d_totals, long counts_off,
-                           long row_off, uint32_t seq, cudaStream_t s) {
-  CM_LAUNCH(nranks, 256, 0, s, k_publish_counts)(d_peer_bases, me, nranks, d_totals, counts_off, row_off, seq);
-}
-
-void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s) {
-  CM_LAUNCH((nranks + 127) / 128, 128, 0, s, k_signal_peers)(d_peer_rows, me, nranks, seq);
 }
 
 // global indices of local indices 0..count-1 on process p (:697, :699)

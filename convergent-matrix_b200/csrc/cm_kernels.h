@@ -36,17 +36,6 @@ struct ScanArenas {
   MsgCounts *totals;  // [kMaxChunks * P], index panel * P + owner
   void **dst_vals;    // [kMaxChunks * P] where this rank's message (panel, owner) starts: values ...
   char **dst_meta;    // ... and metadata. May point into a PEER's receive arena (NVLink stores).
-  const int *overflow;  // device-side layout only (launch_layout): non-zero = some arena is too small, pack nothing
-};
-
-// what the device-side layout needs to know about every owner's receive arenas
-struct ArenaTable {
-  char *const *vals;    // [P] base of owner d's values arena as mapped on this rank
-  char *const *meta;    // [P] ... metadata arena
-  const long *cap_vals; // [P] capacities in bytes
-  const long *cap_meta;
-  const long *base_v;   // [P] first free element / byte (non-zero only while a deferred log is pending)
-  const long *base_m;
 };
 
 size_t dtype_size(int dtype);
@@ -57,25 +46,13 @@ void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const Pan
 // (2) per-owner scans over the staged updates (sizes of every message)
 void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,
                  const long *d_coo_counts, cudaStream_t s);
-// (2b) device-side layout of this rank's messages inside the owners' receive arenas, from the
-// all-gathered counts [src][panel][dst] (same arithmetic as the host's): fills sa.dst_vals / dst_meta and
-// raises *overflow when any arena is too small. Lets the pack kernel start without a host round trip.
-void launch_layout(const MsgCounts *d_counts_all, int nranks, int me, int esz, const ArenaTable &at, void **dst_vals,
-                   char **dst_meta, int *overflow, cudaStream_t s);
 // (3) pack: gather Mat[R_p, C_q] into owner (p,q)'s segment + write the wire metadata, straight
 // to sa.dst_vals / sa.dst_meta (local staging, or the owner's receive arena over NVLink)
 // Packs the column panels [k0, k1) of every staged update.
-// max_rows: largest m_u among the staged updates (sizes the block when pc.threads == 0).
-struct PackConfig {
-  int threads = 384;  // block size; 0 = sized to the update's rows (CM_B200_PACK_THREADS)
-  int cols = 4;       // columns a thread keeps in flight, 4 or 8 (CM_B200_PACK_COLS)
-  int bulk = 0;       // 1: runs of rows leave the SM as bulk copies from shared memory (CM_B200_PACK_BULK)
-};
+// max_rows: largest m_u among the staged updates (sizes the block).
 void launch_pack(int dtype, const UpdDesc *d_descs, int nupd, int k0, int k1, const PanelPlan &pp,
-                 const Geom &g, const MapArenas &ma, const ScanArenas &sa, long max_rows, const PackConfig &pc,
-                 cudaStream_t s);
+                 const Geom &g, const MapArenas &ma, const ScanArenas &sa, long max_rows, cudaStream_t s);
 // (4a) single-rank path: segments point straight at the staged payloads (no pack)
-// d_keys == nullptr: the Seg table only (segment-wise scatter-add, launch_apply_seg)
 void launch_build_direct(int dtype, const UpdDesc *d_descs, const long *d_item_base, int nupd,
                          const Geom &g, const MapArenas &ma, Seg *d_segs, uint32_t *d_keys,
                          uint64_t *d_items, cudaStream_t s);
@@ -94,9 +71,6 @@ void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, con
 // (6a) scatter-add with RED.ADD, one warp per item (apply<T>, reference :178-187)
 void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elements, void *d_local, const Geom &g,
                       cudaStream_t s);
-// (6a') scatter-add with RED straight from the Seg table, one warp per segment: for flushes of small
-// segments (tiny updates), where per-column items would be a handful of rows each
-void launch_apply_seg(int dtype, const Seg *d_segs, long nsegs, void *d_local, const Geom &g, cudaStream_t s);
 // (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
                        void *d_local, long n_local, long m_local, const Geom &g, int max_blocks_per_sm,
@@ -110,15 +84,6 @@ void launch_apply_coo_det(int dtype, const long *d_inds, const void *d_vals, lon
                           void *d_temp, size_t temp_bytes, cudaStream_t s);
 // fill_lower helpers: global indices of this rank's local columns / rows (:697, :699)
 void launch_iota_global(long *d_out, long count, long blk, long np, long p, cudaStream_t s);
-
-// barrier over peer memory: flags[me] = seq in every peer's barrier row (system-scope release)
-void launch_signal_peers(uint32_t *const *d_peer_rows, int me, int nranks, uint32_t seq, cudaStream_t s);
-
-// counts all-gather over peer memory: this rank's totals [kMaxChunks * P] go into row `me` of every
-// rank's table (at counts_off inside its peer-mapped block), then flags[me] = seq in every rank's
-// arrival row (at row_off)
-void launch_publish_counts(char *const *d_peer_bases, int me, int nranks, const MsgCounts *d_totals, long counts_off,
-                           long row_off, uint32_t seq, cudaStream_t s);
 
 int kernel_sm_count();
 

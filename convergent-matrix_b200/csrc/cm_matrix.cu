@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -265,56 +266,8 @@ struct cm_matrix {
   std::vector<bool> peer_ipc_open;
   // receive arenas of every rank (mine included), see ensure_recv_arenas()
   bool p2p_possible = false;
-  bool p2p = false;         // every rank maps every rank's receive arenas (modes 2 and 3)
-  bool dma = false;         // mode 3: messages are packed locally and moved by the copy engines
-  int exchange_mode = 0;    // 0 auto, 1 transport all-to-all-v, 2 peer-to-peer stores, 3 copy-engine pushes
-  // mode 3 signalling: flags[src] on every rank, written by the source after its copies (a 4-byte
-  // copy ordered behind them on the same stream), awaited with cuStreamWaitValue32 by the owner
-  DevBuf d_flags;
-  std::vector<void *> peer_flags;
-  std::vector<bool> peer_flags_open;
-  uint32_t xfer_seq = 0;
-  PinBuf h_seq;
-  // Barrier over the same mapping (second row of d_flags): a one-block kernel stores this rank's
-  // barrier sequence number into every peer's row, then the stream waits (cuStreamWaitValue32) until
-  // every peer's number has arrived in its own row. Replaces the 1-element ncclAllReduce of a commit's
-  // barriers; opt-in (CM_B200_FLAG_BARRIER=1) until measured. =2 also allows it between rank threads
-  // of one process (kernel-logic tests only).
-  // Device-side layout (opt-in, CM_B200_DEVICE_LAYOUT=1; peer-to-peer stores, one-panel commits): a
-  // small kernel computes where this rank's messages go from the all-gathered counts and the pack
-  // kernel is launched right behind it, BEFORE the host has read the counts; the host's read-back of
-  // the counts (still needed for the owner side and for growth) overlaps the pack. If an arena turns
-  // out too small the speculative pack does nothing (same verdict on every rank) and the host path runs.
-  int device_layout = 0;
-  bool arena_tab_dirty = true;
-  DevBuf d_arena_tab;  // [6][P]: vals base, meta base, cap_vals, cap_meta, base_v, base_m
-  DevBuf d_overflow;
-  PinBuf h_overflow;
-  // CM_B200_PINNED_DESCS=1: the descriptor table and the item offsets of a flush travel from two pinned
-  // staging slots used alternately (a truly asynchronous DMA) instead of straight from pageable vectors
-  // (which the driver may stage synchronously, behind whatever the stream still has to do)
-  int pinned_descs = 0;
-  PinBuf h_stage[2];
-  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
-  bool stage_used[2] = {false, false};
-  int stage_slot = 0;
-  PackConfig pack_cfg;  // CM_B200_PACK_THREADS / CM_B200_PACK_COLS
-  int seg_apply = 0;  // CM_B200_SEG_APPLY=1: flushes of small segments are scatter-added segment-wise (k_apply_seg)
-  int flag_barrier = 0;
-  uint32_t bar_seq = 0;
-  DevBuf d_peer_rows;  // [P] device pointers: peer r's barrier row
-  // The peer-mapped block behind d_flags holds, per rank: row 0 arrival flags of mode 3, row 1 barrier
-  // numbers, row 2 "counts have arrived" numbers (4*P bytes each), then — 256-byte aligned — the table
-  // of all-gathered counts [src][panel][owner]. With the flag barrier on, the counts all-gather is peer
-  // stores too (k_publish_counts) instead of an ncclAllGather.
-  size_t counts_off = 0;       // byte offset of the counts table in the block
-  uint32_t counts_seq = 0;
-  DevBuf d_peer_bases;         // [P] device pointers: base of peer r's block
-  unsigned seq_slot = 0;
-  static constexpr int kXferStreams = 4;  // peers are spread over several streams = several copy engines
-  cudaStream_t xfer_stream[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_packed[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_xfer[kXferStreams] = {nullptr, nullptr, nullptr, nullptr};
+  bool p2p = false;       // every rank maps every rank's receive arenas: the pack kernel stores into them (mode 2)
+  int exchange_mode = 0;  // 0 auto, 1 transport all-to-all-v (grouped ncclSend/ncclRecv), 2 peer-to-peer stores
   std::vector<void *> peer_vals, peer_meta;
   std::vector<size_t> cap_vals, cap_meta;
   std::vector<bool> peer_arena_open;
@@ -359,6 +312,7 @@ struct cm_matrix {
   std::vector<long> item_base;  // single-rank path: first item of each update
   long staged_elems = 0, staged_rows = 0, staged_cols = 0, staged_items = 0;
   bool borrowed_pending = false;  // device-API payloads staged since the last flush
+  bool reads_local_block = false;  // a staged payload is the local block itself (fill_lower)
   DevArena payload_arena{64ull << 20};
   MirrorArena index_arena{4ull << 20};
   std::vector<CooBin> coo;  // [owner]
@@ -377,8 +331,9 @@ struct cm_matrix {
   cudaEvent_t ev_panel[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_applied = nullptr;
   cudaEvent_t ev_bg = nullptr;  // main stream -> apply stream dependency of a background scatter-add
-  int pipeline = -1;                    // panel-pipelined commits. -1 (default): in mode 3 only; CM_B200_PIPELINE=1
-                                        // enables them in mode 2 too, =0 disables them everywhere
+  // Panel-pipelined commits (peer-to-peer stores): on by default, CM_B200_PIPELINE=0 disables them.
+  // B200, 8 GPUs: K1-weak 10.78 -> 9.39 ms per step, K3 23.4 -> 14.1 ms.
+  int pipeline = 1;
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
   int npanel_cfg = kMaxChunks;          // column panels of a pipelined commit (CM_B200_PANELS)
   int pipeline_apply_blocks = 2;        // resident scatter-add blocks per SM while the next panel is being packed
@@ -388,6 +343,15 @@ struct cm_matrix {
   cm_stats stats{};
   std::vector<PendingTimer> timers;
   std::vector<cudaEvent_t> event_pool;
+
+  // CM_B200_TRACE=n: per-phase timeline (CUDA events + host clock) of the first n commits of rank 0, on stderr
+  struct TraceMark {
+    const char *name;
+    cudaEvent_t ev;
+    double host_us;
+  };
+  int trace_left = 0;
+  std::vector<TraceMark> marks;
 
   // wire capture (parity tests)
   struct DbgMsg {
@@ -414,6 +378,39 @@ cudaEvent_t get_event(cm_matrix *M) {
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
   return e;
+}
+
+double host_now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+// timeline mark: an event on `st` now, plus the host clock
+void trace_mark(cm_matrix *M, const char *name, cudaStream_t st = nullptr) {
+  if (M->trace_left <= 0) return;
+  cudaEvent_t e = get_event(M);
+  cudaEventRecord(e, st ? st : M->stream);
+  M->marks.push_back(cm_matrix::TraceMark{name, e, host_now_us()});
+}
+
+// print and drop the marks whose events have completed (call with the main stream synchronised)
+void trace_dump(cm_matrix *M, bool end_of_commit) {
+  if (M->marks.empty()) return;
+  cudaEventSynchronize(M->marks.back().ev);
+  const cm_matrix::TraceMark &base = M->marks.front();
+  for (const auto &mk : M->marks) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, base.ev, mk.ev) != cudaSuccess) {
+      cudaGetLastError();
+      ms = -1;
+    }
+    fprintf(stderr, "[cm trace r%d c%ld] %-28s gpu %9.3f us   host %9.3f us\n", M->me, M->stats.commits, mk.name, ms * 1e3,
+            mk.host_us - base.host_us);
+    M->event_pool.push_back(mk.ev);
+  }
+  M->marks.clear();
+  if (end_of_commit) M->trace_left -= 1;
 }
 
 struct ScopedTimer {
@@ -478,6 +475,7 @@ void clear_staged(cm_matrix *M) {
   M->item_base.clear();
   M->staged_elems = M->staged_rows = M->staged_cols = M->staged_items = 0;
   M->borrowed_pending = false;
+  M->reads_local_block = false;
   M->payload_arena.reset();
   M->index_arena.reset();
   for (auto &b : M->coo) {
@@ -489,37 +487,7 @@ void clear_staged(cm_matrix *M) {
 
 int issue_merged_copy(cm_matrix *M);
 
-// host vector -> device buffer on the main stream, optionally through a pinned staging slot
-int upload_table(cm_matrix *M, void *d_dst, const void *h_src, size_t bytes, size_t slot_off) {
-  if (!bytes) return CM_OK;
-  if (!M->pinned_descs) {
-    CM_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, M->stream));
-    return CM_OK;
-  }
-  PinBuf &pb = M->h_stage[M->stage_slot];
-  char *h = static_cast<char *>(pb.p) + slot_off;
-  memcpy(h, h_src, bytes);
-  CM_CUDA_TRY(cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, M->stream));
-  return CM_OK;
-}
-
-// take the next staging slot for a flush holding `bytes` of tables: its previous DMA (two flushes ago) must be done
-int begin_stage(cm_matrix *M, size_t bytes) {
-  if (!M->pinned_descs) return CM_OK;
-  M->stage_slot ^= 1;
-  const int sl = M->stage_slot;
-  if (M->stage_used[sl]) CM_CUDA_TRY(cudaEventSynchronize(M->ev_stage[sl]));
-  if (!M->ev_stage[sl]) CM_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_stage[sl], cudaEventDisableTiming));
-  CM_TRY(M->h_stage[sl].ensure(bytes));
-  return CM_OK;
-}
-int end_stage(cm_matrix *M) {
-  if (!M->pinned_descs) return CM_OK;
-  CM_CUDA_TRY(cudaEventRecord(M->ev_stage[M->stage_slot], M->stream));
-  M->stage_used[M->stage_slot] = true;
-  return CM_OK;
-}
-
+// staged descriptors, raw index sets and the mapped-index arenas of a flush, on the device
 int upload_staged(cm_matrix *M, int npanel = 1) {
   const int nupd = (int)M->descs.size();
   CM_TRY(issue_merged_copy(M));
@@ -530,9 +498,7 @@ int upload_staged(cm_matrix *M, int npanel = 1) {
   }
   CM_TRY(M->index_arena.upload(M->stream, &M->stats.h2d_bytes));
   CM_TRY(M->d_descs.ensure(sizeof(UpdDesc) * (size_t)std::max(nupd, 1)));
-  // staging slot layout: [descriptors][item offsets (single-rank flush only)]
-  CM_TRY(begin_stage(M, (sizeof(UpdDesc) + 8) * (size_t)std::max(nupd, 1)));
-  CM_TRY(upload_table(M, M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, 0));
+  if (nupd) CM_CUDA_TRY(cudaMemcpyAsync(M->d_descs.p, M->descs.data(), sizeof(UpdDesc) * (size_t)nupd, cudaMemcpyHostToDevice, M->stream));
   const int npr = (int)M->g.nprow + 1, npc = (int)M->g.npcol * npanel + 1;
   CM_TRY(M->d_rl.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
   CM_TRY(M->d_rpos.ensure(4 * (size_t)std::max(M->staged_rows, 1L)));
@@ -557,31 +523,13 @@ MapArenas map_arenas(cm_matrix *M) {
   return ma;
 }
 
-// Segment-wise scatter-add (opt-in) instead of per-column items: for the flushes that would take the
-// unsorted RED path anyway (sparse and small) and whose segments are small on average.
-bool use_seg_apply(const cm_matrix *M, long elements, long nsegs) {
-  if (!M->seg_apply || M->deterministic || M->apply_kernel == 2 || nsegs <= 0) return false;
-  const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
-  if (M->apply_kernel == 0 && density >= M->tile_density) return false;  // tile kernel
-  if (M->sorted_sweep && elements >= (4L << 20)) return false;           // sorted RED sweep
-  return elements <= nsegs * 4096;
-}
-
-int seg_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nsegs, long elements) {
-  ScopedTimer t(M, 0, elements, st);
-  launch_apply_seg(M->dtype, w.segs.as<Seg>(), nsegs, M->d_local, M->g, st);
-  M->stats.kernel_launches += 1;
-  CM_CUDA_TRY(cudaGetLastError());
-  return CM_OK;
-}
-
 // sort (optional) + scatter-add over nitems (key,item) pairs sitting in w.keys0 / w.items0
 int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0) {
   if (nitems <= 0) return CM_OK;
   const uint64_t *items = w.items0.as<uint64_t>();
   const uint32_t *keys = w.keys0.as<uint32_t>();
-  // which scatter-add: the column-tile kernel pays 2*s bytes per touched sector of a touched
-  // column and no atomics; RED pays one sector round trip per element. Dense flushes -> tile.
+  // which scatter-add: the column-tile kernel pays 2*s bytes per row of a touched column and no
+  // atomics; RED pays one sector round trip per element. Dense flushes -> tile.
   const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
   bool tile = M->apply_kernel == 2 || (M->apply_kernel == 0 && density >= M->tile_density);
   if (M->deterministic) tile = true;
@@ -633,6 +581,7 @@ int apply_coo_blob(cm_matrix *M, const char *blob, long n) {
     M->stats.kernel_launches += 1;
   }
   M->stats.elements_applied += n;
+  M->mirror_valid = false;  // the block changed, whatever the apply policy
   return CM_OK;
 }
 
@@ -661,29 +610,26 @@ int flush_direct(cm_matrix *M, bool sync = true) {
   }
   if (M->payload_arena.used() || M->index_arena.used() || M->coo_total) sync = true;
   if (nupd) {
+    trace_mark(M, "flush: begin");
     CM_TRY(upload_staged(M));
     const long nitems = M->staged_items;
     CM_TRY(M->d_item_base.ensure(8 * (size_t)nupd));
-    CM_TRY(upload_table(M, M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, sizeof(UpdDesc) * (size_t)nupd));
-    CM_TRY(end_stage(M));
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_item_base.p, M->item_base.data(), 8 * (size_t)nupd, cudaMemcpyHostToDevice, M->stream));
     ApplyWork &w = M->work[0];
     CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)nupd));
     CM_TRY(w.keys0.ensure(4 * (size_t)std::max(nitems, 1L)));
     CM_TRY(w.items0.ensure(8 * (size_t)std::max(nitems, 1L)));
     const MapArenas ma = map_arenas(M);
-    const bool by_seg = use_seg_apply(M, M->staged_elems, nupd);
     {
       ScopedTimer t(M, 1, 0);
       launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, PanelPlan{1, 1}, ma, M->stream);
       launch_build_direct(M->dtype, M->d_descs.as<UpdDesc>(), M->d_item_base.as<long>(), nupd, M->g, ma,
-                          w.segs.as<Seg>(), by_seg ? nullptr : w.keys0.as<uint32_t>(),
-                          by_seg ? nullptr : w.items0.as<uint64_t>(), M->stream);
+                          w.segs.as<Seg>(), w.keys0.as<uint32_t>(), w.items0.as<uint64_t>(), M->stream);
       M->stats.kernel_launches += 2;
     }
-    if (by_seg)
-      CM_TRY(seg_apply(M, w, M->stream, nupd, M->staged_elems));
-    else
-      CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0));
+    trace_mark(M, "flush: mapped, items built");
+    CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0));
+    trace_mark(M, "flush: scatter-add done");
     M->stats.elements_applied += M->staged_elems;
   }
   if (M->coo_total) CM_TRY(apply_coo_local(M, M->coo[0]));
@@ -691,6 +637,7 @@ int flush_direct(cm_matrix *M, bool sync = true) {
     CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
     CM_CUDA_TRY(cudaGetLastError());
     resolve_timers(M);
+    trace_dump(M, true);
   }
   M->stats.flushes += 1;
   M->mirror_valid = false;
@@ -698,75 +645,10 @@ int flush_direct(cm_matrix *M, bool sync = true) {
   return CM_OK;
 }
 
-// cuStreamWaitValue32 through the runtime's driver entry point lookup (no libcuda link dependency)
-typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
-StreamWaitValue32Fn stream_wait_value32() {
-  // looked up once; thread-safe (rank threads of the loopback transport may race here)
-  static const StreamWaitValue32Fn fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      return reinterpret_cast<StreamWaitValue32Fn>(p);
-    cudaGetLastError();
-    return static_cast<StreamWaitValue32Fn>(nullptr);
-  }();
-  return fn;
-}
-
-// flags of a flag wait: "greater or equal", plus — where the device supports it — a flush of outstanding
-// remote writes, so that data a peer stored BEFORE the flag is visible to the work behind the wait
-unsigned wait_value_flags() {
-  static const unsigned flags = [] {
-    int dev = 0, can = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&can, cudaDevAttrCanFlushRemoteWrites, dev) != cudaSuccess) {
-      cudaGetLastError();
-      can = 0;
-    }
-    return /*CU_STREAM_WAIT_VALUE_GEQ*/ 0x0u | (can == 1 ? /*CU_STREAM_WAIT_VALUE_FLUSH*/ (1u << 30) : 0u);
-  }();
-  return flags;
-}
-
-// stream-ordered wait until *(uint32_t *)addr >= value; 0 on success
-int wait_value_geq(cudaStream_t st, const void *addr, uint32_t value) {
-  StreamWaitValue32Fn wait32 = stream_wait_value32();
-  if (!wait32) return -1;
-  static bool flush_ok = true;  // a refused FLUSH flag is dropped for good (benign race: same value)
-  const unsigned flags = flush_ok ? wait_value_flags() : 0x0u;
-  int rc = wait32(st, (unsigned long long)(uintptr_t)addr, value, flags);
-  if (rc != 0 && flags != 0x0u) {
-    cudaGetLastError();
-    flush_ok = false;
-    rc = wait32(st, (unsigned long long)(uintptr_t)addr, value, 0x0u);
-  }
-  return rc;
-}
-
 // ---- barriers of a commit ------------------------------------------------------------------
 // stream-ordered: work enqueued on `st` afterwards starts only when every rank's stream has reached
-// its own call. Default: the transport's (a 1-element ncclAllReduce); opt-in: flags over peer memory.
-// flags in peer-mapped memory instead of NCCL for a commit's synchronisation (opt-in)
-bool flag_sync_enabled(cm_matrix *M) {
-  return M->P > 1 && M->p2p && M->flag_barrier > 0 && (M->flag_barrier > 1 || !M->ctx->tp->same_process()) &&
-         stream_wait_value32() != nullptr;
-}
-
-int commit_stream_barrier(cm_matrix *M, cudaStream_t st) {
-  Transport *tp = M->ctx->tp;
-  if (!flag_sync_enabled(M)) return tp->stream_barrier(st);
-  const uint32_t seq = ++M->bar_seq;
-  launch_signal_peers(M->d_peer_rows.as<uint32_t *>(), M->me, M->P, seq, st);
-  M->stats.kernel_launches += 1;
-  const char *row = M->d_flags.as<char>() + 4 * (size_t)M->P;
-  for (int r = 0; r < M->P; ++r) {
-    if (r == M->me) continue;
-    const int rc = wait_value_geq(st, row + 4 * (size_t)r, seq);
-    if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
-  }
-  return CM_OK;
-}
+// its own call (a 1-element ncclAllReduce; flags over peer memory were measured no faster at 2 and 8 GPUs)
+int commit_stream_barrier(cm_matrix *M, cudaStream_t st) { return M->ctx->tp->stream_barrier(st); }
 // returns when every rank's stream work up to its own call is complete
 int commit_barrier(cm_matrix *M, cudaStream_t st) {
   CM_TRY(commit_stream_barrier(M, st));
@@ -842,7 +724,6 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
     M->cap_vals[d] = grown(need_vals[d]);
     M->cap_meta[d] = grown(need_meta[d]);
   }
-  M->arena_tab_dirty = true;
   return CM_OK;
 }
 
@@ -857,20 +738,14 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
   CM_TRY(w.segs.ensure(sizeof(Seg) * (size_t)seg_total));
   CM_TRY(w.keys0.ensure(4 * (size_t)std::max(item_total, 1L)));
   CM_TRY(w.items0.ensure(8 * (size_t)std::max(item_total, 1L)));
-  const bool by_seg = use_seg_apply(M, elem_total, seg_total);
-  launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(),
-                    by_seg ? nullptr : w.keys0.as<uint32_t>(), by_seg ? nullptr : w.items0.as<uint64_t>(), st);
+  launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
+                    w.items0.as<uint64_t>(), st);
   M->stats.kernel_launches += 1;
-  if (by_seg)
-    CM_TRY(seg_apply(M, w, st, seg_total, elem_total));
-  else
-    CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
+  CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
   M->stats.elements_applied += elem_total;
   return CM_OK;
 }
 
-// deferred policy: apply what has been logged in my arenas and not applied yet (local, not collective;
-// the log itself is only truncated by materialize_all, because every rank tracks its length)
 // a background scatter-add (apply stream) must have finished before anything else touches the local
 // block or the work buffers it uses
 int wait_background(cm_matrix *M) {
@@ -903,6 +778,8 @@ int apply_log(cm_matrix *M, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm
   return CM_OK;
 }
 
+// deferred policy: apply what has been logged in my arenas and not applied yet (local, not collective;
+// the log itself is only truncated by materialize_all, because every rank tracks its length)
 int materialize_local(cm_matrix *M) {
   if (M->pend_applied >= M->pend.size() && !M->bg_running) return CM_OK;
   CM_TRY(wait_background(M));
@@ -922,13 +799,13 @@ int start_background_apply(cm_matrix *M) {
   // earlier background scatter-add precedes it in apply-stream order
   CM_CUDA_TRY(cudaEventRecord(M->ev_bg, M->stream));
   CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_bg, 0));
+  trace_mark(M, "background apply: start", M->apply_stream);
   CM_TRY(apply_log(M, M->work[1], M->apply_stream, M->pipeline_apply_blocks));
+  trace_mark(M, "background apply: end", M->apply_stream);
   CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
   M->bg_running = true;
   return CM_OK;
 }
-
-int commit_barrier(cm_matrix *M, cudaStream_t st);
 
 // COLLECTIVE: everybody applies its log, then the logs are truncated everywhere
 int materialize_all(cm_matrix *M) {
@@ -942,7 +819,6 @@ int materialize_all(cm_matrix *M) {
   M->pend_applied = 0;
   std::fill(M->pend_v.begin(), M->pend_v.end(), 0L);
   std::fill(M->pend_m.begin(), M->pend_m.end(), 0L);
-  M->arena_tab_dirty = true;  // the device-side copy of the log offsets is stale now
   return CM_OK;
 }
 
@@ -950,8 +826,10 @@ int materialize_all(cm_matrix *M) {
 // it has staged; the wire format carries whatever it decides.
 PanelPlan plan_panels(cm_matrix *M) {
   PanelPlan pp{1, 1};
-  const bool wanted = M->P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1);
-  if (!wanted || M->apply_policy != 0 || M->staged_elems < M->pipeline_min_elems) return pp;
+  const bool wanted = M->P > 1 && M->p2p && M->pipeline == 1;
+  // a staged payload that IS the local block (fill_lower) must be packed before any scatter-add of this
+  // commit writes the block: one panel, one batch
+  if (!wanted || M->apply_policy != 0 || M->reads_local_block || M->staged_elems < M->pipeline_min_elems) return pp;
   long k = std::min<long>(M->npanel_cfg, kMaxChunks);
   k = std::min<long>(k, kMaxGridDim / M->g.npcol);
   k = std::min<long>(k, 1024 / M->P);
@@ -968,197 +846,142 @@ PanelPlan plan_panels(cm_matrix *M) {
 }
 
 // ---- general commit path (also used for P == 1 when the wire is being captured, so the pack
-// kernels are testable on one rank):
-//   map -> scan -> counts all-gather (the one host sync) -> pack -> [all-to-all-v] -> barrier ->
-//   build -> sort -> scatter-add -> barrier
+// kernels are testable on one rank), in four stages:
+//   commit_counts   map -> scan -> counts all-gather -> read-back (the one host sync)
+//   commit_layout   where every message of every rank goes; arenas grown; elemental updates staged
+//   commit_deliver  pack (+ all-to-all-v) and, panel by panel, the owners' scatter-adds
+//   commit_finish   wire capture, log or scatter-add, elemental updates, quiescence barrier
 // The pack kernel writes every message where the owner will read it: with peer-to-peer exchange
 // that is the owner's receive arena itself (pack and exchange are ONE kernel whose stores cross
 // NVLink); otherwise a local send arena that a grouped ncclSend/ncclRecv all-to-all-v moves.
-int commit_exchange(cm_matrix *M) {
-  const int P = M->P, me = M->me, K = kMaxChunks;
-  const int nupd = (int)M->descs.size();
-  Transport *tp = M->ctx->tp;
-  const size_t esz = M->esz;
-  auto cidx = [P, K](int src, int k, int dst) { return ((size_t)src * K + k) * P + dst; };  // counts index
-
-  // -- panel plan (a LOCAL decision of this source; owners cope with any mix): a source that stages
-  // a large commit cuts its updates' columns into panels so that the owners can pipeline it
-  const PanelPlan pp = plan_panels(M);
+struct CommitPlan {
+  int P = 1, me = 0, K = kMaxChunks, nupd = 0;
+  PanelPlan pp{1, 1};
   long max_rows = 0;
-  for (const UpdDesc &d : M->descs) max_rows = std::max<long>(max_rows, d.m);
+  MapArenas ma{};
+  ScanArenas sa{};
+  MsgCounts *counts = nullptr;  // host copy of the all-gathered counts [src][panel][dst]
+  long *coo_counts = nullptr;   // [src][dst]
+  bool empty = false;           // nothing staged on any rank
+  bool deferred = false, pipelined = false;
+  int Kp = 0;                   // panel slots that hold data on any rank (same value everywhere)
+  std::vector<long> rbase_v, rbase_m;  // [owner][panel * P + src]: where each message starts (elements / bytes)
+  std::vector<void *> dst_ptrs;        // host copy of sa.dst_vals / sa.dst_meta
+  std::vector<long> r_coo_base, s_coo_base;
+  cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
 
-  // -- source side: owner map + per-(panel, owner) sizes ---------------------------------------
-  CM_TRY(upload_staged(M, pp.npanel));
-  CM_TRY(end_stage(M));
-  const size_t pu = (size_t)pp.npanel * P * std::max(nupd, 1);
+  size_t cidx(int src, int k, int dst) const { return ((size_t)src * K + k) * P + dst; }
+  size_t ridx(int d, int k, int src) const { return (size_t)d * (K * P + 1) + (size_t)k * P + src; }
+  long coo_blob(size_t esz, long n) const { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); }
+  bool panel_has_data(int k) const {  // does this rank send anything in panel k?
+    if (k >= pp.npanel || nupd == 0) return false;
+    for (int d = 0; d < P; ++d)
+      if (counts[cidx(me, k, d)].nvals) return true;
+    return false;
+  }
+};
+
+// -- source side: owner map + per-(panel, owner) sizes; counts all-gathered and read back ----------
+int commit_counts(cm_matrix *M, CommitPlan &cp) {
+  const int P = cp.P, K = cp.K, nupd = cp.nupd;
+  Transport *tp = M->ctx->tp;
+  // panel plan (a LOCAL decision of this source; owners cope with any mix): a source that stages
+  // a large commit cuts its updates' columns into panels so that the owners can pipeline it
+  cp.pp = plan_panels(M);
+  for (const UpdDesc &d : M->descs) cp.max_rows = std::max<long>(cp.max_rows, d.m);
+  CM_TRY(upload_staged(M, cp.pp.npanel));
+  const size_t pu = (size_t)cp.pp.npanel * P * std::max(nupd, 1);
   CM_TRY(M->d_valoff.ensure(8 * pu));
   CM_TRY(M->d_idxoff.ensure(8 * pu));
   CM_TRY(M->d_itemoff.ensure(8 * pu));
   CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P * K));
   CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P * K));
-  const MapArenas ma = map_arenas(M);
-  ScanArenas sa;
-  sa.valoff = M->d_valoff.as<long>();
-  sa.idxoff = M->d_idxoff.as<long>();
-  sa.itemoff = M->d_itemoff.as<long>();
-  sa.totals = M->d_totals.as<MsgCounts>();
-  sa.dst_vals = M->d_dst_ptrs.as<void *>();
-  sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
-  sa.overflow = nullptr;
-  cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
+  cp.ma = map_arenas(M);
+  cp.sa.valoff = M->d_valoff.as<long>();
+  cp.sa.idxoff = M->d_idxoff.as<long>();
+  cp.sa.itemoff = M->d_itemoff.as<long>();
+  cp.sa.totals = M->d_totals.as<MsgCounts>();
+  cp.sa.dst_vals = M->d_dst_ptrs.as<void *>();
+  cp.sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
   if (M->profiling) {
-    ev_pack0 = get_event(M);
-    ev_pack1 = get_event(M);
-    cudaEventRecord(ev_pack0, M->stream);
+    cp.ev_pack0 = get_event(M);
+    cp.ev_pack1 = get_event(M);
+    cudaEventRecord(cp.ev_pack0, M->stream);
   }
   // elemental-update counts ride in the same totals (host-known; one tiny H2D)
   std::vector<long> my_coo(P);
   for (int d = 0; d < P; ++d) my_coo[d] = (long)M->coo[d].inds.size();
   CM_TRY(M->d_coo_counts.ensure(8 * (size_t)P));
   CM_CUDA_TRY(cudaMemcpyAsync(M->d_coo_counts.p, my_coo.data(), 8 * (size_t)P, cudaMemcpyHostToDevice, M->stream));
-  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, pp, ma, M->stream);
-  launch_scan(nupd, pp, M->g, ma, sa, M->d_coo_counts.as<long>(), M->stream);
+  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, cp.pp, cp.ma, M->stream);
+  launch_scan(nupd, cp.pp, M->g, cp.ma, cp.sa, M->d_coo_counts.as<long>(), M->stream);
   M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
   CM_CUDA_TRY(cudaGetLastError());
+  trace_mark(M, "counts: mapped + scanned");
 
-  // -- counts: all-gather the totals, read them back (the one host sync of a commit) -----------
   const size_t per_rank = sizeof(MsgCounts) * (size_t)P * K;
-  void *counts_all = nullptr;  // device table [src][panel][owner]
-  const size_t table_off = M->counts_off + ((M->counts_seq + 1) & 1u) * per_rank * P;  // table of this commit
-  if (P > 1) {
-    counts_all = M->d_flags.as<char>() + table_off;
-  } else {
-    CM_TRY(M->d_counts_all.ensure(per_rank * P));
-    counts_all = M->d_counts_all.p;
-  }
-  if (flag_sync_enabled(M)) {
-    // every rank stores its row into every rank's table over NVLink and says so; the stream waits
-    // until every row of its own table has arrived (no NCCL call)
-    const uint32_t seq = ++M->counts_seq;
-    launch_publish_counts(M->d_peer_bases.as<char *>(), me, P, M->d_totals.as<MsgCounts>(), (long)table_off,
-                          2 * 4 * (long)P, seq, M->stream);
-    M->stats.kernel_launches += 1;
-    const char *row2 = M->d_flags.as<char>() + 2 * 4 * (size_t)P;
-    for (int r = 0; r < P; ++r) {
-      if (r == me) continue;
-      const int rc = wait_value_geq(M->stream, row2 + 4 * (size_t)r, seq);
-      if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
-    }
-  } else {
-    ++M->counts_seq;
-    CM_TRY(tp->allgather(M->d_totals.p, counts_all, per_rank, M->stream));
-  }
+  CM_TRY(M->d_counts_all.ensure(per_rank * P));
+  CM_TRY(tp->allgather(M->d_totals.p, M->d_counts_all.p, per_rank, M->stream));
   CM_TRY(M->h_counts.ensure(per_rank * P + 8 * (size_t)P * P));
-  MsgCounts *counts = static_cast<MsgCounts *>(M->h_counts.p);  // [src][panel][dst]
-  // -- device-side layout + speculative pack (opt-in): nothing below this point needs the host to know
-  // the counts before the pack kernel may run; the read-back overlaps it
-  const bool spec_pack = M->device_layout && P > 1 && M->p2p && !M->dma && pp.npanel == 1 && nupd > 0 &&
-                         !(M->dma ? M->pipeline != 0 : M->pipeline == 1);
-  if (spec_pack) {
-    const bool log_pending = M->apply_policy != 0;
-    CM_TRY(M->d_arena_tab.ensure(6 * 8 * (size_t)P));
-    CM_TRY(M->d_overflow.ensure(256));
-    CM_TRY(M->h_overflow.ensure(256));
-    if (M->arena_tab_dirty || log_pending) {
-      std::vector<long> tab(6 * (size_t)P);
-      for (int d = 0; d < P; ++d) {
-        tab[0 * P + d] = (long)(uintptr_t)M->peer_vals[d];
-        tab[1 * P + d] = (long)(uintptr_t)M->peer_meta[d];
-        tab[2 * P + d] = (long)M->cap_vals[d];
-        tab[3 * P + d] = (long)M->cap_meta[d];
-        tab[4 * P + d] = log_pending ? M->pend_v[d] : 0;
-        tab[5 * P + d] = log_pending ? M->pend_m[d] : 0;
-      }
-      CM_CUDA_TRY(cudaMemcpyAsync(M->d_arena_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, M->stream));
-      M->arena_tab_dirty = false;
-    }
-    const long *tab = M->d_arena_tab.as<long>();
-    ArenaTable at;
-    at.vals = reinterpret_cast<char *const *>(tab);
-    at.meta = reinterpret_cast<char *const *>(tab + P);
-    at.cap_vals = tab + 2 * P;
-    at.cap_meta = tab + 3 * P;
-    at.base_v = tab + 4 * P;
-    at.base_m = tab + 5 * P;
-    CM_CUDA_TRY(cudaMemsetAsync(M->d_overflow.p, 0, 4, M->stream));
-    launch_layout(static_cast<const MsgCounts *>(counts_all), P, me, (int)esz, at, sa.dst_vals, sa.dst_meta, M->d_overflow.as<int>(),
-                  M->stream);
-    sa.overflow = M->d_overflow.as<int>();
-    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
-    M->stats.kernel_launches += 2;
-    if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
-  }
-  CM_CUDA_TRY(cudaMemcpyAsync(counts, counts_all, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
-  if (spec_pack) CM_CUDA_TRY(cudaMemcpyAsync(M->h_overflow.p, M->d_overflow.p, 4, cudaMemcpyDeviceToHost, M->stream));
+  cp.counts = static_cast<MsgCounts *>(M->h_counts.p);
+  CM_CUDA_TRY(cudaMemcpyAsync(cp.counts, M->d_counts_all.p, per_rank * P, cudaMemcpyDeviceToHost, M->stream));
   M->stats.d2h_bytes += (long)(per_rank * P);
+  trace_mark(M, "counts: all-gathered");
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-  // the speculative pack ran to completion unless the layout kernel found an arena too small
-  const bool packed = spec_pack && *static_cast<const int *>(M->h_overflow.p) == 0;
-  sa.overflow = nullptr;
-  long *coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + per_rank * P);  // [src][dst]
+  cp.coo_counts = reinterpret_cast<long *>(static_cast<char *>(M->h_counts.p) + per_rank * P);
   for (int src = 0; src < P; ++src)
-    for (int d = 0; d < P; ++d) coo_counts[(size_t)src * P + d] = counts[cidx(src, 0, d)].ncoo;
+    for (int d = 0; d < P; ++d) cp.coo_counts[(size_t)src * P + d] = cp.counts[cp.cidx(src, 0, d)].ncoo;
+  bool any = false;
+  for (size_t i = 0; i < (size_t)P * K * P && !any; ++i) any = cp.counts[i].nvals != 0 || cp.counts[i].ncoo != 0;
+  cp.empty = !any;
+  return CM_OK;
+}
 
-  // -- nothing staged on any rank: the counts all-gather already was the rendezvous of this commit
-  // (nobody leaves it before everybody has entered it); there is nothing to exchange, to apply or
-  // to wait for, so the two barriers below are skipped (empty-commit latency)
-  {
-    bool any = false;
-    for (size_t i = 0; i < (size_t)P * K * P && !any; ++i) any = counts[i].nvals != 0 || counts[i].ncoo != 0;
-    if (!any) {
-      if (M->profiling) {
-        M->event_pool.push_back(ev_pack0);
-        M->event_pool.push_back(ev_pack1);
-      }
-      if (M->keep_wire) {
-        M->dbg_msgs.clear();
-        M->dbg_coo = M->coo;
-        M->dbg_valid = true;
-      }
-      resolve_timers(M);
-      clear_staged(M);
-      return CM_OK;
-    }
-  }
-
-  // -- pipeline or not: same decision on every rank, taken from the global counts. Pipelining pays
+// -- where everything goes (identical computation on every rank) ------------------------------------
+int commit_layout(cm_matrix *M, CommitPlan &cp) {
+  const int P = cp.P, me = cp.me, K = cp.K;
+  const size_t esz = M->esz;
+  const MsgCounts *counts = cp.counts;
+  // pipeline or not: same decision on every rank, taken from the global counts. Pipelining pays
   // when the commit is large and most of it arrived cut into panels (panel k > 0 non-empty);
   // everything else goes as one batch.
-  const bool deferred = M->apply_policy != 0 && P > 1 && M->p2p;
-  bool pipelined = false;
-  if (!deferred && P > 1 && M->p2p && (M->dma ? M->pipeline != 0 : M->pipeline == 1)) {
+  cp.deferred = M->apply_policy != 0 && P > 1 && M->p2p;
+  if (!cp.deferred && P > 1 && M->p2p && M->pipeline == 1) {
     long total = 0, later = 0;
     for (int src = 0; src < P; ++src)
       for (int k = 0; k < K; ++k)
         for (int d = 0; d < P; ++d) {
-          total += counts[cidx(src, k, d)].nelems;
-          if (k > 0) later += counts[cidx(src, k, d)].nelems;
+          total += counts[cp.cidx(src, k, d)].nelems;
+          if (k > 0) later += counts[cp.cidx(src, k, d)].nelems;
         }
-    pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total;
+    cp.pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total;
   }
+  for (int src = 0; src < P; ++src)
+    for (int k = 0; k < K; ++k)
+      for (int d = 0; d < P; ++d)
+        if (counts[cp.cidx(src, k, d)].nvals) cp.Kp = std::max(cp.Kp, k + 1);
 
-  // -- layout of every rank's receive arenas (identical computation on every rank):
-  // owner d holds, panel after panel, the messages of every source
-  std::vector<long> rbase_v((size_t)P * (K * P + 1), 0), rbase_m((size_t)P * (K * P + 1), 0);
-  auto ridx = [P, K](int d, int k, int src) { return (size_t)d * (K * P + 1) + (size_t)k * P + src; };
+  // layout of every rank's receive arenas: owner d holds, panel after panel, the messages of every source
+  cp.rbase_v.assign((size_t)P * (K * P + 1), 0);
+  cp.rbase_m.assign((size_t)P * (K * P + 1), 0);
   std::vector<size_t> need_vals(P), need_meta(P);
   auto lay_out = [&]() {  // eager: from the start of the arenas; deferred: behind what is logged there
     for (int d = 0; d < P; ++d) {
-      rbase_v[ridx(d, 0, 0)] = deferred ? M->pend_v[d] : 0;
-      rbase_m[ridx(d, 0, 0)] = deferred ? M->pend_m[d] : 0;
+      cp.rbase_v[cp.ridx(d, 0, 0)] = cp.deferred ? M->pend_v[d] : 0;
+      cp.rbase_m[cp.ridx(d, 0, 0)] = cp.deferred ? M->pend_m[d] : 0;
       for (int k = 0; k < K; ++k)
         for (int src = 0; src < P; ++src) {
-          const MsgCounts &c = counts[cidx(src, k, d)];
-          const size_t i = ridx(d, k, src);
-          rbase_v[i + 1] = rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
-          rbase_m[i + 1] = rbase_m[i] + meta_bytes(c.nseg, c.nidx);
+          const MsgCounts &c = counts[cp.cidx(src, k, d)];
+          const size_t i = cp.ridx(d, k, src);
+          cp.rbase_v[i + 1] = cp.rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
+          cp.rbase_m[i + 1] = cp.rbase_m[i] + meta_bytes(c.nseg, c.nidx);
         }
-      need_vals[d] = (size_t)rbase_v[ridx(d, K - 1, P - 1) + 1] * esz;
-      need_meta[d] = (size_t)rbase_m[ridx(d, K - 1, P - 1) + 1];
+      need_vals[d] = (size_t)cp.rbase_v[cp.ridx(d, K - 1, P - 1) + 1] * esz;
+      need_meta[d] = (size_t)cp.rbase_m[cp.ridx(d, K - 1, P - 1) + 1];
     }
   };
   lay_out();
-  if (deferred) {
+  if (cp.deferred) {
     // an arena that has to grow is reallocated: everybody applies and truncates its log first (the
     // capacities are tracked identically on every rank, so this is the same decision everywhere)
     bool grow = false;
@@ -1170,323 +993,237 @@ int commit_exchange(cm_matrix *M) {
   }
   CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
 
-  // -- where my messages go: mode 2 = straight into the owners' arenas; otherwise my own messages
-  // into my arena and the others into a local send arena (moved by NCCL or by the copy engines)
-  const bool remote_store = M->p2p && !M->dma;
+  // where my messages go: peer-to-peer = straight into the owners' arenas; otherwise my own message
+  // into my arena and the others into a local send arena (moved by the all-to-all-v)
   std::vector<long> s_val_base((size_t)K * P + 1, 0), s_meta_base((size_t)K * P + 1, 0);
   for (int k = 0; k < K; ++k)
     for (int d = 0; d < P; ++d) {
-      const MsgCounts &c = counts[cidx(me, k, d)];
-      const bool staged = !remote_store && d != me;
+      const MsgCounts &c = counts[cp.cidx(me, k, d)];
+      const bool staged = !M->p2p && d != me;
       const size_t i = (size_t)k * P + d;
       s_val_base[i + 1] = s_val_base[i] + (staged ? ((c.nvals + 31) & ~31L) : 0);
       s_meta_base[i + 1] = s_meta_base[i] + (staged ? meta_bytes(c.nseg, c.nidx) : 0);
     }
-  if (!remote_store) {
+  if (!M->p2p) {
     CM_TRY(M->d_send_vals.ensure(std::max((size_t)s_val_base[(size_t)K * P] * esz, (size_t)256)));
     CM_TRY(M->d_send_meta.ensure(std::max((size_t)s_meta_base[(size_t)K * P], (size_t)256)));
   }
-  std::vector<void *> dst_ptrs(2 * (size_t)K * P);
+  cp.dst_ptrs.resize(2 * (size_t)K * P);
   for (int k = 0; k < K; ++k)
     for (int d = 0; d < P; ++d) {
       const size_t i = (size_t)k * P + d;
-      if (remote_store || d == me) {
-        dst_ptrs[i] = static_cast<char *>(M->peer_vals[d]) + (size_t)rbase_v[ridx(d, k, me)] * esz;
-        dst_ptrs[(size_t)K * P + i] = static_cast<char *>(M->peer_meta[d]) + rbase_m[ridx(d, k, me)];
+      if (M->p2p || d == me) {
+        cp.dst_ptrs[i] = static_cast<char *>(M->peer_vals[d]) + (size_t)cp.rbase_v[cp.ridx(d, k, me)] * esz;
+        cp.dst_ptrs[(size_t)K * P + i] = static_cast<char *>(M->peer_meta[d]) + cp.rbase_m[cp.ridx(d, k, me)];
       } else {
-        dst_ptrs[i] = M->d_send_vals.as<char>() + (size_t)s_val_base[i] * esz;
-        dst_ptrs[(size_t)K * P + i] = M->d_send_meta.as<char>() + s_meta_base[i];
+        cp.dst_ptrs[i] = M->d_send_vals.as<char>() + (size_t)s_val_base[i] * esz;
+        cp.dst_ptrs[(size_t)K * P + i] = M->d_send_meta.as<char>() + s_meta_base[i];
       }
     }
-  if (!packed)
-    CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
-                                M->stream));
+  CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, cp.dst_ptrs.data(), cp.dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                              M->stream));
 
-  // -- COO blobs (elemental updates): [inds x n][vals x n] per owner, always via the transport --
-  auto coo_blob = [esz](long n) { return n * 8 + (long)(((size_t)n * esz + 7) & ~(size_t)7); };
-  std::vector<long> r_coo_base(P + 1, 0), s_coo_base(P + 1, 0);
+  // COO blobs (elemental updates): [inds x n][vals x n] per owner, always via the transport
+  cp.r_coo_base.assign(P + 1, 0);
+  cp.s_coo_base.assign(P + 1, 0);
   for (int r = 0; r < P; ++r) {
-    r_coo_base[r + 1] = r_coo_base[r] + (r != me ? coo_blob(coo_counts[(size_t)r * P + me]) : 0);
-    s_coo_base[r + 1] = s_coo_base[r] + coo_blob((long)M->coo[r].inds.size());
+    cp.r_coo_base[r + 1] = cp.r_coo_base[r] + (r != me ? cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me]) : 0);
+    cp.s_coo_base[r + 1] = cp.s_coo_base[r] + cp.coo_blob(esz, (long)M->coo[r].inds.size());
   }
-  CM_TRY(M->d_recv_coo.ensure(std::max((size_t)r_coo_base[P], (size_t)256)));
-  CM_TRY(M->d_send_coo.ensure(std::max((size_t)s_coo_base[P], (size_t)256)));
+  CM_TRY(M->d_recv_coo.ensure(std::max((size_t)cp.r_coo_base[P], (size_t)256)));
+  CM_TRY(M->d_send_coo.ensure(std::max((size_t)cp.s_coo_base[P], (size_t)256)));
   for (int d = 0; d < P; ++d) {
     const long n = (long)M->coo[d].inds.size();
     if (!n) continue;
-    char *dst = M->d_send_coo.as<char>() + s_coo_base[d];
+    char *dst = M->d_send_coo.as<char>() + cp.s_coo_base[d];
     CM_CUDA_TRY(cudaMemcpyAsync(dst, M->coo[d].inds.data(), (size_t)n * 8, cudaMemcpyHostToDevice, M->stream));
     CM_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)n * 8, M->coo[d].vals.data(), (size_t)n * esz, cudaMemcpyHostToDevice,
                                 M->stream));
     M->stats.h2d_bytes += n * (long)(8 + esz);
   }
-
-  // -- owner side of the panels [k0, k1): their messages -> one scatter-add
-  auto apply_panels = [&](int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) -> int {
-    std::vector<MsgRef> msgs;
-    long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
-    for (int k = k0; k < k1; ++k)
-      for (int src = 0; src < P; ++src) {
-        const MsgCounts &c = counts[cidx(src, k, me)];
-        if (c.nvals == 0) continue;
-        MsgRef m;
-        m.meta = static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, src)];
-        m.vals = static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, src)] * esz;
-        m.seg_base = seg_total;
-        m.item_base = item_total;
-        seg_total += c.nseg;
-        item_total += c.nitems;
-        elem_total += c.nelems;
-        max_seg = std::max(max_seg, c.nseg);
-        msgs.push_back(m);
-      }
-    return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
-  };
-
-  // -- exchange lanes of the transport (values + metadata only without p2p; COO always) ---------
-  auto transport_lanes = [&](int k0, int k1, bool with_coo) -> int {
-    bool global_lane = false;  // every rank must take the same branch: decide from the global counts
-    for (int src = 0; src < P && !global_lane; ++src)
-      for (int d = 0; d < P && !global_lane; ++d) {
-        if (src == d) continue;
-        if (with_coo && coo_counts[(size_t)src * P + d]) global_lane = true;
-        if (!M->p2p)
-          for (int k = k0; k < k1; ++k)
-            if (counts[cidx(src, k, d)].nvals) global_lane = true;
-      }
-    if (!global_lane) return CM_OK;  // peer-to-peer modes without elemental updates: nothing rides on the transport
-    const int nl = 2 * (k1 - k0) + 1;
-    std::vector<std::vector<XferSpec>> sends(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
-    std::vector<std::vector<XferSpec>> recvs(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
-    for (int r = 0; r < P; ++r) {
-      if (r == me) continue;
-      if (!M->p2p)  // NCCL mode only: values and metadata lanes
-        for (int k = k0; k < k1; ++k) {
-          const MsgCounts &cs = counts[cidx(me, k, r)];
-          const MsgCounts &cr = counts[cidx(r, k, me)];
-          const size_t i = (size_t)k * P + r;
-          const int l = 2 * (k - k0);
-          sends[l][r] = XferSpec{dst_ptrs[i], (size_t)cs.nvals * esz};
-          sends[l + 1][r] = XferSpec{dst_ptrs[(size_t)K * P + i], cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
-          recvs[l][r] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, r)] * esz,
-                                 (size_t)cr.nvals * esz};
-          recvs[l + 1][r] = XferSpec{static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, r)],
-                                     cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
-        }
-      if (with_coo) {
-        if (M->coo[r].inds.size())
-          sends[nl - 1][r] = XferSpec{M->d_send_coo.as<char>() + s_coo_base[r], (size_t)coo_blob((long)M->coo[r].inds.size())};
-        if (coo_counts[(size_t)r * P + me])
-          recvs[nl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + r_coo_base[r], (size_t)coo_blob(coo_counts[(size_t)r * P + me])};
-      }
-    }
-    {
-      ScopedTimer t(M, 2, 0);
-      CM_TRY(tp->alltoallv(sends, recvs, M->stream));
-    }
-    return CM_OK;
-  };
-
-  // -- mode 3: push the panels [k0, k1) to their owners with the copy engines, then tell every owner.
-  // `after` = event on the main stream behind the pack of those panels; the owner-side wait for
-  // all sources is enqueued on `waiter`.
-  auto dma_push = [&](int k0, int k1, cudaEvent_t after, cudaStream_t waiter) -> int {
-    constexpr int NS = cm_matrix::kXferStreams;
-    for (int x = 0; x < NS; ++x) CM_CUDA_TRY(cudaStreamWaitEvent(M->xfer_stream[x], after, 0));
-    const uint32_t seq = ++M->xfer_seq;
-    uint32_t *ring = static_cast<uint32_t *>(M->h_seq.p);
-    // peer r's traffic rides on stream (r - me) mod NS: at any moment the ranks target different peers
-    for (int dr = 1; dr < P; ++dr) {
-      const int r = (me + dr) % P;
-      cudaStream_t xs = M->xfer_stream[dr % NS];
-      for (int k = k0; k < k1; ++k) {
-        const MsgCounts &cs = counts[cidx(me, k, r)];
-        if (!cs.nvals) continue;
-        const size_t i = (size_t)k * P + r;
-        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_vals[r]) + (size_t)rbase_v[ridx(r, k, me)] * esz, dst_ptrs[i],
-                                    (size_t)cs.nvals * esz, cudaMemcpyDefault, xs));
-        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_meta[r]) + rbase_m[ridx(r, k, me)],
-                                    dst_ptrs[(size_t)K * P + i], (size_t)meta_bytes(cs.nseg, cs.nidx), cudaMemcpyDefault, xs));
-      }
-      if (!tp->same_process()) {  // tell owner r: everything of mine for these panels has landed
-        uint32_t *slot = ring + (M->seq_slot++ % 1024);
-        *slot = seq;
-        CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)me, slot, 4, cudaMemcpyDefault, xs));
-      }
-    }
-    if (tp->same_process()) {
-      // threads-as-ranks on one device: a host rendezvous instead of device-side flag waits
-      // (many streams of one process share hardware queues; a stream wait could block its releaser)
-      for (int x = 0; x < NS; ++x) CM_CUDA_TRY(cudaStreamSynchronize(M->xfer_stream[x]));
-      CM_TRY(tp->stream_barrier(M->xfer_stream[0]));
-      return CM_OK;
-    }
-    for (int r = 0; r < P; ++r) {
-      if (r == me) continue;
-      const int rc = wait_value_geq(waiter, M->d_flags.as<char>() + 4 * (size_t)r, seq);
-      if (rc != 0) return fail(CM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
-    }
-    return CM_OK;
-  };
-
   for (int r = 0; r < P; ++r) {
     if (r == me) continue;
     for (int k = 0; k < K; ++k) {
-      const MsgCounts &cs = counts[cidx(me, k, r)], &cr = counts[cidx(r, k, me)];
+      const MsgCounts &cs = counts[cp.cidx(me, k, r)], &cr = counts[cp.cidx(r, k, me)];
       M->stats.bytes_sent += (long)(cs.nvals * esz + (cs.nvals ? meta_bytes(cs.nseg, cs.nidx) : 0));
       M->stats.bytes_received += (long)(cr.nvals * esz + (cr.nvals ? meta_bytes(cr.nseg, cr.nidx) : 0));
     }
-    M->stats.bytes_sent += coo_blob((long)M->coo[r].inds.size()) * (M->coo[r].inds.empty() ? 0 : 1);
-    M->stats.bytes_received += coo_blob(coo_counts[(size_t)r * P + me]) * (coo_counts[(size_t)r * P + me] ? 1 : 0);
+    M->stats.bytes_sent += cp.coo_blob(esz, (long)M->coo[r].inds.size()) * (M->coo[r].inds.empty() ? 0 : 1);
+    M->stats.bytes_received += cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me]) * (cp.coo_counts[(size_t)r * P + me] ? 1 : 0);
   }
+  return CM_OK;
+}
 
-  int Kp = 0;  // panel slots that hold data on any rank (same value everywhere)
-  for (int src = 0; src < P; ++src)
-    for (int k = 0; k < K; ++k)
-      for (int d = 0; d < P; ++d)
-        if (counts[cidx(src, k, d)].nvals) Kp = std::max(Kp, k + 1);
-  auto panel_has_data = [&](int k) {  // does this rank send anything in panel k?
-    if (k >= pp.npanel || nupd == 0) return false;
-    for (int d = 0; d < P; ++d)
-      if (counts[cidx(me, k, d)].nvals) return true;
-    return false;
-  };
-
-  if (!pipelined) {
-    // one batch: pack everything, (all-to-all-v), barrier, one scatter-add over all messages
-    if (!packed) {
-      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, pp.npanel, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
-      M->stats.kernel_launches += nupd ? 1 : 0;
-      if (M->profiling) cudaEventRecord(ev_pack1, M->stream);
+// owner side of the panels [k0, k1): their messages -> one scatter-add on stream `st`
+int apply_panels(cm_matrix *M, const CommitPlan &cp, int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
+  std::vector<MsgRef> msgs;
+  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+  for (int k = k0; k < k1; ++k)
+    for (int src = 0; src < cp.P; ++src) {
+      const MsgCounts &c = cp.counts[cp.cidx(src, k, cp.me)];
+      if (c.nvals == 0) continue;
+      MsgRef m;
+      m.meta = static_cast<char *>(M->peer_meta[cp.me]) + cp.rbase_m[cp.ridx(cp.me, k, src)];
+      m.vals = static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.rbase_v[cp.ridx(cp.me, k, src)] * M->esz;
+      m.seg_base = seg_total;
+      m.item_base = item_total;
+      seg_total += c.nseg;
+      item_total += c.nitems;
+      elem_total += c.nelems;
+      max_seg = std::max(max_seg, c.nseg);
+      msgs.push_back(m);
     }
-    if (M->profiling) M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
+  return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
+}
+
+// exchange lanes of the transport: values + metadata of the panels [k0, k1) without peer-to-peer stores,
+// elemental updates (COO) always
+int transport_lanes(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool with_coo) {
+  const int P = cp.P, me = cp.me, K = cp.K;
+  const size_t esz = M->esz;
+  const MsgCounts *counts = cp.counts;
+  bool global_lane = false;  // every rank must take the same branch: decide from the global counts
+  for (int src = 0; src < P && !global_lane; ++src)
+    for (int d = 0; d < P && !global_lane; ++d) {
+      if (src == d) continue;
+      if (with_coo && cp.coo_counts[(size_t)src * P + d]) global_lane = true;
+      if (!M->p2p)
+        for (int k = k0; k < k1; ++k)
+          if (counts[cp.cidx(src, k, d)].nvals) global_lane = true;
+    }
+  if (!global_lane) return CM_OK;  // peer-to-peer stores without elemental updates: nothing rides on the transport
+  const int nl = 2 * (k1 - k0) + 1;
+  std::vector<std::vector<XferSpec>> sends(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
+  std::vector<std::vector<XferSpec>> recvs(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
+  for (int r = 0; r < P; ++r) {
+    if (r == me) continue;
+    if (!M->p2p)
+      for (int k = k0; k < k1; ++k) {
+        const MsgCounts &cs = counts[cp.cidx(me, k, r)];
+        const MsgCounts &cr = counts[cp.cidx(r, k, me)];
+        const size_t i = (size_t)k * P + r;
+        const int l = 2 * (k - k0);
+        sends[l][r] = XferSpec{cp.dst_ptrs[i], (size_t)cs.nvals * esz};
+        sends[l + 1][r] = XferSpec{cp.dst_ptrs[(size_t)K * P + i], cs.nvals ? (size_t)meta_bytes(cs.nseg, cs.nidx) : 0};
+        recvs[l][r] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)cp.rbase_v[cp.ridx(me, k, r)] * esz,
+                               (size_t)cr.nvals * esz};
+        recvs[l + 1][r] = XferSpec{static_cast<char *>(M->peer_meta[me]) + cp.rbase_m[cp.ridx(me, k, r)],
+                                   cr.nvals ? (size_t)meta_bytes(cr.nseg, cr.nidx) : 0};
+      }
+    if (with_coo) {
+      if (M->coo[r].inds.size())
+        sends[nl - 1][r] = XferSpec{M->d_send_coo.as<char>() + cp.s_coo_base[r], (size_t)cp.coo_blob(esz, (long)M->coo[r].inds.size())};
+      if (cp.coo_counts[(size_t)r * P + me])
+        recvs[nl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + cp.r_coo_base[r], (size_t)cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me])};
+    }
+  }
+  ScopedTimer t(M, 2, 0);
+  return M->ctx->tp->alltoallv(sends, recvs, M->stream);
+}
+
+// -- pack / exchange, and for a pipelined commit the owners' scatter-adds panel by panel ------------
+int commit_deliver(cm_matrix *M, CommitPlan &cp) {
+  const int P = cp.P, K = cp.K, nupd = cp.nupd;
+  if (!cp.pipelined) {
+    // one batch: pack everything, (all-to-all-v), barrier; the scatter-add follows in commit_finish
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, cp.pp.npanel, cp.pp, M->g, cp.ma, cp.sa, cp.max_rows, M->stream);
+    M->stats.kernel_launches += nupd ? 1 : 0;
+    if (M->profiling) {
+      cudaEventRecord(cp.ev_pack1, M->stream);
+      M->timers.push_back(PendingTimer{1, cp.ev_pack0, cp.ev_pack1, 0});
+    }
     CM_CUDA_TRY(cudaGetLastError());
-    CM_TRY(transport_lanes(0, K, true));
-    if (M->dma && P > 1) {
-      // copy engines push my messages; the scatter-add waits for every source's flag
-      CM_CUDA_TRY(cudaEventRecord(M->ev_packed[0], M->stream));
-      ScopedTimer t(M, 2, 0);
-      CM_TRY(dma_push(0, K, M->ev_packed[0], M->stream));
-    } else if (M->p2p && P > 1) {
-      // mode 2: every source's pack kernel has finished storing into my arenas
-      CM_TRY(commit_stream_barrier(M, M->stream));
-    }
-  } else if (M->dma) {
-    // pipelined, mode 3: panel k is packed locally (main stream), pushed by the copy engines
-    // (xfer stream) and scatter-added (apply stream) while panel k+1 is packed and pushed. The
-    // exchange uses no SM at all, so the two kernels never compete with communication.
-    CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
-    for (int k = 0; k < Kp; ++k) {
-      if (panel_has_data(k)) {
-        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
-        M->stats.kernel_launches += 1;
-      }
-      CM_CUDA_TRY(cudaEventRecord(M->ev_packed[k], M->stream));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_packed[k], 0));  // my own message of panel k
-      CM_TRY(dma_push(k, k + 1, M->ev_packed[k], M->apply_stream));
-      CM_TRY(apply_panels(k, k + 1, M->work[k], M->apply_stream, 0));
-    }
-    if (M->profiling) {
-      cudaEventRecord(ev_pack1, M->stream);
-      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
-    }
-    CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
-    CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
-    for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
-      CM_CUDA_TRY(cudaEventRecord(M->ev_xfer[x], M->xfer_stream[x]));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_xfer[x], 0));
-    }
-  } else {
-    // pipelined, mode 2: panel k is packed straight into the owners' arenas, a stream-ordered
-    // barrier says "everybody's panel k has landed", and its scatter-add (which touches only panel
-    // k's columns of the local block) runs on the apply stream while panel k+1 is being packed and
-    // stored across NVLink on the main stream
-    CM_TRY(transport_lanes(0, 0, true));  // COO lane, if any
-    for (int k = 0; k < Kp; ++k) {
-      if (panel_has_data(k)) {
-        launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, pp, M->g, ma, sa, max_rows, M->pack_cfg, M->stream);
-        M->stats.kernel_launches += 1;
-      }
-      // "everybody's panel k has landed" is awaited on the apply stream: the main stream goes straight
-      // on to the pack of panel k+1
-      CM_CUDA_TRY(cudaEventRecord(M->ev_panel[k], M->stream));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_panel[k], 0));
-      CM_TRY(commit_stream_barrier(M, M->apply_stream));
-      // all but the last panel's scatter-add share the SMs with the next panel's pack kernel
-      CM_TRY(apply_panels(k, k + 1, M->work[k], M->apply_stream, k + 1 < Kp ? M->pipeline_apply_blocks : 0));
-    }
-    if (M->profiling) {
-      cudaEventRecord(ev_pack1, M->stream);
-      M->timers.push_back(PendingTimer{1, ev_pack0, ev_pack1, 0});
-    }
-    CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
-    CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
+    trace_mark(M, "deliver: packed");
+    CM_TRY(transport_lanes(M, cp, 0, K, true));
+    // peer-to-peer: every source's pack kernel has finished storing into my arenas
+    if (M->p2p && P > 1) CM_TRY(commit_stream_barrier(M, M->stream));
+    trace_mark(M, "deliver: everybody packed");
+    return CM_OK;
   }
-
-  if (M->keep_wire) {
-    // what THIS rank sent to every owner, panel after panel, read back from wherever pack put it
-    CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
-    if (packed) {  // debug mode: the device-side layout must agree with the host's, pointer for pointer
-      std::vector<void *> dev_ptrs(dst_ptrs.size());
-      CM_CUDA_TRY(cudaMemcpy(dev_ptrs.data(), M->d_dst_ptrs.p, dev_ptrs.size() * sizeof(void *), cudaMemcpyDeviceToHost));
-      for (int k = 0; k < K; ++k)
-        for (int d = 0; d < P; ++d)
-          if (counts[cidx(me, k, d)].nvals &&
-              (dev_ptrs[(size_t)k * P + d] != dst_ptrs[(size_t)k * P + d] ||
-               dev_ptrs[(size_t)K * P + (size_t)k * P + d] != dst_ptrs[(size_t)K * P + (size_t)k * P + d]))
-            return fail(CM_ERR_STATE, "device-side layout disagrees with the host layout (panel %d, owner %d)", k, d);
+  // pipelined (peer-to-peer stores): panel k is packed straight into the owners' arenas, a stream-ordered
+  // barrier says "everybody's panel k has landed", and its scatter-add (which touches only panel
+  // k's columns of the local block) runs on the apply stream while panel k+1 is being packed and
+  // stored across NVLink on the main stream
+  CM_TRY(transport_lanes(M, cp, 0, 0, true));  // COO lane, if any
+  for (int k = 0; k < cp.Kp; ++k) {
+    if (cp.panel_has_data(k)) {
+      launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, k, k + 1, cp.pp, M->g, cp.ma, cp.sa, cp.max_rows, M->stream);
+      M->stats.kernel_launches += 1;
     }
-    M->dbg_msgs.clear();
-    for (int d = 0; d < P; ++d)
-      for (int k = 0; k < K; ++k) {
-        const MsgCounts &c = counts[cidx(me, k, d)];
-        cm_matrix::DbgMsg dm;
-        dm.dst = d;
-        if (c.nvals) {
-          const size_t i = (size_t)k * P + d;
-          dm.meta.resize((size_t)meta_bytes(c.nseg, c.nidx));
-          dm.vals.resize((size_t)c.nvals * esz);
-          CM_CUDA_TRY(cudaMemcpy(dm.meta.data(), dst_ptrs[(size_t)K * P + i], dm.meta.size(), cudaMemcpyDefault));
-          CM_CUDA_TRY(cudaMemcpy(dm.vals.data(), dst_ptrs[i], dm.vals.size(), cudaMemcpyDefault));
-        }
-        M->dbg_msgs.push_back(std::move(dm));
-      }
-    M->dbg_coo = M->coo;
-    M->dbg_valid = true;
+    trace_mark(M, "deliver: panel packed");
+    // "everybody's panel k has landed" is awaited on the apply stream: the main stream goes straight
+    // on to the pack of panel k+1
+    CM_CUDA_TRY(cudaEventRecord(M->ev_panel[k], M->stream));
+    CM_CUDA_TRY(cudaStreamWaitEvent(M->apply_stream, M->ev_panel[k], 0));
+    CM_TRY(commit_stream_barrier(M, M->apply_stream));
+    trace_mark(M, "deliver: panel landed", M->apply_stream);
+    // all but the last panel's scatter-add share the SMs with the next panel's pack kernel
+    CM_TRY(apply_panels(M, cp, k, k + 1, M->work[k], M->apply_stream, k + 1 < cp.Kp ? M->pipeline_apply_blocks : 0));
+    trace_mark(M, "deliver: panel applied", M->apply_stream);
   }
+  if (M->profiling) {
+    cudaEventRecord(cp.ev_pack1, M->stream);
+    M->timers.push_back(PendingTimer{1, cp.ev_pack0, cp.ev_pack1, 0});
+  }
+  CM_CUDA_TRY(cudaEventRecord(M->ev_applied, M->apply_stream));
+  CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_applied, 0));
+  return CM_OK;
+}
 
-  if (deferred) {
+// what THIS rank sent to every owner, panel after panel, read back from wherever pack put it (parity tests)
+int capture_wire(cm_matrix *M, const CommitPlan &cp) {
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  M->dbg_msgs.clear();
+  for (int d = 0; d < cp.P; ++d)
+    for (int k = 0; k < cp.K; ++k) {
+      const MsgCounts &c = cp.counts[cp.cidx(cp.me, k, d)];
+      cm_matrix::DbgMsg dm;
+      dm.dst = d;
+      if (c.nvals) {
+        const size_t i = (size_t)k * cp.P + d;
+        dm.meta.resize((size_t)meta_bytes(c.nseg, c.nidx));
+        dm.vals.resize((size_t)c.nvals * M->esz);
+        CM_CUDA_TRY(cudaMemcpy(dm.meta.data(), cp.dst_ptrs[(size_t)cp.K * cp.P + i], dm.meta.size(), cudaMemcpyDefault));
+        CM_CUDA_TRY(cudaMemcpy(dm.vals.data(), cp.dst_ptrs[i], dm.vals.size(), cudaMemcpyDefault));
+      }
+      M->dbg_msgs.push_back(std::move(dm));
+    }
+  M->dbg_coo = M->coo;
+  M->dbg_valid = true;
+  return CM_OK;
+}
+
+// -- log or scatter-add what was delivered, elemental updates, quiescence ---------------------------
+int commit_finish(cm_matrix *M, CommitPlan &cp) {
+  const int P = cp.P, me = cp.me, K = cp.K;
+  if (M->keep_wire) CM_TRY(capture_wire(M, cp));
+  if (cp.deferred) {
     // log instead of apply: the messages of this commit stay where they landed
     for (int k = 0; k < K; ++k)
       for (int src = 0; src < P; ++src) {
-        const MsgCounts &c = counts[cidx(src, k, me)];
+        const MsgCounts &c = cp.counts[cp.cidx(src, k, me)];
         if (c.nvals == 0) continue;
-        M->pend.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[me]) + rbase_m[ridx(me, k, src)],
-                                            static_cast<char *>(M->peer_vals[me]) + (size_t)rbase_v[ridx(me, k, src)] * esz,
+        M->pend.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[me]) + cp.rbase_m[cp.ridx(me, k, src)],
+                                            static_cast<char *>(M->peer_vals[me]) + (size_t)cp.rbase_v[cp.ridx(me, k, src)] * M->esz,
                                             c.nseg, c.nitems, c.nelems});
       }
     for (int d = 0; d < P; ++d) {
-      M->pend_v[d] = rbase_v[ridx(d, K - 1, P - 1) + 1];
-      M->pend_m[d] = rbase_m[ridx(d, K - 1, P - 1) + 1];
+      M->pend_v[d] = cp.rbase_v[cp.ridx(d, K - 1, P - 1) + 1];
+      M->pend_m[d] = cp.rbase_m[cp.ridx(d, K - 1, P - 1) + 1];
     }
-  } else if (!pipelined) {
-    CM_TRY(apply_panels(0, K, M->work[0], M->stream, 0));
-  }
-  if (M->dma && P > 1 && !pipelined) {  // my pushes are complete before anyone may reuse the arenas
-    for (int x = 0; x < cm_matrix::kXferStreams; ++x) {
-      CM_CUDA_TRY(cudaEventRecord(M->ev_xfer[x], M->xfer_stream[x]));
-      CM_CUDA_TRY(cudaStreamWaitEvent(M->stream, M->ev_xfer[x], 0));
-    }
+  } else if (!cp.pipelined) {
+    CM_TRY(apply_panels(M, cp, 0, K, M->work[0], M->stream, 0));
+    trace_mark(M, "finish: scatter-add done");
   }
   for (int src = 0; src < P; ++src) {
-    const long n = coo_counts[(size_t)src * P + me];
+    const long n = cp.coo_counts[(size_t)src * P + me];
     if (!n) continue;
     CM_TRY(wait_background(M));  // the tile kernel's write-back is not atomic: no RED into the block beside it
-    const char *blob = src == me ? M->d_send_coo.as<char>() + s_coo_base[me] : M->d_recv_coo.as<char>() + r_coo_base[src];
+    const char *blob = src == me ? M->d_send_coo.as<char>() + cp.s_coo_base[me] : M->d_recv_coo.as<char>() + cp.r_coo_base[src];
     CM_TRY(apply_coo_blob(M, blob, n));
   }
   CM_CUDA_TRY(cudaGetLastError());
-  if (deferred) {
+  if (cp.deferred) {
     // delivery is complete (the barrier behind the pack kernels) once this stream has drained; the
     // log is append-only, so no second barrier is needed before the next commit may store
     CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
@@ -1494,18 +1231,54 @@ int commit_exchange(cm_matrix *M) {
     resolve_timers(M);
     clear_staged(M);
     bool over = false;  // same decision on every rank
-    for (int d = 0; d < P; ++d) over = over || (size_t)M->pend_v[d] * esz > M->defer_budget;
+    for (int d = 0; d < P; ++d) over = over || (size_t)M->pend_v[d] * M->esz > M->defer_budget;
     if (over) CM_TRY(materialize_all(M));
     else if (M->apply_policy == CM_APPLY_BACKGROUND) CM_TRY(start_background_apply(M));
+    trace_dump(M, true);
     return CM_OK;
   }
-  // -- quiescence: everybody has applied everything (reference :737-741) --------------------
+  // quiescence: everybody has applied everything (reference :737-741)
   CM_TRY(commit_barrier(M, M->stream));
   CM_CUDA_TRY(cudaGetLastError());
+  trace_mark(M, "finish: quiescent");
   resolve_timers(M);
+  trace_dump(M, true);
   M->mirror_valid = false;
   clear_staged(M);
   return CM_OK;
+}
+
+int commit_exchange(cm_matrix *M) {
+  CommitPlan cp;
+  cp.P = M->P;
+  cp.me = M->me;
+  cp.nupd = (int)M->descs.size();
+  trace_mark(M, "commit: begin");
+  // a staged payload that is the local block itself (fill_lower) is read by the pack kernel: no scatter-add
+  // of an earlier commit may still be writing the block
+  if (M->reads_local_block) CM_TRY(wait_background(M));
+  CM_TRY(commit_counts(M, cp));
+  if (cp.empty) {
+    // nothing staged on any rank: the counts all-gather already was the rendezvous of this commit
+    // (nobody leaves it before everybody has entered it); there is nothing to exchange, to apply or
+    // to wait for, so the barriers are skipped (empty-commit latency)
+    if (M->profiling) {
+      M->event_pool.push_back(cp.ev_pack0);
+      M->event_pool.push_back(cp.ev_pack1);
+    }
+    if (M->keep_wire) {
+      M->dbg_msgs.clear();
+      M->dbg_coo = M->coo;
+      M->dbg_valid = true;
+    }
+    resolve_timers(M);
+    trace_dump(M, true);
+    clear_staged(M);
+    return CM_OK;
+  }
+  CM_TRY(commit_layout(M, cp));
+  CM_TRY(commit_deliver(M, cp));
+  return commit_finish(M, cp);
 }
 
 int do_commit(cm_matrix *M) {
@@ -1727,11 +1500,6 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     e = cudaStreamCreateWithPriority(&M->apply_stream, cudaStreamNonBlocking, prio_hi);
   }
-  for (int k = 0; k < cm_matrix::kXferStreams && e == cudaSuccess; ++k) {
-    e = cudaStreamCreateWithFlags(&M->xfer_stream[k], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_xfer[k], cudaEventDisableTiming);
-  }
-  for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_packed[k], cudaEventDisableTiming);
   for (int k = 0; k < kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&M->ev_panel[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_applied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&M->ev_bg, cudaEventDisableTiming);
@@ -1779,47 +1547,6 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
       }
     }
   }
-  // per-source arrival flags for the copy-engine exchange, mapped like the local block
-  bool flags_ok = true;
-  M->peer_flags.assign(M->P, nullptr);
-  M->peer_flags_open.assign(M->P, false);
-  if (M->P > 1) {
-    M->counts_off = (3 * 4 * (size_t)M->P + 255) & ~(size_t)255;
-    // two tables, used alternately: a rank that leaves an (empty) commit early may already publish the
-    // next commit's counts while a slower rank is still reading this one's
-    const size_t block_bytes = M->counts_off + 2 * sizeof(MsgCounts) * (size_t)M->P * kMaxChunks * M->P;
-    int rcf = M->d_flags.ensure(block_bytes);
-    if (rcf == CM_OK) rcf = M->h_seq.ensure(4 * 1024);
-    if (rcf != CM_OK) return rcf;
-    cudaMemsetAsync(M->d_flags.p, 0, block_bytes, M->stream);
-    cudaStreamSynchronize(M->stream);
-    M->peer_flags[M->me] = M->d_flags.p;
-    if (ctx->tp->same_process()) {
-      std::vector<void *> all(M->P);
-      int rc1 = ctx->tp->host_allgather(&M->d_flags.p, all.data(), sizeof(void *), M->stream);
-      if (rc1 != CM_OK) return rc1;
-      M->peer_flags = all;
-    } else {
-      cudaIpcMemHandle_t mine;
-      std::vector<cudaIpcMemHandle_t> all(M->P);
-      memset(&mine, 0, sizeof(mine));
-      const bool have = cudaIpcGetMemHandle(&mine, M->d_flags.p) == cudaSuccess;
-      if (!have) cudaGetLastError();
-      int rc1 = ctx->tp->host_allgather(&mine, all.data(), sizeof(mine), M->stream);
-      if (rc1 != CM_OK) return rc1;
-      for (int r = 0; r < M->P; ++r) {
-        if (r == M->me) continue;
-        void *pp = nullptr;
-        if (have && cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
-          M->peer_flags[r] = pp;
-          M->peer_flags_open[r] = true;
-        } else {
-          cudaGetLastError();
-          flags_ok = false;
-        }
-      }
-    }
-  }
   M->peer_vals.assign(M->P, nullptr);
   M->peer_meta.assign(M->P, nullptr);
   M->cap_vals.assign(M->P, 0);
@@ -1829,58 +1556,27 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->pend_m.assign(M->P, 0);
   {
     // peer-to-peer stores need every rank to be able to map every other rank's memory
-    int mine_ok = flags_ok ? 1 : 0;
+    int mine_ok = 1;
     for (int r = 0; r < M->P; ++r) mine_ok &= M->peer_local[r] != nullptr;
-    flags_ok = true;  // folded into the collective decision below
     std::vector<int> all_ok(M->P, 0);
     int rc0 = ctx->tp->host_allgather(&mine_ok, all_ok.data(), sizeof(int), M->stream);
     if (rc0 != CM_OK) return rc0;
     M->p2p_possible = true;
     for (int r = 0; r < M->P; ++r) M->p2p_possible &= all_ok[r] != 0;
-    // CM_B200_PROFILE=fast switches on the opt-in protocol variants together (every one of them can still be
-    // overridden by its own variable below); "measured" (default) is the configuration of BASELINE.md section 5
-    if (const char *prof = getenv("CM_B200_PROFILE")) {
-      if (!strcmp(prof, "fast")) {
-        M->pipeline = 1;
-        M->flag_barrier = 1;
-        M->device_layout = 1;
-        M->pinned_descs = 1;
-        M->seg_apply = 1;
-      }
-    }
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PIPELINE_APPLY_BLOCKS")) M->pipeline_apply_blocks = std::max(0, atoi(getenv("CM_B200_PIPELINE_APPLY_BLOCKS")));
     if (getenv("CM_B200_PANELS")) M->npanel_cfg = std::max(1, atoi(getenv("CM_B200_PANELS")));
     if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
-    const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" / "dma" override, must agree on all ranks
+    const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
     if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;
-    if (env && !strcmp(env, "dma")) M->exchange_mode = 3;
-    M->p2p_possible &= flags_ok;
     M->p2p = M->P > 1 && M->p2p_possible && M->exchange_mode != 1;
-    M->dma = M->p2p && M->exchange_mode == 3 && (ctx->tp->same_process() || stream_wait_value32() != nullptr);
-    if (getenv("CM_B200_FLAG_BARRIER")) M->flag_barrier = atoi(getenv("CM_B200_FLAG_BARRIER"));
-    if (getenv("CM_B200_PINNED_DESCS")) M->pinned_descs = atoi(getenv("CM_B200_PINNED_DESCS")) != 0 ? 1 : 0;
-    if (getenv("CM_B200_PACK_THREADS")) M->pack_cfg.threads = std::max(0, atoi(getenv("CM_B200_PACK_THREADS")));
-    if (getenv("CM_B200_PACK_BULK")) M->pack_cfg.bulk = atoi(getenv("CM_B200_PACK_BULK")) != 0 ? 1 : 0;
-    if (getenv("CM_B200_PACK_COLS")) M->pack_cfg.cols = atoi(getenv("CM_B200_PACK_COLS")) == 8 ? 8 : 4;
     if (const char *pol = getenv("CM_B200_APPLY_POLICY")) {  // default policy of new matrices: eager | deferred | background
       if (!strcmp(pol, "deferred")) M->apply_policy = CM_APPLY_DEFERRED;
       if (!strcmp(pol, "background")) M->apply_policy = CM_APPLY_BACKGROUND;
     }
     if (getenv("CM_B200_BG_MIN_ELEMS")) M->bg_min_elems = atol(getenv("CM_B200_BG_MIN_ELEMS"));
-    if (getenv("CM_B200_SEG_APPLY")) M->seg_apply = atoi(getenv("CM_B200_SEG_APPLY")) != 0 ? 1 : 0;
-    if (getenv("CM_B200_DEVICE_LAYOUT")) M->device_layout = atoi(getenv("CM_B200_DEVICE_LAYOUT")) != 0 ? 1 : 0;
-    if (M->P > 1 && M->p2p_possible) {
-      std::vector<void *> rows(M->P);
-      for (int r = 0; r < M->P; ++r) rows[r] = static_cast<char *>(M->peer_flags[r]) + 4 * (size_t)M->P;
-      int rcr = M->d_peer_rows.ensure(sizeof(void *) * (size_t)M->P);
-      if (rcr == CM_OK) rcr = M->d_peer_bases.ensure(sizeof(void *) * (size_t)M->P);
-      if (rcr != CM_OK) return rcr;
-      cudaMemcpyAsync(M->d_peer_rows.p, rows.data(), sizeof(void *) * (size_t)M->P, cudaMemcpyHostToDevice, M->stream);
-      cudaMemcpyAsync(M->d_peer_bases.p, M->peer_flags.data(), sizeof(void *) * (size_t)M->P, cudaMemcpyHostToDevice, M->stream);
-      cudaStreamSynchronize(M->stream);
-    }
+    if (getenv("CM_B200_TRACE") && M->me == 0) M->trace_left = atoi(getenv("CM_B200_TRACE"));
   }
   int rc = ctx->tp->barrier(M->stream);
   if (rc != CM_OK) return rc;
@@ -1899,7 +1595,6 @@ int cm_destroy(cm_matrix *M) {
       cudaIpcCloseMemHandle(M->peer_vals[r]);
       cudaIpcCloseMemHandle(M->peer_meta[r]);
     }
-    if (M->peer_flags_open[r]) cudaIpcCloseMemHandle(M->peer_flags[r]);
   }
   M->ctx->tp->barrier(M->stream);  // nobody still reads my block
   cudaFree(M->d_local);
@@ -1913,20 +1608,6 @@ int cm_destroy(cm_matrix *M) {
   for (DevBuf *b : bufs) b->release();
   for (auto &w : M->work) w.release();
   cudaStreamDestroy(M->apply_stream);
-  for (auto st : M->xfer_stream) cudaStreamDestroy(st);
-  for (auto e : M->ev_packed) cudaEventDestroy(e);
-  for (auto e : M->ev_xfer) cudaEventDestroy(e);
-  for (int k = 0; k < 2; ++k) {
-    M->h_stage[k].release();
-    if (M->ev_stage[k]) cudaEventDestroy(M->ev_stage[k]);
-  }
-  M->d_flags.release();
-  M->d_peer_rows.release();
-  M->d_peer_bases.release();
-  M->d_arena_tab.release();
-  M->d_overflow.release();
-  M->h_overflow.release();
-  M->h_seq.release();
   for (auto e : M->ev_panel) cudaEventDestroy(e);
   cudaEventDestroy(M->ev_applied);
   cudaEventDestroy(M->ev_bg);
@@ -2028,6 +1709,7 @@ int cm_fill_lower(cm_matrix *M) {
   CM_TRY(check_dims(M->n_local, M->m_local));
   CM_TRY(stage_desc(M, M->d_local, M->n_local, M->m_local, g.lld, 1, M->d_fill_ix.as<long>(), M->d_fill_jx.as<long>(),
                     CM_MASK_STRICT_LOWER));
+  M->reads_local_block = true;  // the commit that ships this packs it before any scatter-add touches the block
   // single rank: apply now, so later updates cannot change what fill_lower reads (the
   // reference reads the block at call time)
   if (M->P == 1 && !M->keep_wire) return flush_direct(M);
@@ -2236,7 +1918,6 @@ int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes) {
   if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the apply policy only with nothing staged");
   CM_TRY(materialize_all(M));
   M->apply_policy = policy;
-  M->arena_tab_dirty = true;
   if (budget_bytes > 0) M->defer_budget = (size_t)budget_bytes;
   return M->ctx->tp->barrier(M->stream);
 }
@@ -2248,17 +1929,14 @@ int cm_materialize(cm_matrix *M) {
 
 int cm_set_exchange_mode(cm_matrix *M, int mode) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
-  if (mode < 0 || mode > 3)
-    return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v), 2 (peer-to-peer stores) or 3 (copy engines)");
+  if (mode < 0 || mode > 2)
+    return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v) or 2 (peer-to-peer stores)");
   if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the exchange mode only with nothing staged");
   if (mode >= 2 && M->P > 1 && !M->p2p_possible)
     return fail(CM_ERR_STATE, "peer-to-peer exchange needs every rank's memory mapped (CUDA IPC unavailable)");
-  if (mode == 3 && M->P > 1 && !M->ctx->tp->same_process() && stream_wait_value32() == nullptr)
-    return fail(CM_ERR_STATE, "copy-engine exchange needs cuStreamWaitValue32");
   CM_TRY(materialize_all(M));  // the arenas are about to be released
   M->exchange_mode = mode;
   M->p2p = M->P > 1 && M->p2p_possible && mode != 1;
-  M->dma = M->p2p && mode == 3;
   // arenas allocated under the other mode are not mapped by the peers: start over
   for (int r = 0; r < M->P; ++r) {
     if (M->peer_arena_open[r]) {
@@ -2269,13 +1947,12 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
     M->peer_vals[r] = M->peer_meta[r] = nullptr;
     M->cap_vals[r] = M->cap_meta[r] = 0;
   }
-  M->arena_tab_dirty = true;
   CM_TRY(M->ctx->tp->barrier(M->stream));
   M->d_recv_vals.release();
   M->d_recv_meta.release();
   return CM_OK;
 }
-int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->dma ? 3 : (M->p2p ? 2 : 1)) : -1; }
+int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->p2p ? 2 : 1) : -1; }
 int cm_set_profiling(cm_matrix *M, int on) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   M->profiling = on ? 1 : 0;

@@ -21,43 +21,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS",
-         "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT", "CM_B200_PACK_COLS", "CM_B200_EXCHANGE", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_PINNED_DESCS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PROFILE", "CM_B200_PACK_BULK")
-# CM_B200_TILE_BULKRED is read once per process: time it with a separate invocation (--only batch, variable exported)
+KNOBS = ("CM_B200_PIPELINE", "CM_B200_PANELS", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PIPELINE_APPLY_BLOCKS", "CM_B200_EXCHANGE",
+         "CM_B200_BG_MIN_ELEMS", "CM_B200_APPLY_POLICY")
 
 # name, workloads it applies to, env, harness options
 VARIANTS = [
-    ("batch", "*", {}, {}),
-    ("profile-fast", "*", {"CM_B200_PROFILE": "fast"}, {}),
-    ("batch-pinned-descs", "*", {"CM_B200_PINNED_DESCS": "1"}, {}),
-    ("batch-cols8", "K1,K2", {"CM_B200_PACK_COLS": "8"}, {}),
-    ("batch-bulk", "K1,K2", {"CM_B200_PACK_BULK": "1"}, {}),
-    ("panels4-ab2-bulk", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_PACK_BULK": "1"}, {}),
-    ("batch-threads-auto", "K1,K2,K4", {"CM_B200_PACK_THREADS": "0"}, {}),
-    ("batch-threads-auto-cols8", "K1,K2", {"CM_B200_PACK_THREADS": "0", "CM_B200_PACK_COLS": "8"}, {}),
-    ("panels4-ab1", "K1,K2,K3", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {}),
-    ("panels4-ab2", "K1,K2,K3", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "2"}, {}),
-    ("panels4-ab3", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "3"}, {}),
-    ("panels2-ab2", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_PANELS": "2"}, {}),
-    ("panels4-ab2-cols8", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_PACK_COLS": "8"}, {}),
-    ("panels4-ab2-flags", "K1,K2", {"CM_B200_PIPELINE": "1", "CM_B200_FLAG_BARRIER": "1"}, {}),
-    ("flags", "*", {"CM_B200_FLAG_BARRIER": "1"}, {}),
-    ("flags-devlayout", "*", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {}),
-    ("devlayout", "K2,K4", {"CM_B200_DEVICE_LAYOUT": "1"}, {}),
-    ("segapply", "K4", {"CM_B200_SEG_APPLY": "1"}, {}),
-    ("segapply-flags-devlayout", "K4", {"CM_B200_SEG_APPLY": "1", "CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {}),
-    ("deferred", "K2,K3,K4", {}, {"deferred": 1}),
-    ("background", "K2,K3", {}, {"deferred": 2}),
-    ("background-ab1", "K2,K3", {"CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {"deferred": 2}),
-    ("deferred-flags-devlayout", "K2,K3,K4", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 1}),
-    ("background-flags-devlayout", "K2,K3", {"CM_B200_FLAG_BARRIER": "1", "CM_B200_DEVICE_LAYOUT": "1"}, {"deferred": 2}),
-    ("tile", "K3", {}, {"apply_kernel": 2}),
-    ("flush-2^26", "K1", {}, {"flush_threshold": 1 << 26, "n1_only": True}),
+    ("default", "*", {}, {}),
+    ("batch", "*", {"CM_B200_PIPELINE": "0"}, {}),
+    ("panels4-ab1", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {}),
+    ("panels4-ab2", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "2"}, {}),
+    ("panels4-ab3", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "3"}, {}),
+    ("panels2-ab2", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PANELS": "2"}, {}),
+    ("panels3-ab2", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PANELS": "3"}, {}),
+    ("deferred", "*", {"CM_B200_PIPELINE": "0"}, {"deferred": 1}),
+    ("background", "*", {"CM_B200_PIPELINE": "0"}, {"deferred": 2}),
+    ("background-ab1", "*", {"CM_B200_PIPELINE": "0", "CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {"deferred": 2}),
+    ("background-ab3", "*", {"CM_B200_PIPELINE": "0", "CM_B200_PIPELINE_APPLY_BLOCKS": "3"}, {"deferred": 2}),
+    ("tile", "*", {}, {"apply_kernel": 2}),
+    ("red", "*", {}, {"apply_kernel": 1}),
+    ("nccl", "*", {"CM_B200_EXCHANGE": "nccl"}, {}),
+    ("flush-2^27", "K1", {}, {"flush_threshold": 1 << 27, "n1_only": True}),
     ("flush-2^28", "K1", {}, {"flush_threshold": 1 << 28, "n1_only": True}),
-    ("flush-2^29", "K1", {}, {"flush_threshold": 1 << 29, "n1_only": True}),
-    ("flush-2^30", "K1", {}, {"flush_threshold": 1 << 30, "n1_only": True}),
-    ("flush-2^26-pinned-descs", "K1", {"CM_B200_PINNED_DESCS": "1"}, {"flush_threshold": 1 << 26, "n1_only": True}),
-    ("dma", "K1,K2", {"CM_B200_EXCHANGE": "dma"}, {}),
 ]
 
 
@@ -68,7 +52,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--latency-reps", type=int, default=20)
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="default")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -103,7 +87,7 @@ def main():
         for name, wls, env, opt in VARIANTS:
             if (wls != "*" and wl not in wls.split(",")) or (only and name not in only):
                 continue
-            if nranks == 1 and (any(k not in ("CM_B200_SEG_APPLY", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE") for k in env) or opt.get("deferred")):
+            if nranks == 1 and (env or opt.get("deferred")):
                 continue  # those knobs concern the exchange
             if opt.get("n1_only") and nranks > 1:
                 continue  # the flush threshold only bounds single-rank flushes

@@ -25,8 +25,7 @@ cm.LIB_PATH = os.environ.get("CM_EMU_LIB", os.path.join(HERE, "libcm_b200_emu.so
 from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,  # noqa: E402
                       sorted_unique)
 
-ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_FLAG_BARRIER", "CM_B200_DEVICE_LAYOUT",
-            "CM_B200_PACK_COLS", "CM_B200_SEG_APPLY", "CM_B200_PACK_THREADS", "CM_B200_BG_MIN_ELEMS", "CM_B200_PINNED_DESCS", "CM_B200_PROFILE", "CM_B200_PACK_BULK")
+ENV_KEYS = ("CM_B200_PIPELINE", "CM_B200_PIPELINE_MIN_ELEMS", "CM_B200_PANELS", "CM_B200_BG_MIN_ELEMS")
 
 
 def index_set(rng, hi, k, style):
@@ -90,7 +89,7 @@ def make_scenario(rng):
         if rng.random() < 0.15:
             steps.append(("reset",))
     knobs = dict(apply_kernel=int(rng.choice([0, 1, 2])), sorted_sweep=bool(rng.random() < 0.8),
-                 deterministic=bool(rng.random() < 0.25), exchange_mode=int(rng.choice([0, 1, 2, 3])))
+                 deterministic=bool(rng.random() < 0.25), exchange_mode=int(rng.choice([0, 1, 2])))
     if cfg.P > 1 and knobs["exchange_mode"] != 1 and rng.random() < 0.35:  # deferred scatter-add (peer-to-peer modes)
         knobs["apply_policy"] = int(rng.choice([1, 2]))
         knobs["defer_budget"] = int(rng.choice([0, 1, 20000, 400000]))
@@ -101,21 +100,12 @@ def make_scenario(rng):
     env = {}
     if cfg.P > 1 and rng.random() < 0.6:
         env = {"CM_B200_PIPELINE": str(int(rng.random() < 0.8)), "CM_B200_PIPELINE_MIN_ELEMS": str(int(rng.choice([1, 2000, 50000]))),
-               "CM_B200_PANELS": str(int(rng.integers(1, 5))), "CM_B200_FLAG_BARRIER": str(int(rng.choice([0, 2]))),
-               "CM_B200_DEVICE_LAYOUT": str(int(rng.random() < 0.5)), "CM_B200_PACK_COLS": str(int(rng.choice([4, 8])))}
+               "CM_B200_PANELS": str(int(rng.integers(1, 5)))}
     # stream comparison is defined for slice-only scenarios with panel-monotone index sets: elemental
     # updates travel in a lane of their own here (the reference interleaves them in the same bin) and
     # the symmetric update / fill_lower are masked on the owner
     if knobs.get("apply_policy") == 2:
         env = dict(env, CM_B200_BG_MIN_ELEMS=str(int(rng.choice([1, 5000]))))
-    if rng.random() < 0.3:
-        env = dict(env, CM_B200_PINNED_DESCS="1")
-    if rng.random() < 0.3:
-        env = dict(env, CM_B200_PACK_BULK="1")
-    if rng.random() < 0.4:
-        env = dict(env, CM_B200_SEG_APPLY="1")
-    if rng.random() < 0.3:
-        env = dict(env, CM_B200_PACK_THREADS=str(int(rng.choice([0, 32, 96, 256]))))
     # (any index style, panels or not: an update whose columns are not panel-monotone stays in panel 0)
     wire = all(s[0] in ("slice", "commit", "reset") for s in steps) and rng.random() < 0.8
     return cfg, steps, knobs, env, wire

@@ -38,7 +38,7 @@ CASES = [
                                           [(1, 1, 2048, 2048, 2048), (2, 2, 2000, 1000, 1024), (1, 1, 20000, 300, 20000)]]),
     (T, "test_single_rank_threshold_flush_and_unsorted_sweep", [()]),
     (T, "test_k0_grid_2x2_slices", [(cm.F64,), (cm.F32,), (cm.I32,)]),
-    (T, "test_both_exchange_modes", [(1,), (2,), (3,)]),
+    (T, "test_both_exchange_modes", [(1,), (2,)]),
     (T, "test_nonsquare_grids_wire_bit_exact", [((2, 3, 4, 8, 64, 100, 190),), ((3, 2, 8, 4, 96, 250, 150),),
                                                 ((2, 4, 64, 64, 1024, 2000, 3000),), ((1, 2, 64, 64, 1024, 1000, 2000),),
                                                 ((2, 1, 64, 64, 1024, 2000, 1000),)]),
@@ -53,9 +53,6 @@ CASES = [
     (T, "test_empty_ragged_and_lopsided_inputs", [()]),
     (T, "test_contract_violations_fail_loudly", [()]),
     (T, "test_save_load_reference_file_format", [(1, None), (4, None)]),
-    (V, "test_flag_barrier_is_refused_between_rank_threads", [()]),
-    (V, "test_segment_wise_scatter_add", [()]),
-    (V, "test_pack_with_bulk_stores", [()]),
 ] + [(E, name, params) for name, params in E.CASES]
 
 NAMES = [name for _, name, _ in CASES]

@@ -62,7 +62,7 @@ def test_k0_grid_2x2_slices(dtype):
     assert_blocks_match(cfg, run_cuda(cfg, steps), run_checker(cfg, steps))
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2])
 def test_both_exchange_modes(mode):
     """1 = all-to-all-v through the transport from a send arena, 2 = pack kernel stores straight into
     the owners' receive arenas (peer-to-peer), 3 = copy-engine pushes; same messages, same result"""
@@ -78,14 +78,11 @@ def test_both_exchange_modes(mode):
     assert all(st["bytes_sent"] > 0 for st in got["stats"])
 
 
-@pytest.mark.parametrize("mode", [2, 3])
-def test_pipelined_commit_chunks(mode):
+def test_pipelined_commit_chunks():
     """a commit big enough to be cut into column panels and pipelined (scatter-add of panel k on the
-    apply stream while panel k+1 is packed / pushed): > 32 Mi elements staged per rank.
-    Mode 3 (copy engines) pipelines by default, mode 2 (peer stores) only with CM_B200_PIPELINE=1."""
+    apply stream while panel k+1 is packed across the exchange): > 32 Mi elements staged per rank"""
     import torch
-    if mode == 2:
-        os.environ["CM_B200_PIPELINE"] = "1"  # opt-in path (read at cm_create)
+    mode = 2
     cfg = Cfg(cm.F32, 1024, 1024, 2, 2, 64, 64, 512)
     world = cm.LoopbackWorld(4, 0)
     try:
@@ -126,7 +123,6 @@ def test_pipelined_commit_chunks(mode):
         assert all(st["apply_launches"] == 4 for _, st in out2), [st["apply_launches"] for _, st in out2]
         world.run(lambda r: mats[r].destroy())
     finally:
-        os.environ.pop("CM_B200_PIPELINE", None)
         world.close()
 
 
@@ -334,30 +330,6 @@ def test_full_size_properties_k1():
         M.destroy()
     finally:
         cm.finalize()
-
-
-@pytest.mark.parametrize("env", [{"CM_B200_TILE_TMA": "2"}, {"CM_B200_TILE_VARIANT": "1"}])
-def test_opt_in_tile_kernel_variants(env):
-    """the TMA-ring and the 12-item/2-blocks variants of the column-tile kernel are selected by
-    environment variables read once per process, so they run in a child process"""
-    import subprocess
-    import sys
-    code = (
-        "import sys, numpy as np\n"
-        "sys.path.insert(0, 'tests')\n"
-        "import cm_b200 as cm\n"
-        "from scenario import Cfg, assert_blocks_match, run_checker, run_cuda, slice_steps\n"
-        "for dtype, m in [(cm.F64, 2048), (cm.F32, 1000), (cm.F64, 20000)]:\n"
-        "    cfg = Cfg(dtype, m, 512, 1, 1, 64, 64, m)\n"
-        "    steps = slice_steps(cfg, np.random.default_rng(4), 12, min(m, 600) // 4 * 4, 100, commit_every=6)\n"
-        "    got = run_cuda(cfg, steps, apply_kernel=2)\n"
-        "    assert got['stats'][0]['tile_launches'] > 0\n"
-        "    assert_blocks_match(cfg, got, run_checker(cfg, steps))\n"
-        "print('VARIANT_OK')\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
-                       timeout=600)
-    assert p.returncode == 0 and "VARIANT_OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
 
 
 def test_empty_ragged_and_lopsided_inputs():

@@ -32,18 +32,13 @@ GROUPS = [
     "test_empty_ragged_and_lopsided_inputs",
     "test_contract_violations_fail_loudly",
     "test_save_load_reference_file_format",
-    "test_flag_barrier_is_refused_between_rank_threads",
-    "test_segment_wise_scatter_add",
-    "test_pack_with_bulk_stores",
     "device_api_single_rank",
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
     "panels_unsorted_masked_and_mixed_sources",
-    "flag_barrier_commits",
     "deferred_apply",
     "deferred_apply_api",
     "two_matrices_and_batch_api",
-    "device_layout_speculative_pack",
     "deterministic_mode_under_variants",
     "k1_full_size_properties",
     "bench_step_helpers",
