@@ -66,9 +66,9 @@ def workload_spec(name, nranks):
                     m_u=512, n_u=512, U=1024, commit_every=256, skew=True)
     if name == "NS":  # BASELINE.json north_star target: N=65536, uniform random 512x512 updates
         return dict(name=f"NS (north-star target): N=65536 f64 MB=NB=64 grid {nprow}x{npcol}, 1024 updates/rank of 512x512, "
-                         f"sorted unique random index sets, commit every 256",
+                         f"sorted unique random index sets, one commit (assemble, then commit: the reference's own usage)",
                     dtype=0, m=65536, n=65536, nprow=nprow, npcol=npcol, mb=64, nb=64, lld=65536 // nprow,
-                    m_u=512, n_u=512, U=1024, commit_every=256)
+                    m_u=512, n_u=512, U=1024, commit_every=0)
     if name == "K4":  # BASELINE.json configs[4]: tiny updates, many commits
         nprow, npcol = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
         return dict(name=f"K4: N=32768 f32 MB=NB=64 grid {nprow}x{npcol}, 125000 updates/rank of 32x32, commit every 1024",
@@ -86,6 +86,10 @@ def workload_spec(name, nranks):
         return dict(name="NSown: the scatter-add of one NS owner (block 32768x16384 f64, 256x128 segments, 2048 per commit)",
                     dtype=0, m=32768, n=16384, nprow=1, npcol=1, mb=64, nb=64, lld=32768, m_u=256, n_u=128, U=8192,
                     commit_every=2048)
+    if name == "NSown1" and nranks == 1:
+        return dict(name="NSown1: the scatter-add of one NS owner when the step is ONE commit (block 32768x16384 f64, 8192 segments of 256x128)",
+                    dtype=0, m=32768, n=16384, nprow=1, npcol=1, mb=64, nb=64, lld=32768, m_u=256, n_u=128, U=8192,
+                    commit_every=0)
     if name == "K4own" and nranks == 1:
         return dict(name="K4own: the scatter-add of one K4 owner (block 8192x16384 f32, 8x16 segments, 8192 per commit)",
                     dtype=1, m=8192, n=16384, nprow=1, npcol=1, mb=64, nb=64, lld=8192, m_u=8, n_u=16, U=1 << 20,
@@ -802,7 +806,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="K1", choices=["K1", "K2", "K3", "K4", "NS", "K2own", "NSown", "K4own"])
+    ap.add_argument("--workload", default="K1", choices=["K1", "K2", "K3", "K4", "NS", "K2own", "NSown", "NSown1", "K4own"])
     ap.add_argument("--configs", default="auto",
                     help="other workloads measured in the same invocation and reported under `configs`: "
                          "auto (K2,K3,K4,NS at --gpus 8), none, or a comma-separated list")

@@ -351,6 +351,8 @@ struct cm_matrix {
     double host_us;
   };
   int trace_left = 0;
+  long trace_skip = 0;  // CM_B200_TRACE_SKIP: commits to let pass first (warm-up, arena growth)
+  long commit_seq = 0;
   std::vector<TraceMark> marks;
 
   // wire capture (parity tests)
@@ -388,7 +390,7 @@ double host_now_us() {
 
 // timeline mark: an event on `st` now, plus the host clock
 void trace_mark(cm_matrix *M, const char *name, cudaStream_t st = nullptr) {
-  if (M->trace_left <= 0) return;
+  if (M->trace_left <= 0 || M->commit_seq < M->trace_skip) return;
   cudaEvent_t e = get_event(M);
   cudaEventRecord(e, st ? st : M->stream);
   M->marks.push_back(cm_matrix::TraceMark{name, e, host_now_us()});
@@ -405,7 +407,7 @@ void trace_dump(cm_matrix *M, bool end_of_commit) {
       cudaGetLastError();
       ms = -1;
     }
-    fprintf(stderr, "[cm trace r%d c%ld] %-28s gpu %9.3f us   host %9.3f us\n", M->me, M->stats.commits, mk.name, ms * 1e3,
+    fprintf(stderr, "[cm trace r%d c%ld] %-28s gpu %9.3f us   host %9.3f us\n", M->me, M->commit_seq, mk.name, ms * 1e3,
             mk.host_us - base.host_us);
     M->event_pool.push_back(mk.ev);
   }
@@ -684,6 +686,11 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
   for (int d = 0; d < P; ++d)
     if (need_vals[d] > M->cap_vals[d] || need_meta[d] > M->cap_meta[d]) grow[d] = 1, any = true;
   if (!any) return CM_OK;
+  if (getenv("CM_B200_TRACE") && me == 0)
+    for (int d = 0; d < P; ++d)
+      if (grow[d])
+        fprintf(stderr, "[cm trace r0 c%ld] arena of owner %d grows: values %zu -> %zu bytes, metadata %zu -> %zu\n", M->commit_seq, d,
+                M->cap_vals[d], need_vals[d], M->cap_meta[d], need_meta[d]);
   // 1. nobody keeps a mapping of an arena that is about to be freed
   for (int d = 0; d < P; ++d)
     if (grow[d] && d != me && M->peer_arena_open[d]) {
@@ -987,8 +994,22 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
     bool grow = false;
     for (int d = 0; d < P; ++d) grow = grow || need_vals[d] > M->cap_vals[d] || need_meta[d] > M->cap_meta[d];
     if (grow) {
+      // the new arenas hold what the log WOULD have needed, not just this commit: otherwise a log that is
+      // truncated at every growth never reaches the size a step needs and keeps growing a little each time
+      const std::vector<size_t> log_vals = need_vals, log_meta = need_meta;
       CM_TRY(materialize_all(M));
       lay_out();
+      // ... and twice that, for every owner at once: a growth costs a collective reallocation and re-mapping of
+      // gigabytes (hundreds of milliseconds); the log of a step must fit after a couple of them
+      size_t top_v = 0, top_m = 0;
+      for (int d = 0; d < P; ++d) {
+        top_v = std::max(top_v, log_vals[d]);
+        top_m = std::max(top_m, log_meta[d]);
+      }
+      for (int d = 0; d < P; ++d) {
+        need_vals[d] = std::max(need_vals[d], 2 * top_v);
+        need_meta[d] = std::max(need_meta[d], 2 * top_m);
+      }
     }
   }
   CM_TRY(ensure_recv_arenas(M, need_vals, need_meta));
@@ -1290,6 +1311,7 @@ int do_commit(cm_matrix *M) {
     rc = commit_exchange(M);
   }
   if (rc == CM_OK) M->stats.commits += 1;
+  M->commit_seq += 1;
   return rc;
 }
 
@@ -1576,7 +1598,8 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
       if (!strcmp(pol, "background")) M->apply_policy = CM_APPLY_BACKGROUND;
     }
     if (getenv("CM_B200_BG_MIN_ELEMS")) M->bg_min_elems = atol(getenv("CM_B200_BG_MIN_ELEMS"));
-    if (getenv("CM_B200_TRACE") && M->me == 0) M->trace_left = atoi(getenv("CM_B200_TRACE"));
+    if (getenv("CM_B200_TRACE") && (M->me == 0 || getenv("CM_B200_TRACE_ALL"))) M->trace_left = atoi(getenv("CM_B200_TRACE"));
+    if (getenv("CM_B200_TRACE_SKIP")) M->trace_skip = atol(getenv("CM_B200_TRACE_SKIP"));
   }
   int rc = ctx->tp->barrier(M->stream);
   if (rc != CM_OK) return rc;
