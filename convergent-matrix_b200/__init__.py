@@ -34,7 +34,8 @@ class Stats(C.Structure):
                                         "commits", "kernel_launches", "bytes_sent", "bytes_received",
                                         "h2d_bytes", "d2h_bytes")] + \
                [("apply_ms", C.c_double), ("pack_ms", C.c_double), ("exchange_ms", C.c_double),
-                ("apply_launches", C.c_long), ("apply_elements", C.c_long), ("tile_launches", C.c_long)]
+                ("apply_launches", C.c_long), ("apply_elements", C.c_long), ("tile_launches", C.c_long),
+                ("flushed_shipped", C.c_long), ("flushed_held", C.c_long), ("staging_peak_bytes", C.c_long)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -99,6 +100,7 @@ SYMBOLS = {
     "cm_set_profiling": (_i, [_vp, _i]),
     "cm_stream": (_i, [_vp, C.POINTER(_vp)]),
     "cm_debug_keep_wire": (_i, [_vp, _i]),
+    "cm_debug_set_staging_limit": (_i, [_vp, _l]),
     "cm_debug_wire_count": (_i, [_vp, _i, _lp]),
     "cm_debug_wire_expand": (_i, [_vp, _i, _vp, _vp]),
     "cm_numroc": (_l, [_l, _l, _l, _l]),
@@ -358,6 +360,9 @@ class Matrix:
     # parity hooks --------------------------------------------------------------------
     def keep_wire(self, on=True):
         _check(self.L.cm_debug_keep_wire(self.h, int(on)))
+
+    def set_staging_limit(self, max_updates):
+        _check(self.L.cm_debug_set_staging_limit(self.h, int(max_updates)))
 
     def wire(self, dst):
         n = _l()

@@ -116,6 +116,8 @@ struct MsgCounts {
   long nidx, nseg, nitems;
   long nelems;  // update elements carried (what the scatter-add will add)
   long ncoo;    // elemental updates (COO lane) from this source to this owner; panel 0 only
+  long nflushed;  // messages this source's threshold flushes packed for this owner since the last commit
+                  // (reference flush(thresh) inside update(), :346, :614); panel 0 only
 };
 
 // Layout of one segment's values inside a message: column-major nr x nc with column stride

@@ -178,14 +178,14 @@ struct Long3 {
 };
 
 __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom g, MapArenas ma, ScanArenas sa,
-                                                   const long *__restrict__ coo_counts) {
+                                                   const long *__restrict__ coo_counts) {  // [2P]: ncoo, nflushed per owner
   using BlockScan = cub::BlockScan<Long3, 256>;
   __shared__ typename BlockScan::TempStorage tmp;
   const int dst = blockIdx.x;
   const int panel = blockIdx.y;
   const int P = gridDim.x;
   if (panel >= pp.npanel) {  // unused panel slot: an empty message
-    if (threadIdx.x == 0) sa.totals[panel * P + dst] = MsgCounts{0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) sa.totals[panel * P + dst] = MsgCounts{0, 0, 0, 0, 0, 0, 0};
     return;
   }
   const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom 
   // a message without values ships nothing at all (no segment table either): nseg = 0
   if (threadIdx.x == 0)
     sa.totals[panel * P + dst] = MsgCounts{running.a, running.b, running.a ? (long)nupd : 0, running.c, running.e,
-                                           panel == 0 ? coo_counts[dst] : 0};
+                                           panel == 0 ? coo_counts[dst] : 0, panel == 0 ? coo_counts[P + dst] : 0};
 }
 
 void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,

@@ -53,6 +53,19 @@ struct DevBuf {
     cap = want;
     return CM_OK;
   }
+  // exactly `bytes` (message buffers of threshold flushes: no growth margin)
+  int alloc_exact(size_t bytes) {
+    release();
+    bytes = std::max(bytes, (size_t)256);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return fail(CM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = bytes;
+    return CM_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -244,6 +257,22 @@ struct PendingTimer {
   long elements;
 };
 
+// One message packed by a threshold flush with several ranks (the XBuff of a Bin::flush inside update(),
+// reference :220-245, :346, :614), waiting for the next commit. `remote`: the pack kernel stored it straight
+// into the owner's flush region of this source over NVLink (the reference's rput, :168-171); otherwise it sits
+// in buffers of the source and is delivered by the commit. Exchanged between the ranks at commit as plain bytes.
+struct FlushDesc {
+  int src, dst;
+  int remote;
+  int seq;            // order among this source's flushed messages
+  long off_v, off_m;  // remote: byte offsets inside the (owner, source) flush region
+  MsgCounts c;
+};
+struct FlushedMsg {
+  FlushDesc d;
+  DevBuf vals, meta;  // !remote
+};
+
 }  // namespace cmb
 
 using namespace cmb;
@@ -317,6 +346,16 @@ struct cm_matrix {
   MirrorArena index_arena{4ull << 20};
   std::vector<CooBin> coo;  // [owner]
   long coo_total = 0;
+  // threshold flushes with several ranks (flush_shipped): messages already packed since the last commit
+  std::vector<FlushedMsg> flushed;
+  // flush regions: every owner holds one region per source (flush_region_v / _m bytes each, the same on all
+  // ranks), mapped by every rank; a source fills its region at an owner front to back between two commits
+  DevBuf d_flush_vals, d_flush_meta;
+  std::vector<void *> peer_flush_vals, peer_flush_meta;  // [owner] base of that owner's regions
+  std::vector<bool> peer_flush_open;
+  size_t flush_region_v = 0, flush_region_m = 0;
+  std::vector<size_t> flush_used_v, flush_used_m;  // [owner] bytes this rank has used of its region there
+  long max_staged_updates = (1L << kItemSegBits) - 1;  // segments one scatter-add can address (cm_debug_set_staging_limit)
 
   // fill_lower scratch (global indices of local columns / rows)
   DevBuf d_fill_ix, d_fill_jx;
@@ -358,6 +397,7 @@ struct cm_matrix {
   // wire capture (parity tests)
   struct DbgMsg {
     int dst;
+    int group;  // threshold flushes before the commit: 0, 1, ... in order; the commit's own messages come last
     std::vector<char> meta, vals;
   };
   std::vector<DbgMsg> dbg_msgs;  // the messages of the last commit, owner-major, panel order
@@ -472,7 +512,7 @@ int ceil_log2(long v) {
   return b;
 }
 
-void clear_staged(cm_matrix *M) {
+void clear_staged(cm_matrix *M, bool keep_coo = false) {
   M->descs.clear();
   M->item_base.clear();
   M->staged_elems = M->staged_rows = M->staged_cols = M->staged_items = 0;
@@ -480,6 +520,7 @@ void clear_staged(cm_matrix *M) {
   M->reads_local_block = false;
   M->payload_arena.reset();
   M->index_arena.reset();
+  if (keep_coo) return;  // a threshold flush with several ranks: elemental updates stay in their host bins
   for (auto &b : M->coo) {
     b.inds.clear();
     b.vals.clear();
@@ -737,8 +778,6 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
 // owner side: messages -> Seg table + (key, item) pairs -> sort -> scatter-add
 int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long item_total, long elem_total, long max_seg,
                    ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
-  if (seg_total >= (1L << kItemSegBits))
-    return fail(CM_ERR_INVALID, "too many segments in one scatter-add (%ld); commit / materialise more often", seg_total);
   if (msgs.empty()) return CM_OK;
   CM_TRY(w.msgs.ensure(sizeof(MsgRef) * msgs.size()));
   CM_CUDA_TRY(cudaMemcpyAsync(w.msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, st));
@@ -753,6 +792,34 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
   return CM_OK;
 }
 
+// a list of delivered messages, in order, as ONE scatter-add on stream `st` — or several, when the list holds more
+// segments than one scatter-add can address (many threshold flushes between two commits)
+int apply_list(cm_matrix *M, const cm_matrix::PendMsg *first, const cm_matrix::PendMsg *last, ApplyWork &w, cudaStream_t st,
+               int max_blocks_per_sm) {
+  std::vector<MsgRef> msgs;
+  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+  for (const cm_matrix::PendMsg *pm = first; pm != last; ++pm) {
+    if (pm->nseg > M->max_staged_updates)
+      return fail(CM_ERR_INVALID, "a message holds %ld segments; the limit per scatter-add is %ld", pm->nseg, M->max_staged_updates);
+    if (seg_total + pm->nseg > M->max_staged_updates) {
+      CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm));
+      msgs.clear();
+      seg_total = item_total = elem_total = max_seg = 0;
+    }
+    MsgRef m;
+    m.meta = pm->meta;
+    m.vals = pm->vals;
+    m.seg_base = seg_total;
+    m.item_base = item_total;
+    seg_total += pm->nseg;
+    item_total += pm->nitems;
+    elem_total += pm->nelems;
+    max_seg = std::max(max_seg, pm->nseg);
+    msgs.push_back(m);
+  }
+  return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
+}
+
 // a background scatter-add (apply stream) must have finished before anything else touches the local
 // block or the work buffers it uses
 int wait_background(cm_matrix *M) {
@@ -764,22 +831,7 @@ int wait_background(cm_matrix *M) {
 
 // the un-applied part of my log as one scatter-add on stream `st`
 int apply_log(cm_matrix *M, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
-  std::vector<MsgRef> msgs;
-  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
-  for (size_t i = M->pend_applied; i < M->pend.size(); ++i) {
-    const cm_matrix::PendMsg &pm = M->pend[i];
-    MsgRef m;
-    m.meta = pm.meta;
-    m.vals = pm.vals;
-    m.seg_base = seg_total;
-    m.item_base = item_total;
-    seg_total += pm.nseg;
-    item_total += pm.nitems;
-    elem_total += pm.nelems;
-    max_seg = std::max(max_seg, pm.nseg);
-    msgs.push_back(m);
-  }
-  CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm));
+  CM_TRY(apply_list(M, M->pend.data() + M->pend_applied, M->pend.data() + M->pend.size(), w, st, max_blocks_per_sm));
   M->pend_applied = M->pend.size();
   M->mirror_valid = false;
   return CM_OK;
@@ -876,6 +928,11 @@ struct CommitPlan {
   std::vector<void *> dst_ptrs;        // host copy of sa.dst_vals / sa.dst_meta
   std::vector<long> r_coo_base, s_coo_base;
   cudaEvent_t ev_pack0 = nullptr, ev_pack1 = nullptr;
+  // messages packed by threshold flushes since the last commit, of EVERY rank (source-major, in flush order)
+  std::vector<FlushDesc> fl;
+  std::vector<long> fl_pos_v, fl_pos_m;  // !remote: where the message goes in its owner's receive arena (elements / bytes)
+  std::vector<long> end_v, end_m;        // [owner] end of everything this commit puts into that owner's receive arenas
+  int fl_lanes = 0;                      // without peer-to-peer stores: transport lanes that carry them (2 per message of a pair)
 
   size_t cidx(int src, int k, int dst) const { return ((size_t)src * K + k) * P + dst; }
   size_t ridx(int d, int k, int src) const { return (size_t)d * (K * P + 1) + (size_t)k * P + src; }
@@ -888,6 +945,39 @@ struct CommitPlan {
   }
 };
 
+// owner map + grouping + per-(panel, owner) sizes of the staged updates, on the main stream
+int map_and_scan(cm_matrix *M, const PanelPlan &pp, int nupd, MapArenas &ma, ScanArenas &sa) {
+  const int P = M->P, K = kMaxChunks;
+  CM_TRY(upload_staged(M, pp.npanel));
+  const size_t pu = (size_t)pp.npanel * P * std::max(nupd, 1);
+  CM_TRY(M->d_valoff.ensure(8 * pu));
+  CM_TRY(M->d_idxoff.ensure(8 * pu));
+  CM_TRY(M->d_itemoff.ensure(8 * pu));
+  CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P * K));
+  CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P * K));
+  ma = map_arenas(M);
+  sa.valoff = M->d_valoff.as<long>();
+  sa.idxoff = M->d_idxoff.as<long>();
+  sa.itemoff = M->d_itemoff.as<long>();
+  sa.totals = M->d_totals.as<MsgCounts>();
+  sa.dst_vals = M->d_dst_ptrs.as<void *>();
+  sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
+  // host-known per-owner counts ride in the same totals (one tiny H2D): elemental updates and the
+  // messages threshold flushes have packed since the last commit
+  std::vector<long> extra(2 * (size_t)P, 0);
+  for (int d = 0; d < P; ++d) extra[d] = (long)M->coo[d].inds.size();
+  for (const FlushedMsg &f : M->flushed) extra[(size_t)P + f.d.dst] += 1;
+  CM_TRY(M->d_coo_counts.ensure(16 * (size_t)P));
+  CM_CUDA_TRY(cudaMemcpyAsync(M->d_coo_counts.p, extra.data(), 16 * (size_t)P, cudaMemcpyHostToDevice, M->stream));
+  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, pp, ma, M->stream);
+  launch_scan(nupd, pp, M->g, ma, sa, M->d_coo_counts.as<long>(), M->stream);
+  M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
+  CM_CUDA_TRY(cudaGetLastError());
+  return CM_OK;
+}
+
+long pad32(long nvals) { return (nvals + 31) & ~31L; }  // every message starts on a 256-byte boundary
+
 // -- source side: owner map + per-(panel, owner) sizes; counts all-gathered and read back ----------
 int commit_counts(cm_matrix *M, CommitPlan &cp) {
   const int P = cp.P, K = cp.K, nupd = cp.nupd;
@@ -896,34 +986,12 @@ int commit_counts(cm_matrix *M, CommitPlan &cp) {
   // a large commit cuts its updates' columns into panels so that the owners can pipeline it
   cp.pp = plan_panels(M);
   for (const UpdDesc &d : M->descs) cp.max_rows = std::max<long>(cp.max_rows, d.m);
-  CM_TRY(upload_staged(M, cp.pp.npanel));
-  const size_t pu = (size_t)cp.pp.npanel * P * std::max(nupd, 1);
-  CM_TRY(M->d_valoff.ensure(8 * pu));
-  CM_TRY(M->d_idxoff.ensure(8 * pu));
-  CM_TRY(M->d_itemoff.ensure(8 * pu));
-  CM_TRY(M->d_totals.ensure(sizeof(MsgCounts) * (size_t)P * K));
-  CM_TRY(M->d_dst_ptrs.ensure(2 * sizeof(void *) * (size_t)P * K));
-  cp.ma = map_arenas(M);
-  cp.sa.valoff = M->d_valoff.as<long>();
-  cp.sa.idxoff = M->d_idxoff.as<long>();
-  cp.sa.itemoff = M->d_itemoff.as<long>();
-  cp.sa.totals = M->d_totals.as<MsgCounts>();
-  cp.sa.dst_vals = M->d_dst_ptrs.as<void *>();
-  cp.sa.dst_meta = reinterpret_cast<char **>(M->d_dst_ptrs.as<void *>() + (size_t)P * K);
   if (M->profiling) {
     cp.ev_pack0 = get_event(M);
     cp.ev_pack1 = get_event(M);
     cudaEventRecord(cp.ev_pack0, M->stream);
   }
-  // elemental-update counts ride in the same totals (host-known; one tiny H2D)
-  std::vector<long> my_coo(P);
-  for (int d = 0; d < P; ++d) my_coo[d] = (long)M->coo[d].inds.size();
-  CM_TRY(M->d_coo_counts.ensure(8 * (size_t)P));
-  CM_CUDA_TRY(cudaMemcpyAsync(M->d_coo_counts.p, my_coo.data(), 8 * (size_t)P, cudaMemcpyHostToDevice, M->stream));
-  launch_map_group(M->d_descs.as<UpdDesc>(), nupd, M->g, cp.pp, cp.ma, M->stream);
-  launch_scan(nupd, cp.pp, M->g, cp.ma, cp.sa, M->d_coo_counts.as<long>(), M->stream);
-  M->stats.kernel_launches += (nupd ? 1 : 0) + 1;
-  CM_CUDA_TRY(cudaGetLastError());
+  CM_TRY(map_and_scan(M, cp.pp, nupd, cp.ma, cp.sa));
   trace_mark(M, "counts: mapped + scanned");
 
   const size_t per_rank = sizeof(MsgCounts) * (size_t)P * K;
@@ -939,8 +1007,24 @@ int commit_counts(cm_matrix *M, CommitPlan &cp) {
   for (int src = 0; src < P; ++src)
     for (int d = 0; d < P; ++d) cp.coo_counts[(size_t)src * P + d] = cp.counts[cp.cidx(src, 0, d)].ncoo;
   bool any = false;
-  for (size_t i = 0; i < (size_t)P * K * P && !any; ++i) any = cp.counts[i].nvals != 0 || cp.counts[i].ncoo != 0;
+  for (size_t i = 0; i < (size_t)P * K * P && !any; ++i)
+    any = cp.counts[i].nvals != 0 || cp.counts[i].ncoo != 0 || cp.counts[i].nflushed != 0;
   cp.empty = !any;
+  // messages of threshold flushes (rare): everybody learns every message's owner, size and place
+  long nmax = 0;
+  for (int src = 0; src < P; ++src) {
+    long n = 0;
+    for (int d = 0; d < P; ++d) n += cp.counts[cp.cidx(src, 0, d)].nflushed;
+    nmax = std::max(nmax, n);
+  }
+  if (nmax > 0) {
+    std::vector<FlushDesc> mine((size_t)nmax), all((size_t)nmax * P);
+    for (auto &f : mine) f.src = -1;
+    for (size_t i = 0; i < M->flushed.size(); ++i) mine[i] = M->flushed[i].d;
+    CM_TRY(tp->host_allgather(mine.data(), all.data(), sizeof(FlushDesc) * (size_t)nmax, M->stream));
+    for (const FlushDesc &f : all)
+      if (f.src >= 0) cp.fl.push_back(f);
+  }
   return CM_OK;
 }
 
@@ -963,6 +1047,7 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
         }
     cp.pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total;
   }
+  if (!cp.fl.empty()) cp.pipelined = false;  // flushed messages are applied with the commit's own, as one batch
   for (int src = 0; src < P; ++src)
     for (int k = 0; k < K; ++k)
       for (int d = 0; d < P; ++d)
@@ -971,6 +1056,10 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
   // layout of every rank's receive arenas: owner d holds, panel after panel, the messages of every source
   cp.rbase_v.assign((size_t)P * (K * P + 1), 0);
   cp.rbase_m.assign((size_t)P * (K * P + 1), 0);
+  cp.fl_pos_v.assign(cp.fl.size(), 0);
+  cp.fl_pos_m.assign(cp.fl.size(), 0);
+  cp.end_v.assign(P, 0);
+  cp.end_m.assign(P, 0);
   std::vector<size_t> need_vals(P), need_meta(P);
   auto lay_out = [&]() {  // eager: from the start of the arenas; deferred: behind what is logged there
     for (int d = 0; d < P; ++d) {
@@ -983,8 +1072,20 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
           cp.rbase_v[i + 1] = cp.rbase_v[i] + ((c.nvals + 31) & ~31L);  // every message on a 256-byte boundary
           cp.rbase_m[i + 1] = cp.rbase_m[i] + meta_bytes(c.nseg, c.nidx);
         }
-      need_vals[d] = (size_t)cp.rbase_v[cp.ridx(d, K - 1, P - 1) + 1] * esz;
-      need_meta[d] = (size_t)cp.rbase_m[cp.ridx(d, K - 1, P - 1) + 1];
+      // behind them: the flushed messages that still sit at their sources
+      long fv = cp.rbase_v[cp.ridx(d, K - 1, P - 1) + 1], fm = cp.rbase_m[cp.ridx(d, K - 1, P - 1) + 1];
+      for (size_t i = 0; i < cp.fl.size(); ++i) {
+        const FlushDesc &f = cp.fl[i];
+        if (f.dst != d || f.remote) continue;
+        cp.fl_pos_v[i] = fv;
+        cp.fl_pos_m[i] = fm;
+        fv += pad32(f.c.nvals);
+        fm += meta_bytes(f.c.nseg, f.c.nidx);
+      }
+      cp.end_v[d] = fv;
+      cp.end_m[d] = fm;
+      need_vals[d] = (size_t)fv * esz;
+      need_meta[d] = (size_t)fm;
     }
   };
   lay_out();
@@ -1072,29 +1173,53 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
     M->stats.bytes_sent += cp.coo_blob(esz, (long)M->coo[r].inds.size()) * (M->coo[r].inds.empty() ? 0 : 1);
     M->stats.bytes_received += cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me]) * (cp.coo_counts[(size_t)r * P + me] ? 1 : 0);
   }
+  // flushed messages: what went out at flush time (remote) was counted then
+  std::vector<int> per_pair((size_t)P * P, 0);
+  for (const FlushDesc &f : cp.fl) {
+    const long bytes = (long)(f.c.nvals * esz) + meta_bytes(f.c.nseg, f.c.nidx);
+    if (f.src == me && f.dst != me && !f.remote) M->stats.bytes_sent += bytes;
+    if (f.dst == me && f.src != me) M->stats.bytes_received += bytes;
+    if (!f.remote && f.src != f.dst) cp.fl_lanes = std::max(cp.fl_lanes, 2 * ++per_pair[(size_t)f.src * P + f.dst]);
+  }
   return CM_OK;
 }
 
-// owner side of the panels [k0, k1): their messages -> one scatter-add on stream `st`
-int apply_panels(cm_matrix *M, const CommitPlan &cp, int k0, int k1, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
-  std::vector<MsgRef> msgs;
-  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+// where a flushed message for THIS rank sits: in my flush region of its source, or in my receive arena
+cm_matrix::PendMsg flushed_ref(cm_matrix *M, const CommitPlan &cp, size_t i) {
+  const FlushDesc &f = cp.fl[i];
+  const char *meta, *vals;
+  if (f.remote) {
+    meta = M->d_flush_meta.as<char>() + (size_t)f.src * M->flush_region_m + f.off_m;
+    vals = M->d_flush_vals.as<char>() + (size_t)f.src * M->flush_region_v + f.off_v;
+  } else {
+    meta = static_cast<char *>(M->peer_meta[cp.me]) + cp.fl_pos_m[i];
+    vals = static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.fl_pos_v[i] * M->esz;
+  }
+  return cm_matrix::PendMsg{meta, vals, f.c.nseg, f.c.nitems, f.c.nelems};
+}
+
+// what this commit delivered to THIS rank, in stream order per source: the messages of threshold flushes
+// (with_flushed), then the commit's own messages of the panels [k0, k1)
+void delivered_messages(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool with_flushed, std::vector<cm_matrix::PendMsg> &out) {
+  if (with_flushed)
+    for (size_t i = 0; i < cp.fl.size(); ++i)
+      if (cp.fl[i].dst == cp.me) out.push_back(flushed_ref(M, cp, i));
   for (int k = k0; k < k1; ++k)
     for (int src = 0; src < cp.P; ++src) {
       const MsgCounts &c = cp.counts[cp.cidx(src, k, cp.me)];
       if (c.nvals == 0) continue;
-      MsgRef m;
-      m.meta = static_cast<char *>(M->peer_meta[cp.me]) + cp.rbase_m[cp.ridx(cp.me, k, src)];
-      m.vals = static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.rbase_v[cp.ridx(cp.me, k, src)] * M->esz;
-      m.seg_base = seg_total;
-      m.item_base = item_total;
-      seg_total += c.nseg;
-      item_total += c.nitems;
-      elem_total += c.nelems;
-      max_seg = std::max(max_seg, c.nseg);
-      msgs.push_back(m);
+      out.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[cp.me]) + cp.rbase_m[cp.ridx(cp.me, k, src)],
+                                       static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.rbase_v[cp.ridx(cp.me, k, src)] * M->esz,
+                                       c.nseg, c.nitems, c.nelems});
     }
-  return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
+}
+
+// owner side of the panels [k0, k1): their messages -> one scatter-add on stream `st`
+int apply_panels(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool with_flushed, ApplyWork &w, cudaStream_t st,
+                 int max_blocks_per_sm) {
+  std::vector<cm_matrix::PendMsg> msgs;
+  delivered_messages(M, cp, k0, k1, with_flushed, msgs);
+  return apply_list(M, msgs.data(), msgs.data() + msgs.size(), w, st, max_blocks_per_sm);
 }
 
 // exchange lanes of the transport: values + metadata of the panels [k0, k1) without peer-to-peer stores,
@@ -1112,8 +1237,10 @@ int transport_lanes(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool wit
         for (int k = k0; k < k1; ++k)
           if (counts[cp.cidx(src, k, d)].nvals) global_lane = true;
     }
+  const int nfl = (with_coo && !M->p2p) ? cp.fl_lanes : 0;  // flushed messages still at their sources ride along
+  if (nfl) global_lane = true;
   if (!global_lane) return CM_OK;  // peer-to-peer stores without elemental updates: nothing rides on the transport
-  const int nl = 2 * (k1 - k0) + 1;
+  const int nl = 2 * (k1 - k0) + 1 + nfl;
   std::vector<std::vector<XferSpec>> sends(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
   std::vector<std::vector<XferSpec>> recvs(nl, std::vector<XferSpec>(P, XferSpec{nullptr, 0}));
   for (int r = 0; r < P; ++r) {
@@ -1133,9 +1260,27 @@ int transport_lanes(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool wit
       }
     if (with_coo) {
       if (M->coo[r].inds.size())
-        sends[nl - 1][r] = XferSpec{M->d_send_coo.as<char>() + cp.s_coo_base[r], (size_t)cp.coo_blob(esz, (long)M->coo[r].inds.size())};
+        sends[nl - nfl - 1][r] = XferSpec{M->d_send_coo.as<char>() + cp.s_coo_base[r], (size_t)cp.coo_blob(esz, (long)M->coo[r].inds.size())};
       if (cp.coo_counts[(size_t)r * P + me])
-        recvs[nl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + cp.r_coo_base[r], (size_t)cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me])};
+        recvs[nl - nfl - 1][r] = XferSpec{M->d_recv_coo.as<char>() + cp.r_coo_base[r], (size_t)cp.coo_blob(esz, cp.coo_counts[(size_t)r * P + me])};
+    }
+  }
+  if (nfl) {  // the j-th message a pair (source, owner) still holds at the source: lanes 2j (values), 2j + 1 (metadata)
+    std::vector<int> nth((size_t)P * P, 0);
+    const int base = nl - nfl;
+    for (size_t i = 0; i < cp.fl.size(); ++i) {
+      const FlushDesc &f = cp.fl[i];
+      if (f.remote || f.src == f.dst) continue;
+      const int j = nth[(size_t)f.src * P + f.dst]++;
+      const size_t vb = (size_t)f.c.nvals * esz, mb = (size_t)meta_bytes(f.c.nseg, f.c.nidx);
+      if (f.src == me) {
+        const FlushedMsg &fm = M->flushed[f.seq];
+        sends[base + 2 * j][f.dst] = XferSpec{fm.vals.p, vb};
+        sends[base + 2 * j + 1][f.dst] = XferSpec{fm.meta.p, mb};
+      } else if (f.dst == me) {
+        recvs[base + 2 * j][f.src] = XferSpec{static_cast<char *>(M->peer_vals[me]) + (size_t)cp.fl_pos_v[i] * esz, vb};
+        recvs[base + 2 * j + 1][f.src] = XferSpec{static_cast<char *>(M->peer_meta[me]) + cp.fl_pos_m[i], mb};
+      }
     }
   }
   ScopedTimer t(M, 2, 0);
@@ -1155,6 +1300,16 @@ int commit_deliver(cm_matrix *M, CommitPlan &cp) {
     }
     CM_CUDA_TRY(cudaGetLastError());
     trace_mark(M, "deliver: packed");
+    // flushed messages that still sit here: into their owners' arenas (peer copies), or over the transport below
+    for (size_t i = 0; i < cp.fl.size(); ++i) {
+      const FlushDesc &f = cp.fl[i];
+      if (f.src != cp.me || f.remote || !(M->p2p || f.dst == cp.me)) continue;
+      const FlushedMsg &fm = M->flushed[f.seq];
+      CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_vals[f.dst]) + (size_t)cp.fl_pos_v[i] * M->esz, fm.vals.p,
+                                  (size_t)f.c.nvals * M->esz, cudaMemcpyDefault, M->stream));
+      CM_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(M->peer_meta[f.dst]) + cp.fl_pos_m[i], fm.meta.p,
+                                  (size_t)meta_bytes(f.c.nseg, f.c.nidx), cudaMemcpyDefault, M->stream));
+    }
     CM_TRY(transport_lanes(M, cp, 0, K, true));
     // peer-to-peer: every source's pack kernel has finished storing into my arenas
     if (M->p2p && P > 1) CM_TRY(commit_stream_barrier(M, M->stream));
@@ -1179,7 +1334,7 @@ int commit_deliver(cm_matrix *M, CommitPlan &cp) {
     CM_TRY(commit_stream_barrier(M, M->apply_stream));
     trace_mark(M, "deliver: panel landed", M->apply_stream);
     // all but the last panel's scatter-add share the SMs with the next panel's pack kernel
-    CM_TRY(apply_panels(M, cp, k, k + 1, M->work[k], M->apply_stream, k + 1 < cp.Kp ? M->pipeline_apply_blocks : 0));
+    CM_TRY(apply_panels(M, cp, k, k + 1, false, M->work[k], M->apply_stream, k + 1 < cp.Kp ? M->pipeline_apply_blocks : 0));
     trace_mark(M, "deliver: panel applied", M->apply_stream);
   }
   if (M->profiling) {
@@ -1191,15 +1346,33 @@ int commit_deliver(cm_matrix *M, CommitPlan &cp) {
   return CM_OK;
 }
 
-// what THIS rank sent to every owner, panel after panel, read back from wherever pack put it (parity tests)
+// what THIS rank sent to every owner — flushed messages first, then the commit's own, panel after panel —
+// read back from wherever pack put it (parity tests)
 int capture_wire(cm_matrix *M, const CommitPlan &cp) {
   CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
   M->dbg_msgs.clear();
+  int group = 0;
+  for (const FlushedMsg &fm : M->flushed) {
+    const FlushDesc &f = fm.d;
+    cm_matrix::DbgMsg dm;
+    dm.dst = f.dst;
+    dm.group = group++;
+    dm.meta.resize((size_t)meta_bytes(f.c.nseg, f.c.nidx));
+    dm.vals.resize((size_t)f.c.nvals * M->esz);
+    const char *meta = f.remote ? static_cast<char *>(M->peer_flush_meta[f.dst]) + (size_t)cp.me * M->flush_region_m + f.off_m
+                                : fm.meta.as<char>();
+    const char *vals = f.remote ? static_cast<char *>(M->peer_flush_vals[f.dst]) + (size_t)cp.me * M->flush_region_v + f.off_v
+                                : fm.vals.as<char>();
+    CM_CUDA_TRY(cudaMemcpy(dm.meta.data(), meta, dm.meta.size(), cudaMemcpyDefault));
+    CM_CUDA_TRY(cudaMemcpy(dm.vals.data(), vals, dm.vals.size(), cudaMemcpyDefault));
+    M->dbg_msgs.push_back(std::move(dm));
+  }
   for (int d = 0; d < cp.P; ++d)
     for (int k = 0; k < cp.K; ++k) {
       const MsgCounts &c = cp.counts[cp.cidx(cp.me, k, d)];
       cm_matrix::DbgMsg dm;
       dm.dst = d;
+      dm.group = group;
       if (c.nvals) {
         const size_t i = (size_t)k * cp.P + d;
         dm.meta.resize((size_t)meta_bytes(c.nseg, c.nidx));
@@ -1214,26 +1387,105 @@ int capture_wire(cm_matrix *M, const CommitPlan &cp) {
   return CM_OK;
 }
 
+// ---- flush regions -------------------------------------------------------------------------------
+// Every owner holds, for every source, a region its threshold flushes store into over NVLink between two
+// commits without any rendezvous (the reference's rput into a buffer the owner allocated by RPC, :163-173,
+// :226-228; here the buffers exist beforehand). Allocated and mapped COLLECTIVELY, at the end of the first
+// commit that carried flushed messages (until then, and whenever a region is full, flushed messages wait in
+// buffers of the source): room for four flushes of the largest size seen per (owner, source) pair, at most
+// 8 GiB per owner. Same decision on every rank: it is taken from the all-gathered descriptors.
+int ensure_flush_regions(cm_matrix *M, const CommitPlan &cp) {
+  if (cp.fl.empty() || !M->p2p || M->P <= 1 || M->apply_policy != 0) return CM_OK;
+  const int P = M->P, me = M->me;
+  Transport *tp = M->ctx->tp;
+  size_t top_v = 0, top_m = 0;
+  for (const FlushDesc &f : cp.fl) {
+    top_v = std::max(top_v, (size_t)pad32(f.c.nvals) * M->esz);
+    top_m = std::max(top_m, (size_t)meta_bytes(f.c.nseg, f.c.nidx));
+  }
+  const size_t cap_v = ((size_t)8 << 30) / P;
+  size_t want_v = std::min(cap_v, (4 * top_v + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1));
+  size_t want_m = (4 * top_m + 65535) & ~(size_t)65535;
+  if (want_v <= M->flush_region_v && want_m <= M->flush_region_m) return CM_OK;
+  want_v = std::max(want_v, M->flush_region_v);
+  want_m = std::max(want_m, M->flush_region_m);
+  // nobody keeps a mapping of regions that are about to be freed
+  for (int d = 0; d < P; ++d)
+    if (M->peer_flush_open[d]) {
+      cudaIpcCloseMemHandle(M->peer_flush_vals[d]);
+      cudaIpcCloseMemHandle(M->peer_flush_meta[d]);
+      M->peer_flush_open[d] = false;
+    }
+  CM_TRY(tp->barrier(M->stream));
+  CM_TRY(M->d_flush_vals.alloc_exact(want_v * P));
+  CM_TRY(M->d_flush_meta.alloc_exact(want_m * P));
+  ArenaHandles mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.pvals = M->d_flush_vals.p;
+  mine.pmeta = M->d_flush_meta.p;
+  if (!tp->same_process()) {
+    CM_CUDA_TRY(cudaIpcGetMemHandle(&mine.vals, M->d_flush_vals.p));
+    CM_CUDA_TRY(cudaIpcGetMemHandle(&mine.meta, M->d_flush_meta.p));
+  }
+  std::vector<ArenaHandles> all(P);
+  CM_TRY(tp->host_allgather(&mine, all.data(), sizeof(mine), M->stream));
+  for (int d = 0; d < P; ++d) {
+    if (d == me || tp->same_process()) {
+      M->peer_flush_vals[d] = all[d].pvals;
+      M->peer_flush_meta[d] = all[d].pmeta;
+    } else {
+      CM_CUDA_TRY(cudaIpcOpenMemHandle(&M->peer_flush_vals[d], all[d].vals, cudaIpcMemLazyEnablePeerAccess));
+      CM_CUDA_TRY(cudaIpcOpenMemHandle(&M->peer_flush_meta[d], all[d].meta, cudaIpcMemLazyEnablePeerAccess));
+      M->peer_flush_open[d] = true;
+    }
+  }
+  M->flush_region_v = want_v;
+  M->flush_region_m = want_m;
+  return tp->barrier(M->stream);
+}
+
+// collective: nobody maps or uses the flush regions any more (exchange mode change, destruction)
+void release_flush_regions(cm_matrix *M) {
+  for (int d = 0; d < M->P; ++d)
+    if (M->peer_flush_open[d]) {
+      cudaIpcCloseMemHandle(M->peer_flush_vals[d]);
+      cudaIpcCloseMemHandle(M->peer_flush_meta[d]);
+      M->peer_flush_open[d] = false;
+    }
+  M->ctx->tp->barrier(M->stream);
+  M->d_flush_vals.release();
+  M->d_flush_meta.release();
+  M->flush_region_v = M->flush_region_m = 0;
+  std::fill(M->peer_flush_vals.begin(), M->peer_flush_vals.end(), nullptr);
+  std::fill(M->peer_flush_meta.begin(), M->peer_flush_meta.end(), nullptr);
+}
+
+// the flushed messages of this commit have been applied (or logged) by their owners: drop them
+void forget_flushed(cm_matrix *M) {
+  for (FlushedMsg &f : M->flushed) {
+    f.vals.release();
+    f.meta.release();
+  }
+  M->flushed.clear();
+  std::fill(M->flush_used_v.begin(), M->flush_used_v.end(), (size_t)0);
+  std::fill(M->flush_used_m.begin(), M->flush_used_m.end(), (size_t)0);
+}
+
 // -- log or scatter-add what was delivered, elemental updates, quiescence ---------------------------
 int commit_finish(cm_matrix *M, CommitPlan &cp) {
   const int P = cp.P, me = cp.me, K = cp.K;
   if (M->keep_wire) CM_TRY(capture_wire(M, cp));
   if (cp.deferred) {
     // log instead of apply: the messages of this commit stay where they landed
-    for (int k = 0; k < K; ++k)
-      for (int src = 0; src < P; ++src) {
-        const MsgCounts &c = cp.counts[cp.cidx(src, k, me)];
-        if (c.nvals == 0) continue;
-        M->pend.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[me]) + cp.rbase_m[cp.ridx(me, k, src)],
-                                            static_cast<char *>(M->peer_vals[me]) + (size_t)cp.rbase_v[cp.ridx(me, k, src)] * M->esz,
-                                            c.nseg, c.nitems, c.nelems});
-      }
+    std::vector<cm_matrix::PendMsg> msgs;
+    delivered_messages(M, cp, 0, K, true, msgs);
+    M->pend.insert(M->pend.end(), msgs.begin(), msgs.end());
     for (int d = 0; d < P; ++d) {
-      M->pend_v[d] = cp.rbase_v[cp.ridx(d, K - 1, P - 1) + 1];
-      M->pend_m[d] = cp.rbase_m[cp.ridx(d, K - 1, P - 1) + 1];
+      M->pend_v[d] = cp.end_v[d];
+      M->pend_m[d] = cp.end_m[d];
     }
   } else if (!cp.pipelined) {
-    CM_TRY(apply_panels(M, cp, 0, K, M->work[0], M->stream, 0));
+    CM_TRY(apply_panels(M, cp, 0, K, true, M->work[0], M->stream, 0));
     trace_mark(M, "finish: scatter-add done");
   }
   for (int src = 0; src < P; ++src) {
@@ -1251,6 +1503,7 @@ int commit_finish(cm_matrix *M, CommitPlan &cp) {
     CM_CUDA_TRY(cudaGetLastError());
     resolve_timers(M);
     clear_staged(M);
+    forget_flushed(M);  // under this policy they all waited at their sources and have been copied into the log
     bool over = false;  // same decision on every rank
     for (int d = 0; d < P; ++d) over = over || (size_t)M->pend_v[d] * M->esz > M->defer_budget;
     if (over) CM_TRY(materialize_all(M));
@@ -1266,7 +1519,86 @@ int commit_finish(cm_matrix *M, CommitPlan &cp) {
   trace_dump(M, true);
   M->mirror_valid = false;
   clear_staged(M);
+  forget_flushed(M);  // every owner has applied them: the flush regions are free again
+  return ensure_flush_regions(M, cp);
+}
+
+// ---- threshold flush with several ranks (reference flush(thresh) inside update(), :330-375, :614) ----
+// NOT collective. Everything staged is mapped and packed NOW, one message per owner: straight into the
+// owner's flush region of this source over NVLink when there is one with room (the reference's rput,
+// :168-171), otherwise into buffers of this rank that the next commit delivers. Either way the staged
+// payloads, index sets and descriptors are released on return (borrowed device payloads included), and
+// the owner scatter-adds the message inside its next commit, in front of that commit's own messages, so
+// the per-(source, owner) stream stays the reference's. Elemental updates stay in their host bins.
+int flush_shipped(cm_matrix *M) {
+  const int nupd = (int)M->descs.size();
+  if (nupd == 0) return CM_OK;
+  const int P = M->P, me = M->me, K = kMaxChunks;
+  const size_t esz = M->esz;
+  if (M->reads_local_block) CM_TRY(wait_background(M));  // fill_lower's payload is the local block itself
+  const PanelPlan pp{1, 1};
+  long max_rows = 0;
+  for (const UpdDesc &d : M->descs) max_rows = std::max<long>(max_rows, d.m);
+  trace_mark(M, "flush: begin");
+  {
+    ScopedTimer t(M, 1, 0);
+    MapArenas ma{};
+    ScanArenas sa{};
+    CM_TRY(map_and_scan(M, pp, nupd, ma, sa));
+    // sizes of MY messages only: a local read-back, no rendezvous
+    std::vector<MsgCounts> mine((size_t)P * K);
+    CM_CUDA_TRY(cudaMemcpyAsync(mine.data(), M->d_totals.p, sizeof(MsgCounts) * mine.size(), cudaMemcpyDeviceToHost, M->stream));
+    CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+    M->stats.d2h_bytes += (long)(sizeof(MsgCounts) * mine.size());
+    const bool regions = M->p2p && M->apply_policy == 0 && M->flush_region_v > 0;
+    std::vector<void *> dst_ptrs(2 * (size_t)K * P, nullptr);
+    for (int d = 0; d < P; ++d) {
+      MsgCounts c = mine[d];  // panel 0
+      if (c.nvals == 0) continue;
+      c.ncoo = c.nflushed = 0;
+      const size_t vb = (size_t)pad32(c.nvals) * esz, mb = (size_t)meta_bytes(c.nseg, c.nidx);
+      FlushedMsg fm;
+      fm.d = FlushDesc{me, d, 0, (int)M->flushed.size(), 0, 0, c};
+      if (regions && M->flush_used_v[d] + vb <= M->flush_region_v && M->flush_used_m[d] + mb <= M->flush_region_m) {
+        fm.d.remote = 1;
+        fm.d.off_v = (long)M->flush_used_v[d];
+        fm.d.off_m = (long)M->flush_used_m[d];
+        M->flush_used_v[d] += vb;
+        M->flush_used_m[d] += (mb + 255) & ~(size_t)255;
+        dst_ptrs[d] = static_cast<char *>(M->peer_flush_vals[d]) + (size_t)me * M->flush_region_v + fm.d.off_v;
+        dst_ptrs[(size_t)K * P + d] = static_cast<char *>(M->peer_flush_meta[d]) + (size_t)me * M->flush_region_m + fm.d.off_m;
+        if (d != me) M->stats.bytes_sent += (long)(c.nvals * esz + mb);
+        M->stats.flushed_shipped += 1;
+      } else {
+        M->stats.flushed_held += 1;
+        CM_TRY(fm.vals.alloc_exact(vb));
+        CM_TRY(fm.meta.alloc_exact(mb));
+        dst_ptrs[d] = fm.vals.p;
+        dst_ptrs[(size_t)K * P + d] = fm.meta.p;
+      }
+      M->flushed.push_back(fm);
+    }
+    CM_CUDA_TRY(cudaMemcpyAsync(M->d_dst_ptrs.p, dst_ptrs.data(), dst_ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice, M->stream));
+    launch_pack(M->dtype, M->d_descs.as<UpdDesc>(), nupd, 0, 1, pp, M->g, ma, sa, max_rows, M->stream);
+    M->stats.kernel_launches += 1;
+    CM_CUDA_TRY(cudaGetLastError());
+  }
+  // the staged payloads (borrowed ones included) and the host-side arenas are released on return
+  CM_CUDA_TRY(cudaStreamSynchronize(M->stream));
+  CM_CUDA_TRY(cudaGetLastError());
+  trace_mark(M, "flush: packed");
+  resolve_timers(M);
+  trace_dump(M, false);
+  M->stats.flushes += 1;
+  clear_staged(M, true);
   return CM_OK;
+}
+
+// everything staged on this rank leaves the staging area: scatter-added at once with one rank, packed
+// (and, with a flush region, shipped) with several
+int flush_any(cm_matrix *M, bool sync) {
+  if (M->P == 1 && !M->keep_wire) return flush_direct(M, sync);
+  return flush_shipped(M);
 }
 
 int commit_exchange(cm_matrix *M) {
@@ -1328,8 +1660,8 @@ int check_dims(long m_u, long n_u) {
 int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, int trans, const long *d_ix,
                const long *d_jx, int mask) {
   if (m_u == 0 || n_u == 0) return CM_OK;
-  if ((long)M->descs.size() + 1 >= (1L << kItemSegBits))
-    return fail(CM_ERR_INVALID, "more than %ld updates staged; flush or commit more often", (1L << kItemSegBits) - 1);
+  if ((long)M->descs.size() + 1 > M->max_staged_updates)  // make_room() flushes before this can happen
+    return fail(CM_ERR_INVALID, "more than %ld updates staged", M->max_staged_updates);
   UpdDesc d;
   d.data = d_data;
   d.ix = d_ix;
@@ -1354,7 +1686,14 @@ int stage_desc(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld, in
 
 // reference flush(thresh) trigger, :346 / :614: strict '>' on the number of staged elements
 int maybe_flush(cm_matrix *M) {
-  if (M->P == 1 && !M->keep_wire && M->staged_elems + M->coo_total > M->flush_threshold) return flush_direct(M, false);
+  if (M->staged_elems + M->coo_total > M->flush_threshold) return flush_any(M, false);
+  return CM_OK;
+}
+
+// called before an update is staged: one scatter-add addresses at most max_staged_updates segments, so a
+// rank that has staged that many flushes first (instead of refusing the update)
+int make_room(cm_matrix *M) {
+  if ((long)M->descs.size() + 1 > M->max_staged_updates) return flush_any(M, true);
   return CM_OK;
 }
 
@@ -1384,6 +1723,7 @@ int stage_host_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld
   // storage footprint: contiguous dim x other dim with leading dimension ld
   const long rows_s = trans ? n_u : m_u, cols_s = trans ? m_u : n_u;
   if (ld < rows_s) return fail(CM_ERR_INVALID, "ld (%ld) smaller than the stored leading dimension (%ld)", ld, rows_s);
+  CM_TRY(make_room(M));
   const size_t esz = M->esz;
   void *d_payload = nullptr;
   CM_TRY(M->payload_arena.alloc((size_t)rows_s * cols_s * esz, &d_payload));
@@ -1431,6 +1771,7 @@ int stage_host_slice(cm_matrix *M, const void *data, long m_u, long n_u, long ld
       cudaGetLastError();
     }
   }
+  M->stats.staging_peak_bytes = std::max(M->stats.staging_peak_bytes, (long)(M->payload_arena.used() + M->index_arena.used()));
   CM_TRY(stage_desc(M, d_payload, m_u, n_u, rows_s, trans, static_cast<const long *>(dv_ix),
                     static_cast<const long *>(dv_jx), mask));
   return maybe_flush(M);
@@ -1576,6 +1917,11 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
   M->peer_arena_open.assign(M->P, false);
   M->pend_v.assign(M->P, 0);
   M->pend_m.assign(M->P, 0);
+  M->peer_flush_vals.assign(M->P, nullptr);
+  M->peer_flush_meta.assign(M->P, nullptr);
+  M->peer_flush_open.assign(M->P, false);
+  M->flush_used_v.assign(M->P, 0);
+  M->flush_used_m.assign(M->P, 0);
   {
     // peer-to-peer stores need every rank to be able to map every other rank's memory
     int mine_ok = 1;
@@ -1619,6 +1965,8 @@ int cm_destroy(cm_matrix *M) {
       cudaIpcCloseMemHandle(M->peer_meta[r]);
     }
   }
+  forget_flushed(M);
+  release_flush_regions(M);        // (contains a barrier)
   M->ctx->tp->barrier(M->stream);  // nobody still reads my block
   cudaFree(M->d_local);
   free(M->h_mirror);
@@ -1682,6 +2030,7 @@ int cm_update_slice_device(cm_matrix *M, const void *d_data, long m_u, long n_u,
   if (!d_data || !d_ix || !d_jx) return fail(CM_ERR_INVALID, "null device pointer");
   if (mask < 0 || mask > 2) return fail(CM_ERR_INVALID, "bad mask %d", mask);
   if (ld < (trans ? n_u : m_u)) return fail(CM_ERR_INVALID, "ld too small");
+  CM_TRY(make_room(M));
   CM_TRY(stage_desc(M, d_data, m_u, n_u, ld, trans, d_ix, d_jx, mask));
   M->borrowed_pending = true;
   return maybe_flush(M);
@@ -1730,6 +2079,7 @@ int cm_fill_lower(cm_matrix *M) {
   launch_iota_global(M->d_fill_jx.as<long>(), M->m_local, g.mb, g.nprow, g.myprow, M->stream);
   M->stats.kernel_launches += 2;
   CM_TRY(check_dims(M->n_local, M->m_local));
+  CM_TRY(make_room(M));
   CM_TRY(stage_desc(M, M->d_local, M->n_local, M->m_local, g.lld, 1, M->d_fill_ix.as<long>(), M->d_fill_jx.as<long>(),
                     CM_MASK_STRICT_LOWER));
   M->reads_local_block = true;  // the commit that ships this packs it before any scatter-add touches the block
@@ -1741,8 +2091,7 @@ int cm_fill_lower(cm_matrix *M) {
 
 int cm_flush(cm_matrix *M) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
-  if (M->P == 1 && !M->keep_wire) return flush_direct(M);
-  return CM_OK;
+  return flush_any(M, true);
 }
 
 int cm_commit(cm_matrix *M) {
@@ -1938,7 +2287,8 @@ int cm_set_apply_policy(cm_matrix *M, int policy, long budget_bytes) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   if (policy != CM_APPLY_EAGER && policy != CM_APPLY_DEFERRED && policy != CM_APPLY_BACKGROUND)
     return fail(CM_ERR_INVALID, "apply policy must be CM_APPLY_EAGER (0), CM_APPLY_DEFERRED (1) or CM_APPLY_BACKGROUND (2)");
-  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the apply policy only with nothing staged");
+  if (!M->descs.empty() || M->coo_total || !M->flushed.empty())
+    return fail(CM_ERR_STATE, "change the apply policy only with nothing staged (right after a commit)");
   CM_TRY(materialize_all(M));
   M->apply_policy = policy;
   if (budget_bytes > 0) M->defer_budget = (size_t)budget_bytes;
@@ -1954,7 +2304,8 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
   if (mode < 0 || mode > 2)
     return fail(CM_ERR_INVALID, "exchange mode must be 0 (auto), 1 (all-to-all-v) or 2 (peer-to-peer stores)");
-  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "change the exchange mode only with nothing staged");
+  if (!M->descs.empty() || M->coo_total || !M->flushed.empty())
+    return fail(CM_ERR_STATE, "change the exchange mode only with nothing staged (right after a commit)");
   if (mode >= 2 && M->P > 1 && !M->p2p_possible)
     return fail(CM_ERR_STATE, "peer-to-peer exchange needs every rank's memory mapped (CUDA IPC unavailable)");
   CM_TRY(materialize_all(M));  // the arenas are about to be released
@@ -1973,6 +2324,7 @@ int cm_set_exchange_mode(cm_matrix *M, int mode) {
   CM_TRY(M->ctx->tp->barrier(M->stream));
   M->d_recv_vals.release();
   M->d_recv_meta.release();
+  release_flush_regions(M);  // mapped for peer-to-peer stores only
   return CM_OK;
 }
 int cm_get_exchange_mode(const cm_matrix *M) { return M ? (M->p2p ? 2 : 1) : -1; }
@@ -2007,7 +2359,8 @@ int cm_reset_stats(cm_matrix *M) {
 // ---- parity hooks -------------------------------------------------------------------
 int cm_debug_keep_wire(cm_matrix *M, int on) {
   if (!M) return fail(CM_ERR_INVALID, "null matrix");
-  if (!M->descs.empty() || M->coo_total) return fail(CM_ERR_STATE, "toggle wire capture only with nothing staged");
+  if (!M->descs.empty() || M->coo_total || !M->flushed.empty())
+    return fail(CM_ERR_STATE, "toggle wire capture only with nothing staged (right after a commit)");
   M->keep_wire = on ? 1 : 0;
   M->dbg_valid = false;
   return CM_OK;
@@ -2023,37 +2376,41 @@ static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *da
   const size_t esz = M->esz;
   const int dp = dst / (int)g.npcol, dq = dst % (int)g.npcol;
   long n = 0;
-  std::vector<const cm_matrix::DbgMsg *> msgs;
-  long nseg_max = 0;
-  for (const auto &dm : M->dbg_msgs) {
-    if (dm.dst != dst || dm.meta.size() < sizeof(WireHdr)) continue;
-    msgs.push_back(&dm);
-    nseg_max = std::max(nseg_max, reinterpret_cast<const WireHdr *>(dm.meta.data())->nseg);
-  }
-  for (long u = 0; u < nseg_max; ++u)
-    for (const cm_matrix::DbgMsg *dm : msgs) {
-      const char *meta = dm->meta.data();
-      const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
-      if (u >= h->nseg) continue;
-      const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
-      const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
-      const unsigned char *vals = reinterpret_cast<const unsigned char *>(dm->vals.data());
-      const WireSeg &s = ws[u];
-      const int *lrow = idx + s.idx_off, *lcol = lrow + s.nr;
-      for (int b = 0; b < s.nc; ++b)
-        for (int a = 0; a < s.nr; ++a) {
-          if (s.mask) {
-            const long gr = global_index(lrow[a], g.mb, g.nprow, dp), gc = global_index(lcol[b], g.nb, g.npcol, dq);
-            if (s.mask == CM_MASK_UPPER ? !(gr <= gc) : !(gr > gc)) continue;
-          }
-          if (inds_out) {
-            inds_out[n] = g.lld * (long)lcol[b] + lrow[a];
-            memcpy(data_out + (size_t)n * esz,
-                   vals + ((size_t)s.val_off + (size_t)a + (size_t)b * seg_col_stride(s.nr)) * esz, esz);
-          }
-          ++n;
-        }
+  int ngroups = 0;
+  for (const auto &dm : M->dbg_msgs) ngroups = std::max(ngroups, dm.group + 1);
+  for (int grp = 0; grp < ngroups; ++grp) {  // threshold flushes in order, then the commit's own messages
+    std::vector<const cm_matrix::DbgMsg *> msgs;
+    long nseg_max = 0;
+    for (const auto &dm : M->dbg_msgs) {
+      if (dm.dst != dst || dm.group != grp || dm.meta.size() < sizeof(WireHdr)) continue;
+      msgs.push_back(&dm);
+      nseg_max = std::max(nseg_max, reinterpret_cast<const WireHdr *>(dm.meta.data())->nseg);
     }
+    for (long u = 0; u < nseg_max; ++u)
+      for (const cm_matrix::DbgMsg *dm : msgs) {
+        const char *meta = dm->meta.data();
+        const WireHdr *h = reinterpret_cast<const WireHdr *>(meta);
+        if (u >= h->nseg) continue;
+        const WireSeg *ws = reinterpret_cast<const WireSeg *>(meta + sizeof(WireHdr));
+        const int *idx = reinterpret_cast<const int *>(meta + sizeof(WireHdr) + h->nseg * sizeof(WireSeg));
+        const unsigned char *vals = reinterpret_cast<const unsigned char *>(dm->vals.data());
+        const WireSeg &s = ws[u];
+        const int *lrow = idx + s.idx_off, *lcol = lrow + s.nr;
+        for (int b = 0; b < s.nc; ++b)
+          for (int a = 0; a < s.nr; ++a) {
+            if (s.mask) {
+              const long gr = global_index(lrow[a], g.mb, g.nprow, dp), gc = global_index(lcol[b], g.nb, g.npcol, dq);
+              if (s.mask == CM_MASK_UPPER ? !(gr <= gc) : !(gr > gc)) continue;
+            }
+            if (inds_out) {
+              inds_out[n] = g.lld * (long)lcol[b] + lrow[a];
+              memcpy(data_out + (size_t)n * esz,
+                     vals + ((size_t)s.val_off + (size_t)a + (size_t)b * seg_col_stride(s.nr)) * esz, esz);
+            }
+            ++n;
+          }
+      }
+  }
   const CooBin &cb = M->dbg_coo[dst];
   for (size_t k = 0; k < cb.inds.size(); ++k) {
     if (inds_out) {
@@ -2063,6 +2420,13 @@ static long expand_wire(cm_matrix *M, int dst, long *inds_out, unsigned char *da
     ++n;
   }
   return n;
+}
+
+int cm_debug_set_staging_limit(cm_matrix *M, long max_updates) {
+  if (!M) return fail(CM_ERR_INVALID, "null matrix");
+  if (max_updates < 1 || max_updates > (1L << kItemSegBits) - 1) return fail(CM_ERR_INVALID, "limit out of range");
+  M->max_staged_updates = max_updates;
+  return CM_OK;
 }
 
 int cm_debug_wire_count(cm_matrix *M, int dst, long *n_out) {

@@ -114,7 +114,8 @@ int cm_fill_lower(cm_matrix *M);
 
 /* Device-resident variant of update(): d_data, d_ix, d_jx are DEVICE pointers on this
  * rank's GPU. The payload and index arrays are BORROWED (stream-ordered) until the next
- * cm_flush()/cm_commit() on this matrix returns; mask is one of CM_MASK_*. This is the
+ * cm_flush()/cm_commit() on this matrix returns — on any number of ranks: a flush packs (or
+ * scatter-adds) everything staged before it returns; mask is one of CM_MASK_*. This is the
  * zero-copy path behind cm::DeviceLocalMatrix. */
 int cm_update_slice_device(cm_matrix *M, const void *d_data, long m_u, long n_u, long ld,
                            int trans, const long *d_ix, const long *d_jx, int mask);
@@ -129,9 +130,16 @@ int cm_update_slices(cm_matrix *M, long count, const void *const *data, const lo
                      const long *n_u, const long *ld, const int *trans, const long *const *ix,
                      const long *const *jx);
 
-/* Apply / pack everything staged so far on THIS rank (the analogue of the reference's
- * flush(thresh), :330-375). Non-collective. With one rank it maps and scatter-adds the
- * staged updates; with several it is a no-op (staged data is exchanged by commit). */
+/* Everything staged so far on THIS rank leaves the staging area (the reference's flush(thresh),
+ * :330-375, with thresh = 0). NOT collective. With one rank the staged updates are mapped and
+ * scatter-added. With several they are mapped and packed into one message per owner, which the pack
+ * kernel stores straight into the owner's flush region of this rank over NVLink (the reference's rput,
+ * :168-171; regions exist from the end of the first commit that carried a flushed message, and hold four
+ * flushes per (owner, source) pair) or, without a region with room, into buffers of this rank that the
+ * next commit delivers; the owner scatter-adds flushed messages inside its next commit, in front of that
+ * commit's own (the reference: inside its next progress()). On return the staged payloads, index sets
+ * and descriptors are released, borrowed device payloads included. update() calls this by itself when
+ * more than bin_flush_threshold elements are staged (:346, :614). Elemental updates stay in host bins. */
 int cm_flush(cm_matrix *M);
 /* commit(), :723-742 — COLLECTIVE: pack, exchange (all-to-all-v), scatter-add, barrier.
  * On return every update issued by ANY rank before its matching commit() is applied. */
@@ -170,7 +178,9 @@ long cm_pgrid_col(const cm_matrix *M);
 int cm_dtype(const cm_matrix *M);
 
 /* bin_flush_threshold, :507-514 — number of staged update ELEMENTS above which update()
- * triggers a local flush (strict '>', :346). Default CM_DEFAULT_FLUSH_THRESHOLD. */
+ * triggers cm_flush (strict '>', :346), on any number of ranks. Default CM_DEFAULT_FLUSH_THRESHOLD
+ * (2^30 elements, not the reference's 10000: batches are what make the sorted sweep pay); a per-rank
+ * setting. Independently of it a rank flushes before it stages its 2^26-th update. */
 #define CM_DEFAULT_FLUSH_THRESHOLD (1L << 30)
 long cm_get_flush_threshold(const cm_matrix *M);
 int cm_set_flush_threshold(cm_matrix *M, long elements);
@@ -214,12 +224,9 @@ int cm_materialize(cm_matrix *M);
 /* How commit() moves the per-owner messages (COLLECTIVE: same call on every rank, nothing staged):
  * 0 = auto, 1 = grouped ncclSend/ncclRecv all-to-all-v from a local send arena, 2 = peer-to-peer
  * stores: the pack kernel writes each message straight into the owner's receive arena over NVLink
- * (arenas mapped with CUDA IPC), so packing and exchange are one kernel, 3 = copy engines: messages
- * are packed locally and pushed into the owners' arenas with peer cudaMemcpyAsync, arrival is
- * signalled with a flag the owner awaits with cuStreamWaitValue32 (no SM does communication, so
- * the scatter-add of one column panel overlaps the push of the next). Auto picks 2 when every rank can map
- * every other rank's memory, else 1. The environment variable CM_B200_EXCHANGE=nccl|p2p|dma sets
- * the default. cm_get_exchange_mode returns the mode in effect (1, 2 or 3). */
+ * (arenas mapped with CUDA IPC), so packing and exchange are one kernel. Auto picks 2 when every rank
+ * can map every other rank's memory, else 1. The environment variable CM_B200_EXCHANGE=nccl|p2p sets
+ * the default. cm_get_exchange_mode returns the mode in effect (1 or 2). */
 int cm_set_exchange_mode(cm_matrix *M, int mode);
 int cm_get_exchange_mode(const cm_matrix *M);
 
@@ -245,6 +252,9 @@ typedef struct cm_stats {
   long apply_launches;
   long apply_elements;     /* elements covered by the timed scatter-add launches        */
   long tile_launches;      /* scatter-add launches that used the column-tile kernel     */
+  long flushed_shipped;    /* messages of threshold flushes stored into their owner's flush region at flush time */
+  long flushed_held;       /* ... packed into buffers of this rank and delivered by the next commit */
+  long staging_peak_bytes; /* high-water mark of the host-API staging arenas (payload copies + index sets) */
 } cm_stats;
 int cm_get_stats(cm_matrix *M, cm_stats *out);
 int cm_reset_stats(cm_matrix *M);
@@ -258,6 +268,9 @@ int cm_stream(cm_matrix *M, void **out);
  * expanded from the compact wire format into the reference's per-element (inds, data)
  * stream (XBuff, :128-133) in the reference's order (:605-613). */
 int cm_debug_keep_wire(cm_matrix *M, int on);
+/* lowers the number of updates a rank may stage before it flushes by itself (and the number of segments
+ * one scatter-add addresses) from 2^26 - 1, so that tests reach that path with small inputs */
+int cm_debug_set_staging_limit(cm_matrix *M, long max_updates);
 int cm_debug_wire_count(cm_matrix *M, int dst, long *n_out);
 int cm_debug_wire_expand(cm_matrix *M, int dst, long *inds_out, void *data_out);
 

@@ -95,8 +95,14 @@ def make_scenario(rng):
         knobs["defer_budget"] = int(rng.choice([0, 1, 20000, 400000]))
     if cfg.P == 1:
         knobs["exchange_mode"] = 0
-        if rng.random() < 0.5:
-            knobs["threshold"] = int(rng.integers(1, 60000))
+    # threshold flushes on any number of ranks (reference :346, :614), explicit cm_flush calls, and the limit of
+    # staged updates at which a rank flushes by itself
+    if rng.random() < 0.5:
+        knobs["threshold"] = int(rng.integers(1, 60000))
+    if rng.random() < 0.15:
+        knobs["flush_every"] = int(rng.integers(1, 4))
+    if rng.random() < 0.15:
+        knobs["staging_limit"] = int(rng.integers(1, 4))
     env = {}
     if cfg.P > 1 and rng.random() < 0.6:
         env = {"CM_B200_PIPELINE": str(int(rng.random() < 0.8)), "CM_B200_PIPELINE_MIN_ELEMS": str(int(rng.choice([1, 2000, 50000]))),
@@ -122,8 +128,6 @@ def run_one(seed, verbose=False):
     os.environ.update(env)
     try:
         want = run_checker(cfg, steps, wire=wire, threshold=(1 << 40) if wire else None)
-        if wire and "threshold" in knobs:
-            knobs = {k: v for k, v in knobs.items() if k != "threshold"}  # wire capture = one message per commit
         got = run_cuda(cfg, steps, wire=wire, **knobs)
         if wire:
             assert_wire_match(cfg, got, want)

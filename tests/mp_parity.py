@@ -57,6 +57,9 @@ def main():
             M.set_exchange_mode(int(os.environ["CM_TEST_EXCHANGE_MODE"]))
         if os.environ.get("CM_TEST_APPLY_POLICY"):  # 1 = deferred scatter-add (peer-to-peer modes)
             M.set_apply_policy(int(os.environ["CM_TEST_APPLY_POLICY"]), int(os.environ.get("CM_TEST_DEFER_BUDGET", "0")))
+        thr = int(os.environ.get("CM_TEST_FLUSH_THRESHOLD", "0"))
+        if thr:  # threshold flushes inside update() (reference :346, :614): flush regions over CUDA IPC / NVLink
+            M.set_flush_threshold(thr)
         M.keep_wire(True)
         wires = {}
         for st in steps:
@@ -98,6 +101,12 @@ def main():
         print(f"[rank {rank}] {cfg}: normwise rel err {err:.2e} ok={ok} wire_ok={wire_ok} remote_read_ok={read_ok} "
               f"exchange_mode={M.exchange_mode()} stats={ {k: v for k, v in M.stats().items() if k in ('bytes_sent', 'bytes_received', 'kernel_launches')} }", flush=True)
         failures += (not ok) + (not wire_ok) + (not read_ok)
+        if thr:
+            st = M.stats()
+            shipped_ok = st["flushes"] > 0 and (st["flushed_shipped"] > 0 if M.exchange_mode() == 2 and not os.environ.get("CM_TEST_APPLY_POLICY")
+                                                 else st["flushed_held"] > 0)
+            print(f"[rank {rank}] threshold {thr}: flushes={st['flushes']} shipped={st['flushed_shipped']} held={st['flushed_held']} ok={shipped_ok}", flush=True)
+            failures += not shipped_ok
         M.destroy()
     cm.finalize()
     ft = torch.tensor([failures], device=dev)

@@ -66,8 +66,33 @@ def run_checker(cfg, steps, kind="oracle", wire=False, threshold=None):
     return out
 
 
+def torch_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+class _HostBuf:
+    """stand-in for a device tensor under the kernel-logic test library"""
+
+    def __init__(self, a, dt):
+        self.a = np.ascontiguousarray(a, dtype=dt).copy()
+
+    def data_ptr(self):
+        return self.a.ctypes.data
+
+    def is_floating_point(self):
+        return self.a.dtype.kind == "f"
+
+    def fill_(self, v):
+        self.a[...] = v
+
+
 def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, deterministic=False, device_api=False,
-             apply_kernel=0, exchange_mode=0, apply_policy=0, defer_budget=0):
+             apply_kernel=0, exchange_mode=0, apply_policy=0, defer_budget=0, staging_limit=None, flush_every=0,
+             free_after_flush=False):
     """Execute on the GPU. P == 1 uses the process runtime, P > 1 the loopback transport
     (threads-as-ranks on one device). device_api=True feeds slices through
     cm_update_slice_device from torch tensors already resident in HBM."""
@@ -81,6 +106,9 @@ def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, determin
         world = cm.LoopbackWorld(P, 0)
         run, on = world.run, world.on
     keep = []  # device tensors borrowed until commit
+    keep_r = {r: [] for r in range(P)}  # free_after_flush: ... or until the issuing rank's next flush
+    nflush = [0] * P
+    nslice = [0] * P
     try:
         mats = run(lambda r: cm.Matrix(*cfg.args()))
 
@@ -97,22 +125,41 @@ def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, determin
                 M.set_exchange_mode(exchange_mode)
             if apply_policy:
                 M.set_apply_policy(apply_policy, defer_budget)
+            if staging_limit:
+                M.set_staging_limit(staging_limit)
         run(setup)
         wires = {}
         for st in steps:
             op = st[0]
             if op == "slice":
                 _, r, data, m_u, n_u, ld, trans, ix, jx = st
-                if device_api:
+                if device_api and not torch_cuda():
+                    # kernel-logic test library (tests/emu): "device" memory is host memory
+                    d, di, dj = _HostBuf(data, cm.NP_DTYPE[cfg.dtype]), _HostBuf(ix, np.int64), _HostBuf(jx, np.int64)
+                if device_api and torch_cuda():
                     import torch
                     d = torch.from_numpy(np.ascontiguousarray(data, dtype=cm.NP_DTYPE[cfg.dtype])).cuda()
                     di = torch.from_numpy(np.ascontiguousarray(ix, dtype=np.int64)).cuda()
                     dj = torch.from_numpy(np.ascontiguousarray(jx, dtype=np.int64)).cuda()
                     torch.cuda.synchronize()
-                    keep.extend([d, di, dj])
+                if device_api:
+                    (keep_r[r] if free_after_flush else keep).extend([d, di, dj])
                     on(r, lambda rr: mats[rr].update_device(d.data_ptr(), m_u, n_u, ld, trans, di.data_ptr(), dj.data_ptr()))
+                    if free_after_flush:
+                        # the borrow ends when a flush returns (include/cm_b200.h): scribble over what was lent
+                        n = on(r, lambda rr: mats[rr].stats()["flushes"])
+                        if n > nflush[r]:
+                            nflush[r] = n
+                            for t in keep_r[r]:
+                                t.fill_(float("nan") if t.is_floating_point() else -7)
+                            if torch_cuda():
+                                torch.cuda.synchronize()
+                            keep_r[r] = []
                 else:
                     on(r, lambda rr: mats[rr].update(data, ix, jx, m_u, n_u, ld, trans))
+                nslice[r] += 1
+                if flush_every and nslice[r] % flush_every == 0:
+                    on(r, lambda rr: mats[rr].flush())
             elif op == "sym":
                 _, r, data, n_u, ld, trans, ix = st
                 on(r, lambda rr: mats[rr].update_sym(data, ix, ld, trans))
@@ -124,6 +171,8 @@ def run_cuda(cfg, steps, wire=False, threshold=None, sorted_sweep=True, determin
             elif op == "commit":
                 run(lambda r: mats[r].commit())
                 keep.clear()
+                keep_r = {r: [] for r in range(P)}
+                nflush = run(lambda r: mats[r].stats()["flushes"])
                 if wire:
                     for s in range(P):
                         for d in range(P):

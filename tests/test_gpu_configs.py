@@ -116,3 +116,30 @@ def test_deterministic_mode_run_to_run_on_2x4(env, monkeypatch):
     for r in range(cfg.P):
         assert a["local"][r].tobytes() == b["local"][r].tobytes(), f"rank {r}: not bit-exact run to run"
     assert_blocks_match(cfg, a, run_checker(cfg, steps, kind=_kind(cfg)))
+
+
+def test_more_than_2_26_elements_per_rank_between_commits_on_2x2():
+    """bin_flush_threshold with several ranks (reference :330-375, :614): every rank of a
+    2 x 2 grid issues 71 Mi elements (> 2^26) through the HOST API between two commits, twice. A rank whose staged
+    elements exceed the threshold (2^22) packs them at once and releases its staging: the arenas stay at one
+    threshold's worth instead of growing with what is issued. Round 1 holds the flushed messages at the source (no
+    flush regions yet), round 2 stores them into the owners' regions at flush time. Blocks match the reference."""
+    cfg = Cfg(cm.F64, 16384, 4096, 2, 2, 64, 64, 8192)
+    rng = np.random.default_rng(106)
+    payloads = [rand_payload(rng, cfg.dtype, (512, 512)) for _ in range(8)]
+    U, thr = 272, 1 << 22
+    steps = []
+    for rnd in range(2):
+        for u in range(U):
+            for r in range(cfg.P):
+                steps.append(("slice", r, payloads[(u + r) % 8], 512, 512, 512, False, sorted_unique(rng, cfg.m, 512),
+                              sorted_unique(rng, cfg.n, 512)))
+        steps.append(("commit",))
+    assert U * 512 * 512 > 1 << 26
+    got = run_cuda(cfg, steps, threshold=thr)
+    for st in got["stats"]:
+        assert st["elements_staged"] == 2 * U * 512 * 512
+        assert st["flushes"] >= 2 * (U * 512 * 512 // (thr + 512 * 512)) - 2
+        assert st["flushed_held"] > 0 and st["flushed_shipped"] > 0
+        assert st["staging_peak_bytes"] < 2 * (thr + 512 * 512) * 8, st  # bounded by the threshold, not by 2 x 570 MB issued
+    assert_blocks_match(cfg, got, run_checker(cfg, steps, kind=_kind(cfg)))

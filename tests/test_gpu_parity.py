@@ -8,6 +8,8 @@ import cm_b200 as cm
 from scenario import (Cfg, assert_blocks_match, assert_wire_match, rand_payload, run_checker, run_cuda,
                       slice_steps, sorted_unique)
 
+from oracle_bindings import ref_available  # noqa: E402
+
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1200)]  # a hang must become a failure (pytest-timeout)
 
 
@@ -434,3 +436,64 @@ def test_save_load_reference_file_format(P, tmp_path):
             world.close()
         else:
             cm.finalize()
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+def test_multi_rank_threshold_flush(mode):
+    """bin_flush_threshold with several ranks (reference :346, :614, flush(thresh) inside update()): a rank whose
+    staged elements exceed the threshold maps and packs them at once, NOT collectively — into the owners' flush
+    regions over the peer-to-peer path once those exist (mode 2, from the second round on; the fifth flush of a
+    round no longer fits and waits at the source), into buffers of the source otherwise (round 1; mode 1:
+    all-to-all-v) — and the owners apply them inside the next commit. Per-(source, owner) streams stay
+    bit-exact with the reference's, blocks within tolerance, staging is released at every flush."""
+    cfg = Cfg(cm.F64, 2000, 1000, 2, 2, 64, 64, 1024)
+    rng = np.random.default_rng(77)
+    steps, steps_e = [], []  # steps_e: the same with elemental updates in between (they stay in host bins until the commit,
+    for rnd in range(3):     # so their place in the stream differs from the reference's: blocks only)
+        for u in range(12):
+            for r in range(cfg.P):
+                if r == 3 and rnd == 1:
+                    continue  # a rank that flushes nothing in a round
+                ix, jx = sorted_unique(rng, cfg.m, 200), sorted_unique(rng, cfg.n, 150)
+                steps.append(("slice", r, rand_payload(rng, cfg.dtype, (150, 200)), 200, 150, 200, False, ix, jx))
+                steps_e.append(steps[-1])
+            if u == 5:
+                v = rand_payload(rng, cfg.dtype, (40,))
+                steps_e.append(("elems", 1, v, rng.integers(0, cfg.m, 40), rng.integers(0, cfg.n, 40)))
+        steps.append(("commit",))
+        steps_e.append(("commit",))
+    kind = "ref" if ref_available() else "oracle"
+    want = run_checker(cfg, steps, kind=kind, wire=True)
+    got = run_cuda(cfg, steps, wire=True, threshold=50000, exchange_mode=mode)  # 30000 elements per update: a flush every 2
+    assert_wire_match(cfg, got, want)
+    assert_blocks_match(cfg, got, want)
+    assert_blocks_match(cfg, run_cuda(cfg, steps_e, threshold=50000, exchange_mode=mode), run_checker(cfg, steps_e, kind=kind))
+    for r, st in enumerate(got["stats"]):
+        assert st["flushes"] >= 12, st
+        if mode == 2:
+            assert st["flushed_shipped"] > 0 and st["flushed_held"] > 0, st
+        else:
+            assert st["flushed_shipped"] == 0 and st["flushed_held"] > 0, st
+    # same through the device API (borrowed payloads are released by the flush) and in deterministic mode
+    got2 = run_cuda(cfg, steps, threshold=50000, exchange_mode=mode, device_api=True, deterministic=True, free_after_flush=True)
+    assert_blocks_match(cfg, got2, want)
+    got3 = run_cuda(cfg, steps, threshold=50000, exchange_mode=mode, device_api=True, deterministic=True, free_after_flush=True)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(got2["local"], got3["local"]))
+
+
+def test_flush_call_and_staging_limit_several_ranks():
+    """cm_flush() on several ranks packs what is staged (it used to be a no-op there), and a rank that reaches the
+    limit of updates one scatter-add can address flushes by itself instead of refusing the update; the owners
+    then apply more segments than one scatter-add addresses in several launches. Deferred policy: flushed
+    messages join the log."""
+    cfg = Cfg(cm.F32, 1000, 600, 2, 2, 64, 64, 512)
+    rng = np.random.default_rng(78)
+    steps = slice_steps(cfg, rng, 23, 48, 40, commit_every=12)
+    want = run_checker(cfg, steps)
+    for policy in (0, 1):
+        got = run_cuda(cfg, steps, staging_limit=5, apply_policy=policy)
+        assert all(st["flushes"] >= 4 for st in got["stats"])
+        assert_blocks_match(cfg, got, want)
+    got = run_cuda(cfg, steps, flush_every=3)
+    assert all(st["flushes"] >= 6 for st in got["stats"])
+    assert_blocks_match(cfg, got, want)

@@ -42,6 +42,10 @@ MP_VARIANTS = {
     "deferred": {"CM_TEST_APPLY_POLICY": "1"},
     "background": {"CM_TEST_APPLY_POLICY": "2", "CM_B200_BG_MIN_ELEMS": "1"},
     "nccl": {"CM_TEST_EXCHANGE_MODE": "1"},
+    # threshold flushes inside update() with several ranks: flush regions mapped with CUDA IPC, stored into over NVLink
+    "flush": {"CM_TEST_FLUSH_THRESHOLD": "50000"},
+    "flush-nccl": {"CM_TEST_FLUSH_THRESHOLD": "50000", "CM_TEST_EXCHANGE_MODE": "1"},
+    "flush-deferred": {"CM_TEST_FLUSH_THRESHOLD": "50000", "CM_TEST_APPLY_POLICY": "1"},
 }
 
 

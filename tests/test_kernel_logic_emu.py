@@ -32,6 +32,8 @@ GROUPS = [
     "test_empty_ragged_and_lopsided_inputs",
     "test_contract_violations_fail_loudly",
     "test_save_load_reference_file_format",
+    "test_multi_rank_threshold_flush",
+    "test_flush_call_and_staging_limit_several_ranks",
     "device_api_single_rank",
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
