@@ -99,7 +99,7 @@ static_assert(sizeof(WireSeg) == 40, "wire segment layout");
 // Implementation: panels widen the column-group key of the grouping kernel from the owner column q
 // to gq = panel * NPCOL + q ("virtual owner columns"); the rest of the path sees npanel * NPCOL
 // column groups per update.
-constexpr int kMaxChunks = 4;
+constexpr int kMaxChunks = 8;
 struct PanelPlan {
   int npanel;       // 1 .. kMaxChunks, and npanel * NPCOL <= kMaxGridDim
   long panel_cols;  // local columns per panel, a multiple of NB (the last panel takes the rest)

@@ -367,14 +367,14 @@ struct cm_matrix {
   DevBuf d_counts_all, d_dst_ptrs, d_coo_counts;
   ApplyWork work[kMaxChunks];
   cudaStream_t apply_stream = nullptr;  // scatter-add of panel k while panel k+1 is packed / exchanged
-  cudaEvent_t ev_panel[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_panel[kMaxChunks] = {};
   cudaEvent_t ev_applied = nullptr;
   cudaEvent_t ev_bg = nullptr;  // main stream -> apply stream dependency of a background scatter-add
   // Panel-pipelined commits (peer-to-peer stores): on by default, CM_B200_PIPELINE=0 disables them.
   // B200, 8 GPUs: K1-weak 10.78 -> 9.39 ms per step, K3 23.4 -> 14.1 ms.
   int pipeline = 1;
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
-  int npanel_cfg = kMaxChunks;          // column panels of a pipelined commit (CM_B200_PANELS)
+  int npanel_cfg = 4;                   // column panels of a pipelined commit (CM_B200_PANELS, at most kMaxChunks)
   int pipeline_apply_blocks = 2;        // resident scatter-add blocks per SM while the next panel is being packed
                                         // (CM_B200_PIPELINE_APPLY_BLOCKS; 0 = no cap)
   PinBuf h_counts;

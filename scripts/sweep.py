@@ -33,6 +33,9 @@ VARIANTS = [
     ("panels4-ab3", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PIPELINE_APPLY_BLOCKS": "3"}, {}),
     ("panels2-ab2", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PANELS": "2"}, {}),
     ("panels3-ab2", "*", {"CM_B200_PIPELINE": "1", "CM_B200_PANELS": "3"}, {}),
+    ("panels6", "*", {"CM_B200_PANELS": "6"}, {}),
+    ("panels8", "*", {"CM_B200_PANELS": "8"}, {}),
+    ("panels8-ab3", "*", {"CM_B200_PANELS": "8", "CM_B200_PIPELINE_APPLY_BLOCKS": "3"}, {}),
     ("deferred", "*", {"CM_B200_PIPELINE": "0"}, {"deferred": 1}),
     ("background", "*", {"CM_B200_PIPELINE": "0"}, {"deferred": 2}),
     ("background-ab1", "*", {"CM_B200_PIPELINE": "0", "CM_B200_PIPELINE_APPLY_BLOCKS": "1"}, {"deferred": 2}),

@@ -106,7 +106,7 @@ def make_scenario(rng):
     env = {}
     if cfg.P > 1 and rng.random() < 0.6:
         env = {"CM_B200_PIPELINE": str(int(rng.random() < 0.8)), "CM_B200_PIPELINE_MIN_ELEMS": str(int(rng.choice([1, 2000, 50000]))),
-               "CM_B200_PANELS": str(int(rng.integers(1, 5)))}
+               "CM_B200_PANELS": str(int(rng.integers(1, 9)))}
     # stream comparison is defined for slice-only scenarios with panel-monotone index sets: elemental
     # updates travel in a lane of their own here (the reference interleaves them in the same bin) and
     # the symmetric update / fill_lower are masked on the owner

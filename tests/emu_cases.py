@@ -165,6 +165,7 @@ def panels_unsorted_masked_and_mixed_sources():
 
 CASES += [
     ("panels_wire_and_blocks", [((2, 2, 64, 64, 1024, 2000, 1000), 2, 4), ((2, 4, 16, 16, 256, 500, 900), 2, 4),
+                                ((2, 4, 16, 16, 256, 500, 900), 2, 8), ((2, 2, 64, 64, 1024, 2000, 1000), 2, 7),
                                 ((3, 2, 8, 4, 96, 250, 150), 2, 3), ((1, 2, 64, 64, 1024, 1000, 130), 2, 4),
                                 ((2, 1, 64, 64, 1024, 2000, 40), 2, 2)]),
     ("panels_unsorted_masked_and_mixed_sources", [()]),
