@@ -517,9 +517,25 @@ void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint3
 // col_start (optional, sorted keys only): col_start[c] = first sorted position whose key >= c, for
 // c in [0, ncols]; the thread at the head of a run writes the entries of its column and of the
 // empty columns before it, the last thread the tail.
+// first position in the strictly increasing rows[0, n) whose value is >= key
+__device__ __forceinline__ int first_row_ge(const int *__restrict__ rows, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(rows + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// cuts (optional; local blocks of 2 .. kMaxCutTiles row bands): cuts[t * kMaxCutTiles + k - 1] = first element of
+// item t whose row lies in band k or above, k = 1 .. ntiles - 1 — where the item's (strictly increasing) rows
+// cross the band boundaries. The tile kernel trims a staged item to its band with two loads instead of two
+// binary searches: 16 dependent loads per staged item were 40 % of a band's time at K2 / NS shapes.
+constexpr int kMaxCutTiles = 8;
 __global__ void __launch_bounds__(256) k_build_recs(const Seg *__restrict__ segs, const uint32_t *__restrict__ keys,
                                                     const uint64_t *__restrict__ items, long nitems, int esz,
-                                                    ItemRec *__restrict__ recs, long ncols, long *__restrict__ col_start) {
+                                                    ItemRec *__restrict__ recs, long ncols, long *__restrict__ col_start,
+                                                    unsigned short *__restrict__ cuts, int ntiles, int tile_rows) {
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nitems; t += (long)gridDim.x * blockDim.x) {
     if (col_start) {
       const long key = keys[t];
@@ -542,6 +558,8 @@ __global__ void __launch_bounds__(256) k_build_recs(const Seg *__restrict__ segs
     r.mask_flags = s.mask | (s.flags << 8);
     r.col = (int)keys[t];
     recs[t] = r;
+    if (cuts && s.flags == 0 && s.row_stride == 1)
+      for (int k = 1; k < ntiles; ++k) cuts[t * kMaxCutTiles + k - 1] = (unsigned short)first_row_ge(r.lrow, r.n, k * tile_rows);
   }
 }
 
@@ -550,13 +568,19 @@ int tile_count(int dtype, long m_local) {
   return (int)((m_local + tile_rows - 1) / tile_rows);
 }
 
+size_t cuts_bytes(int dtype, long m_local, long nitems) {
+  const int ntiles = tile_count(dtype, m_local);
+  return ntiles > 1 && ntiles <= kMaxCutTiles ? (size_t)nitems * kMaxCutTiles * sizeof(unsigned short) : 0;
+}
+
 void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, const uint64_t *d_items, long nitems,
-                       ItemRec *d_recs, long n_local, long *d_col_start, cudaStream_t s) {
+                       ItemRec *d_recs, long n_local, long *d_col_start, unsigned short *d_cuts, long m_local, cudaStream_t s) {
   if (nitems <= 0) return;
   const long cap = (long)kernel_sm_count() * 8;
   long blocks = std::min((nitems + 255) / 256, cap);
+  const int ntiles = tile_count(dtype, m_local);
   CM_LAUNCH((unsigned)blocks, 256, 0, s, k_build_recs)(d_segs, d_keys, d_items, nitems, (int)dtype_size(dtype), d_recs, n_local,
-                                                d_col_start);
+                                                d_col_start, d_cuts, ntiles, (int)(65536 / dtype_size(dtype)));
 }
 
 // ------------------------------------------------------------------------------------
@@ -703,16 +727,6 @@ __device__ __forceinline__ int mask_threshold(long gcol, long m_local, const Geo
   return (int)lo - 1;
 }
 
-// first position in the strictly increasing rows[0, n) whose value is >= key
-__device__ __forceinline__ int first_row_ge(const int *__restrict__ rows, int n, int key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(rows + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
 template <typename P>
 struct alignas(16) Pair16 {  // two pointers, one 16-byte shared-memory load
   P x, y;
@@ -782,6 +796,60 @@ __device__ __forceinline__ void tile_add_block(T *acc, int r0, int h, const int 
   }
 }
 
+// Item-parallel walk of a staged chunk (the default, order-free mode): warp w takes the staged items w, w + 8, ...
+// whole — lane l their elements l, l + 32, ... — and adds them into the tile with shared-memory atomics, so no
+// barrier separates the items and every lane has work whatever the height of the band (a 256-row item leaves 64
+// rows in one of four row bands: thread-per-element keeps a quarter of the block busy between two barriers). G items
+// x 2 passes of values and row indices are in flight per lane. The order in which items meet on an element is
+// not fixed: results agree with the ordered walk within rounding, not bit for bit (the deterministic mode keeps
+// the ordered walk). kGeneral: masks, strided payloads (repeated rows need nothing special here).
+template <typename T, bool kGeneral>
+__device__ __forceinline__ void tile_atomic_chunk(TileSmem<T> &sm, int cnt, int r0, int h, int thr, int tid) {
+  constexpr int G = 4, PASS = 2, kWarps = 8;
+  const int warp = tid >> 5, lane = tid & 31;
+  T *acc = sm.acc;
+  for (int j0 = warp; j0 < cnt; j0 += kWarps * G) {
+    const T *vp[G];
+    const int *rp[G];
+    int nn[G], st[G], mk[G];
+    int nmax = 0;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int j = j0 + kWarps * i;
+      const bool ok = j < cnt;
+      vp[i] = sm.v[ok ? j : 0];
+      rp[i] = sm.rows[ok ? j : 0];
+      nn[i] = ok ? sm.n[j] : 0;
+      st[i] = kGeneral ? sm.stride[ok ? j : 0] : 1;
+      mk[i] = kGeneral ? (sm.mf[ok ? j : 0] & 0xff) : 0;
+      nmax = max(nmax, nn[i]);
+    }
+    for (int a0 = 0; a0 < nmax; a0 += 32 * PASS) {
+      int row[G][PASS];
+      T val[G][PASS];
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int p = 0; p < PASS; ++p) {
+          const int a = a0 + 32 * p + lane;
+          const int aa = a < nn[i] ? a : 0;  // idle lanes re-read element 0 (always valid memory)
+          row[i][p] = __ldg(rp[i] + aa);
+          val[i][p] = __ldg(vp[i] + (long)aa * st[i]);
+        }
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int p = 0; p < PASS; ++p) {
+          const int a = a0 + 32 * p + lane;
+          const int rr = row[i][p] - r0;
+          bool ok = a < nn[i] && (unsigned)rr < (unsigned)h;
+          if (kGeneral) ok = ok && (mk[i] == 0 || (mk[i] == 1) == (rr + r0 <= thr));
+          if (ok) atomicAdd(acc + rr, val[i][p]);
+        }
+    }
+  }
+}
+
 // Write-back of a tile by the TMA unit: one bulk reduce-add (cp.reduce.async.bulk, SASS UBLKRED) adds the
 // whole shared-memory tile to its column in global memory. Needs 16-byte aligned ends; adds zeros where
 // nothing was hit.
@@ -814,9 +882,12 @@ struct alignas(16) Vec16 {
 // BLK: items a thread keeps in flight per register set (two sets); CTAS: resident blocks per SM
 // bulk: write the tile back with one bulk reduce-add (0: per-thread loads / stores; the kernel-logic
 // build and misaligned columns always take those)
-template <typename T, bool kMulti, int BLK, int CTAS>
+// kOrdered: items of a column are added strictly in sorted order, one barrier per item (bit-exact run to run: the
+// deterministic mode); otherwise the item-parallel walk with shared-memory atomics (tile_atomic_chunk)
+template <typename T, bool kMulti, int BLK, int CTAS, bool kOrdered>
 __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
-                                                       long ncols, int ntiles, long m_local, T *local, Geom g, int bulk) {
+                                                       long ncols, int ntiles, long m_local, T *local, Geom g, int bulk,
+                                                       const unsigned short *__restrict__ cuts) {
   CM_DYN_SMEM(smem_raw);
   TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
   constexpr int kTileRows = TileSmem<T>::kTileRows;
@@ -848,12 +919,20 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         const int *rows = r.lrow;
         int n = tid < cnt ? r.n : 0;
         const int mf = tid < cnt ? r.mask_flags : 0;
-        if (kMulti && n > 0 && (mf >> 8) == 0) {
+        if (kMulti && n > 0 && (mf >> 8) == 0 && r.row_stride == 1) {
           // taller than one tile: this block owns the rows [r0, r0 + h). An item's rows are strictly
           // increasing, so the ones that fall into the band are a contiguous sub-range: keep only
           // that (two binary searches per staged item instead of a range check per element, and
           // the warps beyond the sub-range have nothing to load)
-          const int a_lo = first_row_ge(r.lrow, r.n, r0), a_hi = first_row_ge(r.lrow, r.n, r0 + h);
+          int a_lo, a_hi;
+          if (cuts) {  // where the item's rows cross the band boundaries was worked out when the records were built
+            const unsigned short *ct = cuts + (base + tid) * kMaxCutTiles;
+            a_lo = tile == 0 ? 0 : (int)ct[tile - 1];
+            a_hi = tile == ntiles - 1 ? r.n : (int)ct[tile];
+          } else {
+            a_lo = first_row_ge(r.lrow, r.n, r0);
+            a_hi = first_row_ge(r.lrow, r.n, r0 + h);
+          }
           n = a_hi - a_lo;
           if (n > 0) {  // (an empty sub-range keeps the item's own, valid, base addresses)
             rows = r.lrow + a_lo;
@@ -865,10 +944,15 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
         sm.n[tid] = n;
         sm.stride[tid] = r.row_stride;
         sm.mf[tid] = mf;
-        special = tid < cnt ? (r.mask_flags | (r.row_stride != 1)) : 0;
+        special = tid < cnt ? ((kOrdered ? r.mask_flags : (r.mask_flags & 0xff)) | (r.row_stride != 1)) : 0;
       }
-      const bool plain = __syncthreads_or(special) == 0;  // no mask, no repeated rows, unit stride
-      if (plain) {
+      const bool plain = __syncthreads_or(special) == 0;  // no mask, unit stride (ordered walk: no repeated rows either)
+      if (!kOrdered) {
+        if (plain)
+          tile_atomic_chunk<T, false>(sm, cnt, r0, h, 0, tid);
+        else
+          tile_atomic_chunk<T, true>(sm, cnt, r0, h, mask_threshold(global_index(c, g.nb, g.npcol, g.mypcol), m_local, g), tid);
+      } else if (plain) {
         // thread t owns element t of every item; block b+1's elements are in flight while block b
         // is added; one barrier per item keeps the items in order
         int rowA[BLK], rowB[BLK];
@@ -964,42 +1048,49 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
 #endif
 }
 
-template <typename T, bool kMulti, int BLK, int CTAS>
+template <typename T, bool kMulti, int BLK, int CTAS, bool kOrdered>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
-                                T *d_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+                                T *d_local, const Geom &g, int max_blocks_per_sm, const unsigned short *d_cuts, cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
   static int resident = 0;
   const int bulk = 1;  // (0: per-thread write-back everywhere; kept for misaligned columns and the kernel-logic build)
   if (resident == 0) {
-    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS>, 256, smem);
+    cudaFuncSetAttribute(k_apply_tile<T, kMulti, BLK, CTAS, kOrdered>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    resident = resident_blocks(k_apply_tile<T, kMulti, BLK, CTAS, kOrdered>, 256, smem);
   }
   const long nunits = n_local * ntiles;
   // max_blocks_per_sm > 0 leaves room on every SM for a kernel of another stream (the pack of
   // the next panel in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
-  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS>)(
-      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, bulk);
+  CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS, kOrdered>)(
+      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, bulk, d_cuts);
 }
 
 template <typename T>
 static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, long n_local, long m_local, T *d_local,
-                                const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+                                const Geom &g, int max_blocks_per_sm, int ordered, const unsigned short *d_cuts, cudaStream_t s) {
   const int ntiles = tile_count(sizeof(T) == 8 ? 0 : 1, m_local);
-  // 6-item register sets, 3 blocks per SM (measured best on B200; 8- and 12-item sets spill or lose residency)
+  if (ntiles > kMaxCutTiles) d_cuts = nullptr;
+  // 6-item register sets, 3 blocks per SM (measured best on B200; 8- and 12-item sets spill or lose residency).
+  // Which walk (B200, one launch): one tile per column (K1) ordered 1.71 ms, item-parallel 2.01; two row bands
+  // (K2 owner) 0.486 / 0.524 ms; four (NS owner) 2.44 / 2.18 ms — the atomics cost more per element than the
+  // barrier per item until a block's share of an item falls to a quarter of its rows.
   if (ntiles == 1)
-    launch_tile_variant<T, false, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
+  else if (ordered || ntiles < 3)
+    launch_tile_variant<T, true, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
   else
-    launch_tile_variant<T, true, 6, 3>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, s);
+    launch_tile_variant<T, true, 6, 3, false>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
-                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, cudaStream_t s) {
+                       long n_local, long m_local, const Geom &g, int max_blocks_per_sm, int ordered,
+                       const unsigned short *d_cuts, cudaStream_t s) {
   if (nitems <= 0) return;
   switch (dtype) {
-    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, s); break;
-    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, s); break;
-    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, s); break;
+    case 0: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<double *>(d_local), g, max_blocks_per_sm, ordered, d_cuts, s); break;
+    case 1: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<float *>(d_local), g, max_blocks_per_sm, ordered, d_cuts, s); break;
+    default: launch_apply_tile_t(d_recs, d_col_start, n_local, m_local, static_cast<int *>(d_local), g, max_blocks_per_sm, ordered, d_cuts, s); break;
   }
 }
 

@@ -66,15 +66,19 @@ void launch_sort(void *d_temp, size_t temp_bytes, const uint32_t *keys_in, uint3
                  cudaStream_t s);
 // (5b) sorted items -> ItemRec (absolute pointers) + start of every destination column's run
 int tile_count(int dtype, long m_local);  // column tiles stacked over the local rows
+// d_cuts (cuts_bytes() > 0: local blocks of several row bands): where every item's rows cross the band boundaries
+size_t cuts_bytes(int dtype, long m_local, long nitems);
 void launch_build_recs(int dtype, const Seg *d_segs, const uint32_t *d_keys, const uint64_t *d_items,
-                       long nitems, ItemRec *d_recs, long n_local, long *d_col_start, cudaStream_t s);
+                       long nitems, ItemRec *d_recs, long n_local, long *d_col_start, unsigned short *d_cuts,
+                       long m_local, cudaStream_t s);
 // (6a) scatter-add with RED.ADD, one warp per item (apply<T>, reference :178-187)
 void launch_apply_red(int dtype, const ItemRec *d_recs, long nitems, long elements, void *d_local, const Geom &g,
                       cudaStream_t s);
-// (6b) column-tile scatter-add in shared memory: no atomics, fixed order (bit-exact run to run)
+// (6b) column-tile scatter-add in shared memory. ordered: items strictly in sorted order, no atomics (bit-exact run
+// to run); otherwise item-parallel with shared-memory atomics (order-free, faster on tall blocks)
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems,
                        void *d_local, long n_local, long m_local, const Geom &g, int max_blocks_per_sm,
-                       cudaStream_t s);
+                       int ordered, const unsigned short *d_cuts, cudaStream_t s);
 // COO path for elemental updates: local[inds[k]] += vals[k]
 void launch_apply_coo(int dtype, const long *d_inds, const void *d_vals, long n, void *d_local,
                       cudaStream_t s);

@@ -244,9 +244,9 @@ struct CooBin {
 
 // device buffers of one scatter-add batch (one per pipelined panel)
 struct ApplyWork {
-  DevBuf msgs, segs, keys0, keys1, items0, items1, sort_tmp, recs, col_start;
+  DevBuf msgs, segs, keys0, keys1, items0, items1, sort_tmp, recs, col_start, cuts;
   void release() {
-    DevBuf *b[] = {&msgs, &segs, &keys0, &keys1, &items0, &items1, &sort_tmp, &recs, &col_start};
+    DevBuf *b[] = {&msgs, &segs, &keys0, &keys1, &items0, &items1, &sort_tmp, &recs, &col_start, &cuts};
     for (DevBuf *x : b) x->release();
   }
 };
@@ -334,7 +334,9 @@ struct cm_matrix {
   int profiling = 0;
   int keep_wire = 0;
   int apply_kernel = 0;        // 0 auto, 1 RED, 2 column tiles
-  double tile_density = 0.25;  // auto: tile when (elements / local block elements) >= this
+  // auto: tile when (elements / local block elements) >= this. B200, NS-owner shape (4 GiB block) at 0.125:
+  // tile 1.61 ms, RED 1.93 ms per commit; K3's cold owners at 0.056: RED
+  double tile_density = 0.125;
 
   // staged updates
   std::vector<UpdDesc> descs;
@@ -593,14 +595,17 @@ int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, lon
   }
   CM_TRY(w.recs.ensure(sizeof(ItemRec) * (size_t)nitems));
   if (tile) CM_TRY(w.col_start.ensure(8 * (size_t)(M->n_local + 1)));
+  const size_t cb = tile ? cuts_bytes(M->dtype, M->m_local, nitems) : 0;
+  if (cb) CM_TRY(w.cuts.ensure(cb));
+  unsigned short *cuts = cb ? w.cuts.as<unsigned short>() : nullptr;
   launch_build_recs(M->dtype, w.segs.as<Seg>(), keys, items, nitems, w.recs.as<ItemRec>(), M->n_local,
-                    tile ? w.col_start.as<long>() : nullptr, st);
+                    tile ? w.col_start.as<long>() : nullptr, cuts, M->m_local, st);
   M->stats.kernel_launches += 1;
   {
     ScopedTimer t(M, 0, elements, st);
     if (tile)
       launch_apply_tile(M->dtype, w.recs.as<ItemRec>(), w.col_start.as<long>(), nitems, M->d_local, M->n_local,
-                        M->m_local, M->g, max_blocks_per_sm, st);
+                        M->m_local, M->g, max_blocks_per_sm, M->deterministic, cuts, st);
     else
       launch_apply_red(M->dtype, w.recs.as<ItemRec>(), nitems, elements, M->d_local, M->g, st);
     M->stats.kernel_launches += 1;

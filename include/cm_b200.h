@@ -187,7 +187,10 @@ int cm_set_flush_threshold(cm_matrix *M, long elements);
 /* progress_interval, :529-545 — stored for API compatibility; there is no progress engine. */
 int cm_get_progress_interval(const cm_matrix *M);
 int cm_set_progress_interval(cm_matrix *M, int interval);
-/* deterministic-order mode: accumulation order fixed per element => bit-exact run to run */
+/* deterministic-order mode: accumulation order fixed per element => bit-exact run to run. Off (default), a
+ * local block taller than two shared-memory tiles (16384 fp64 rows) is scatter-added item-parallel with
+ * shared-memory atomics: the order in which updates meet on an element is then not fixed (neither is it in
+ * the reference, README.md:30-32); results agree within rounding. */
 int cm_set_deterministic(cm_matrix *M, int on);
 /* sort work items by destination column before the scatter-add (L2-resident sweep). on by
  * default; exposed so benches can show its effect. */
@@ -196,7 +199,7 @@ int cm_set_sorted_sweep(cm_matrix *M, int on);
 /* which scatter-add kernel a flush uses: 0 = auto (column tiles in shared memory when the
  * flush holds >= tile_density update elements per element of the local block, RED.ADD
  * otherwise), 1 = always RED.ADD, 2 = always column tiles. tile_density <= 0 keeps the
- * current value (default 0.25). Deterministic mode always uses column tiles. */
+ * current value (default 0.125). Deterministic mode always uses column tiles. */
 int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
 
 /* When the owner scatter-adds what commit() delivered (COLLECTIVE, nothing staged; extension — the

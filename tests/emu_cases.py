@@ -328,7 +328,7 @@ def k1_full_size_properties():
         ones = np.ones((256, 256))
         ix = np.stack([np.sort(rng.choice(8192, 256, replace=False)) for _ in range(U)]).astype(np.int64)
         jx = np.stack([np.sort(rng.choice(8192, 256, replace=False)) for _ in range(U)]).astype(np.int64)
-        M.set_flush_threshold(1 << 24)  # 257 updates per threshold flush: density just above / below 0.25
+        M.set_flush_threshold(1 << 23)  # 129 updates per threshold flush (density 0.126: tiles), 125 in the last one (0.122: RED)
         for sign in (ones, -ones):
             for u in range(U):
                 M.update_device(_ptr(sign), 256, 256, 256, False, _ptr(ix[u]), _ptr(jx[u]))
