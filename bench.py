@@ -454,6 +454,7 @@ def parity_leg(ctx, M, spec, data, ix, jx, n_upd):
 def measure_workload(ctx, args, wl, steps, warmup, main):
     torch, dist, cm = ctx.torch, ctx.dist, ctx.cm
     nranks, rank, device = ctx.nranks, ctx.rank, ctx.device
+    t_begin = time.perf_counter()
     spec = workload_spec(wl, nranks)
     esz = 8 if spec["dtype"] == 0 else 4
     M = cm.Matrix(spec["dtype"], spec["m"], spec["n"], spec["nprow"], spec["npcol"], spec["mb"], spec["nb"], spec["lld"])
@@ -591,6 +592,7 @@ def measure_workload(ctx, args, wl, steps, warmup, main):
                "pack_ms_per_step": max(r[4] for r in per_rank), "apply_ms_per_step": max(r[3] for r in per_rank),
                "scatter_add_kernel": roof["kernel"] if roof else None,
                "apply_policy": args.apply_policy if spec["deferred"] else "eager", "parity": parity,
+               "harness_seconds": time.perf_counter() - t_begin,  # input generation, warm-up, timed steps, latency probes, parity leg
                "_main": {"st": st, "roof": roof, "clocks": clocks, "e2e": e2e, "cpu": cpu, "wall": wall, "spec": spec,
                          "flush_threshold": M.flush_threshold(), "exchange": {1: "nccl", 2: "p2p"}.get(M.exchange_mode(), "none") if nranks > 1 else "none",
                          "step_bytes": step_bytes}}

@@ -887,7 +887,7 @@ struct alignas(16) Vec16 {
 template <typename T, bool kMulti, int BLK, int CTAS, bool kOrdered>
 __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restrict__ recs, const long *__restrict__ col_start,
                                                        long ncols, int ntiles, long m_local, T *local, Geom g, int bulk,
-                                                       const unsigned short *__restrict__ cuts) {
+                                                       const unsigned short *__restrict__ cuts, int strict) {
   CM_DYN_SMEM(smem_raw);
   TileSmem<T> &sm = *reinterpret_cast<TileSmem<T> *>(smem_raw);
   constexpr int kTileRows = TileSmem<T>::kTileRows;
@@ -980,8 +980,16 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
           const int *rows = sm.rows[j];
           const int n = sm.n[j], stride = sm.stride[j], mf = sm.mf[j];
           const int mask = mf & 0xff;
-          if (mf >> 8) {
-            if (tid == 0) {  // rows may repeat: one thread applies the item serially
+          if ((mf >> 8) && !strict) {
+            // rows may repeat (an index set that is not strictly increasing) and the order is free: every thread
+            // adds its element with a shared-memory atomic
+            if (tid < n) {
+              const int rr = __ldg(rows + tid) - r0;
+              if ((unsigned)rr < (unsigned)h && (mask == 0 || (mask == 1) == (rr + r0 <= thr)))
+                atomicAdd(sm.acc + rr, __ldg(v + (long)tid * stride));
+            }
+          } else if (mf >> 8) {
+            if (tid == 0) {  // deterministic mode: one thread applies the item serially, in index order
               for (int a = 0; a < n; ++a) {
                 const int rr = rows[a] - r0;
                 if ((unsigned)rr >= (unsigned)h) continue;
@@ -1050,7 +1058,8 @@ __global__ void __launch_bounds__(256, CTAS) k_apply_tile(const ItemRec *__restr
 
 template <typename T, bool kMulti, int BLK, int CTAS, bool kOrdered>
 static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, long n_local, int ntiles, long m_local,
-                                T *d_local, const Geom &g, int max_blocks_per_sm, const unsigned short *d_cuts, cudaStream_t s) {
+                                T *d_local, const Geom &g, int max_blocks_per_sm, const unsigned short *d_cuts, int strict,
+                                cudaStream_t s) {
   const size_t smem = sizeof(TileSmem<T>);
   static int resident = 0;
   const int bulk = 1;  // (0: per-thread write-back everywhere; kept for misaligned columns and the kernel-logic build)
@@ -1063,7 +1072,7 @@ static void launch_tile_variant(const ItemRec *d_recs, const long *d_col_start, 
   // the next panel in a pipelined commit)
   const long cap = max_blocks_per_sm > 0 ? (long)max_blocks_per_sm * kernel_sm_count() : (1L << 40);
   CM_LAUNCH((unsigned)std::min({nunits, (long)resident, cap}), 256, smem, s, k_apply_tile<T, kMulti, BLK, CTAS, kOrdered>)(
-      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, bulk, d_cuts);
+      d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, bulk, d_cuts, strict);
 }
 
 template <typename T>
@@ -1076,11 +1085,11 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   // (K2 owner) 0.486 / 0.524 ms; four (NS owner) 2.44 / 2.18 ms — the atomics cost more per element than the
   // barrier per item until a block's share of an item falls to a quarter of its rows.
   if (ntiles == 1)
-    launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
+    launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, ordered, s);
   else if (ordered || ntiles < 3)
-    launch_tile_variant<T, true, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
+    launch_tile_variant<T, true, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, ordered, s);
   else
-    launch_tile_variant<T, true, 6, 3, false>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, s);
+    launch_tile_variant<T, true, 6, 3, false>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, ordered, s);
 }
 
 void launch_apply_tile(int dtype, const ItemRec *d_recs, const long *d_col_start, long nitems, void *d_local,
