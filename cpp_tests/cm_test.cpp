@@ -147,6 +147,9 @@ template <typename T>
 bool randomSliceUpdates() {
   const long m = 2000, n = 1000, sm = 800, sn = 500;
   cm::ConvergentMatrix<T, NPROW, NPCOL, MB, NB, LLD> dist(m, n);
+  // the reference's default threshold (:73-75): as there, every 800 x 500 update exceeds it and is shipped from
+  // inside update() (:346, :614) — here: packed and stored into the owners' flush regions, applied by commit()
+  dist.bin_flush_threshold(10000);
   std::vector<T> want(m * n, T(0)), scale(m * n, T(0));
   std::vector<std::mt19937> gens;
   for (int r = 0; r < cm::rank_n(); ++r) gens.emplace_back(kSeed + 17 * r);
@@ -176,6 +179,7 @@ template <typename T>
 bool randomSliceUpdatesSymmetricFill() {
   const long m = 2000, sn = 500;
   cm::ConvergentMatrix<T, NPROW, NPCOL, MB, NB, LLD> dist(m, m);
+  dist.bin_flush_threshold(10000);  // the reference's default: every update is shipped from inside update()
   std::vector<T> want(m * m, T(0)), scale(m * m, T(0));
   std::vector<std::mt19937> gens;
   for (int r = 0; r < cm::rank_n(); ++r) gens.emplace_back(kSeed + 19 * r);

@@ -12,8 +12,10 @@
 //     reference :611); owner mapping, per-owner packing and the scatter-add run in CUDA
 //     kernels; there is no progress engine, so progress_interval() is stored but unused.
 //   * With several ranks the exchange happens inside commit() (the pack kernel stores into the
-//     owners' arenas over NVLink, or a grouped ncclSend/ncclRecv all-to-all-v);
-//     bin_flush_threshold() bounds the elements staged per local flush on one rank.
+//     owners' arenas over NVLink, or a grouped ncclSend/ncclRecv all-to-all-v) — and, as in the
+//     reference (:346, :614), inside update() once more than bin_flush_threshold() elements are
+//     staged: the rank then packs what it has staged and stores it into the owners' flush regions
+//     without any collective call; the owners apply it inside their next commit().
 //   * Process-grid coordinates are row-major (pgrid_row() = rank / NPCOL), which is what the
 //     reference's owner formula implies; its ctor's rank / NPROW (:409) is a defect for
 //     NPROW != NPCOL.
