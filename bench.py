@@ -65,10 +65,10 @@ def workload_spec(name, nranks):
                     dtype=0, m=65536, n=65536, nprow=nprow, npcol=npcol, mb=64, nb=64, lld=65536 // nprow,
                     m_u=512, n_u=512, U=1024, commit_every=256, skew=True)
     if name == "NS":  # BASELINE.json north_star target: N=65536, uniform random 512x512 updates
-        return dict(name=f"NS (north-star target): N=65536 f64 MB=NB=64 grid {nprow}x{npcol}, 1024 updates/rank of 512x512, "
+        return dict(name=f"NS (north-star target): N=65536 f64 MB=NB=64 grid {nprow}x{npcol}, 2048 updates/rank of 512x512 (K2's count), "
                          f"sorted unique random index sets, one commit (assemble, then commit: the reference's own usage)",
                     dtype=0, m=65536, n=65536, nprow=nprow, npcol=npcol, mb=64, nb=64, lld=65536 // nprow,
-                    m_u=512, n_u=512, U=1024, commit_every=0)
+                    m_u=512, n_u=512, U=2048, commit_every=0)
     if name == "K4":  # BASELINE.json configs[4]: tiny updates, many commits
         nprow, npcol = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
         return dict(name=f"K4: N=32768 f32 MB=NB=64 grid {nprow}x{npcol}, 125000 updates/rank of 32x32, commit every 1024",

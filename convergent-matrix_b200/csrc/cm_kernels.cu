@@ -1084,6 +1084,8 @@ static void launch_apply_tile_t(const ItemRec *d_recs, const long *d_col_start, 
   // Which walk (B200, one launch): one tile per column (K1) ordered 1.71 ms, item-parallel 2.01; two row bands
   // (K2 owner) 0.486 / 0.524 ms; four (NS owner) 2.44 / 2.18 ms — the atomics cost more per element than the
   // barrier per item until a block's share of an item falls to a quarter of its rows.
+  // (a 64-register build that lets three scatter-add blocks and a pack block of the next panel share an SM was
+  // measured at 2 GPUs: the scatter-add gained, the pack kernel lost more — both live on the L1 / LSU pipe)
   if (ntiles == 1)
     launch_tile_variant<T, false, 6, 3, true>(d_recs, d_col_start, n_local, ntiles, m_local, d_local, g, max_blocks_per_sm, d_cuts, ordered, s);
   else if (ordered || ntiles < 3)

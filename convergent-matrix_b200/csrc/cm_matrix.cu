@@ -337,6 +337,7 @@ struct cm_matrix {
   // auto: tile when (elements / local block elements) >= this. B200, NS-owner shape (4 GiB block) at 0.125:
   // tile 1.61 ms, RED 1.93 ms per commit; K3's cold owners at 0.056: RED
   double tile_density = 0.125;
+  double apply_share = 1.0;  // share of the local block's columns the scatter-add being issued can reach (one panel: 1 / panels)
 
   // staged updates
   std::vector<UpdDesc> descs;
@@ -376,6 +377,7 @@ struct cm_matrix {
   // B200, 8 GPUs: K1-weak 10.78 -> 9.39 ms per step, K3 23.4 -> 14.1 ms.
   int pipeline = 1;
   long pipeline_min_elems = 32L << 20;  // ... when the ranks stage at least this many elements each on average
+  long pipeline_owner_min_elems = 128L << 20;  // ... and the busiest owner receives at least this many (CM_B200_PIPELINE_MIN_ELEMS sets both)
   int npanel_cfg = 4;                   // column panels of a pipelined commit (CM_B200_PANELS, at most kMaxChunks)
   int pipeline_apply_blocks = 2;        // resident scatter-add blocks per SM while the next panel is being packed
                                         // (CM_B200_PIPELINE_APPLY_BLOCKS; 0 = no cap)
@@ -575,7 +577,8 @@ int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, lon
   const uint32_t *keys = w.keys0.as<uint32_t>();
   // which scatter-add: the column-tile kernel pays 2*s bytes per row of a touched column and no
   // atomics; RED pays one sector round trip per element. Dense flushes -> tile.
-  const double density = (double)elements / ((double)M->m_local * (double)M->n_local);
+  // (a panel of a pipelined commit only reaches its share of the block's columns)
+  const double density = (double)elements / ((double)M->m_local * (double)M->n_local * M->apply_share);
   bool tile = M->apply_kernel == 2 || (M->apply_kernel == 0 && density >= M->tile_density);
   if (M->deterministic) tile = true;
   // the column sort pays when the flush is big enough for L2 locality to matter; a small sparse
@@ -1050,7 +1053,18 @@ int commit_layout(cm_matrix *M, CommitPlan &cp) {
           total += counts[cp.cidx(src, k, d)].nelems;
           if (k > 0) later += counts[cp.cidx(src, k, d)].nelems;
         }
-    cp.pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total;
+    // ... and the busiest owner receives enough for its scatter-add to be worth hiding: every panel costs a
+    // stream-ordered barrier and a round of small kernels (B200, 8 GPUs: K2's commits of 67 Mi elements per owner
+    // 1.98 ms pipelined against 1.55 ms as one batch; NS, 268 Mi per owner, 6.05 against 6.26 ms; K1-weak, 655 Mi,
+    // 9.7 against 10.8 ms; K3's hot owner receives 243 Mi per commit)
+    long busiest = 0;
+    for (int d = 0; d < P; ++d) {
+      long got = 0;
+      for (int src = 0; src < P; ++src)
+        for (int k = 0; k < K; ++k) got += counts[cp.cidx(src, k, d)].nelems;
+      busiest = std::max(busiest, got);
+    }
+    cp.pipelined = total / P >= M->pipeline_min_elems && 2 * later >= total && busiest >= M->pipeline_owner_min_elems;
   }
   if (!cp.fl.empty()) cp.pipelined = false;  // flushed messages are applied with the commit's own, as one batch
   for (int src = 0; src < P; ++src)
@@ -1339,7 +1353,10 @@ int commit_deliver(cm_matrix *M, CommitPlan &cp) {
     CM_TRY(commit_stream_barrier(M, M->apply_stream));
     trace_mark(M, "deliver: panel landed", M->apply_stream);
     // all but the last panel's scatter-add share the SMs with the next panel's pack kernel
-    CM_TRY(apply_panels(M, cp, k, k + 1, false, M->work[k], M->apply_stream, k + 1 < cp.Kp ? M->pipeline_apply_blocks : 0));
+    M->apply_share = 1.0 / cp.Kp;
+    const int rc = apply_panels(M, cp, k, k + 1, false, M->work[k], M->apply_stream, k + 1 < cp.Kp ? M->pipeline_apply_blocks : 0);
+    M->apply_share = 1.0;
+    CM_TRY(rc);
     trace_mark(M, "deliver: panel applied", M->apply_stream);
   }
   if (M->profiling) {
@@ -1939,7 +1956,7 @@ int cm_create(cm_matrix **out, int dtype, long m, long n, long nprow, long npcol
     if (getenv("CM_B200_PIPELINE")) M->pipeline = atoi(getenv("CM_B200_PIPELINE")) != 0 ? 1 : 0;
     if (getenv("CM_B200_PIPELINE_APPLY_BLOCKS")) M->pipeline_apply_blocks = std::max(0, atoi(getenv("CM_B200_PIPELINE_APPLY_BLOCKS")));
     if (getenv("CM_B200_PANELS")) M->npanel_cfg = std::max(1, atoi(getenv("CM_B200_PANELS")));
-    if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
+    if (getenv("CM_B200_PIPELINE_MIN_ELEMS")) M->pipeline_min_elems = M->pipeline_owner_min_elems = atol(getenv("CM_B200_PIPELINE_MIN_ELEMS"));
     const char *env = getenv("CM_B200_EXCHANGE");  // "nccl" / "p2p" override, must agree on all ranks
     if (env && !strcmp(env, "nccl")) M->exchange_mode = 1;
     if (env && !strcmp(env, "p2p")) M->exchange_mode = 2;
