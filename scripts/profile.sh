@@ -12,7 +12,8 @@ cap() {  # cap <name> <kernel regex> <skip> <count> <cmd...>
 cap k1_tile k_apply_tile 3 1 $B --workload K1
 cap k2own_tile k_apply_tile 24 2 $B --workload K2own
 cap nsown1_tile k_apply_tile 3 1 $B --workload NSown1 --apply-kernel tile
-cap nsown_red k_apply_red 12 2 $B --workload NSown
+cap nsown_tile k_apply_tile 12 2 $B --workload NSown
+cap nsown_red k_apply_red 12 2 $B --workload NSown --apply-kernel red
 cap k4own_red k_apply_red 400 2 $B --workload K4own
 cap pack_loopback k_pack 16 2 python scripts/profile_pack.py
 # launch list of the K1 step (shares)
