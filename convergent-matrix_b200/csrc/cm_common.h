@@ -118,6 +118,7 @@ struct MsgCounts {
   long ncoo;    // elemental updates (COO lane) from this source to this owner; panel 0 only
   long nflushed;  // messages this source's threshold flushes packed for this owner since the last commit
                   // (reference flush(thresh) inside update(), :346, :614); panel 0 only
+  long nadj;      // of nelems: elements whose local row directly follows the previous row of their segment
 };
 
 // Layout of one segment's values inside a message: column-major nr x nc with column stride

@@ -68,17 +68,28 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
   int *__restrict__ off_out = (axis == 0 ? ma.roff : ma.coff) + (long)u * (np + 1);
 
   const int tid = threadIdx.x;
+  // radj (rows only): per owner row, how many of its rows directly follow the previous index of the update (same
+  // MB block, so the same owner and the next local row). The owner's choice between the two scatter-adds needs it:
+  // RED pays per 32-byte sector, and a run of consecutive rows shares its sectors.
+  __shared__ int adjc[kMaxGridDim];
   if (np == 1) {  // single group along this axis: identity grouping
     bool rep = false;
+    int adj = 0;
+    if (tid == 0) adjc[0] = 0;
+    __syncthreads();
     for (int k = tid; k < len; k += blockDim.x) {
       lout[k] = (int)local_index(idx[k], blk, 1);
       pout[k] = k;
       if (k > 0) rep |= idx[k] <= idx[k - 1];
+      if (k > 0) adj += idx[k] == idx[k - 1] + 1;
     }
     if (axis == 0 && rep) atomicOr(&ma.uflags[u], kSegRowsMayRepeat);
+    if (axis == 0 && adj) atomicAdd(&adjc[0], adj);
+    __syncthreads();
     if (tid == 0) {
       off_out[0] = 0;
       off_out[1] = len;
+      if (axis == 0) ma.radj[(long)u * 2] = adjc[0];
     }
     return;
   }
@@ -107,6 +118,7 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
   if (tid < np) {
     cnt[tid] = 0;
     run[tid] = 0;
+    adjc[tid] = 0;
   }
   for (int k = tid; k < 8 * kMaxGridDim; k += blockDim.x) (&wcnt[0][0])[k] = 0;
   __syncthreads();
@@ -114,10 +126,15 @@ __global__ void __launch_bounds__(256) k_map_group(const UpdDesc *__restrict__ d
   for (int k = tid; k < len; k += blockDim.x) atomicAdd(&cnt[group_of(idx[k])], 1);
   if (axis == 0) {
     bool rep = false;
-    for (int k = tid + 1; k < len; k += blockDim.x) rep |= idx[k] <= idx[k - 1];
+    for (int k = tid + 1; k < len; k += blockDim.x) {
+      const long a = idx[k - 1], b = idx[k];
+      rep |= b <= a;
+      if (b == a + 1 && b % blk != 0) atomicAdd(&adjc[owner_coord(b, blk, npo)], 1);
+    }
     if (rep) atomicOr(&ma.uflags[u], kSegRowsMayRepeat);
   }
   __syncthreads();
+  if (axis == 0 && tid < np) ma.radj[(long)u * (np + 1) + tid] = adjc[tid];
   if (tid == 0) {
     int acc = 0;
     for (int p = 0; p < np; ++p) {
@@ -173,8 +190,8 @@ void launch_map_group(const UpdDesc *d_descs, int nupd, const Geom &g, const Pan
 // (2) per-owner exclusive scans over the staged updates. grid = P blocks (one per owner).
 // ------------------------------------------------------------------------------------
 struct Long3 {
-  long a, b, c, e;
-  __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e}; }
+  long a, b, c, e, f;
+  __host__ __device__ Long3 operator+(const Long3 &o) const { return Long3{a + o.a, b + o.b, c + o.c, e + o.e, f + o.f}; }
 };
 
 __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom g, MapArenas ma, ScanArenas sa,
@@ -185,17 +202,17 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom 
   const int panel = blockIdx.y;
   const int P = gridDim.x;
   if (panel >= pp.npanel) {  // unused panel slot: an empty message
-    if (threadIdx.x == 0) sa.totals[panel * P + dst] = MsgCounts{0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) sa.totals[panel * P + dst] = MsgCounts{0, 0, 0, 0, 0, 0, 0, 0};
     return;
   }
   const int p = dst / (int)g.npcol, q = dst % (int)g.npcol;
   const int gq = panel * (int)g.npcol + q;  // column group of (panel, owner column)
   const int npr = (int)g.nprow + 1, npc = (int)g.npcol * pp.npanel + 1;
   const long obase = ((long)panel * P + dst) * nupd;
-  Long3 running{0, 0, 0, 0};
+  Long3 running{0, 0, 0, 0, 0};
   for (int c0 = 0; c0 < nupd; c0 += 256) {
     const int u = c0 + threadIdx.x;
-    Long3 v{0, 0, 0, 0};
+    Long3 v{0, 0, 0, 0, 0};
     if (u < nupd) {
       const int nr = ma.roff[(long)u * npr + p + 1] - ma.roff[(long)u * npr + p];
       const int nc = ma.coff[(long)u * npc + gq + 1] - ma.coff[(long)u * npc + gq];
@@ -205,10 +222,11 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom 
         v.b = nr + nc;
         v.c = (long)nc * ((nr + kRowChunk - 1) / kRowChunk);
         v.e = nv;
+        v.f = (long)ma.radj[(long)u * npr + p] * nc;
       }
     }
     Long3 excl, total;
-    BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0, 0}, cub::Sum(), total);
+    BlockScan(tmp).ExclusiveScan(v, excl, Long3{0, 0, 0, 0, 0}, cub::Sum(), total);
     if (u < nupd) {
       sa.valoff[obase + u] = running.a + excl.a;
       sa.idxoff[obase + u] = running.b + excl.b;
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(256) k_scan_dest(int nupd, PanelPlan pp, Geom 
   // a message without values ships nothing at all (no segment table either): nseg = 0
   if (threadIdx.x == 0)
     sa.totals[panel * P + dst] = MsgCounts{running.a, running.b, running.a ? (long)nupd : 0, running.c, running.e,
-                                           panel == 0 ? coo_counts[dst] : 0, panel == 0 ? coo_counts[P + dst] : 0};
+                                           panel == 0 ? coo_counts[dst] : 0, panel == 0 ? coo_counts[P + dst] : 0, running.f};
 }
 
 void launch_scan(int nupd, const PanelPlan &pp, const Geom &g, const MapArenas &ma, const ScanArenas &sa,

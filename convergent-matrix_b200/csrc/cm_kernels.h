@@ -26,6 +26,7 @@ struct MapArenas {
   int *cpos;
   int *coff;  // (npanel*npcol+1) per update: column groups gq = panel * npcol + owner column
   int *uflags;  // per update: kSegRowsMayRepeat if ix is not strictly increasing (zeroed by the caller)
+  int *radj;    // (nprow+1) per update: rows of each owner row that directly follow the update's previous index
 };
 
 // per-(owner, update) exclusive scans produced by k_scan_dest

@@ -318,7 +318,7 @@ struct cm_matrix {
   struct PendMsg {
     const char *meta;
     const void *vals;
-    long nseg, nitems, nelems;
+    long nseg, nitems, nelems, nadj;
   };
   int apply_policy = 0;               // CM_APPLY_EAGER / CM_APPLY_DEFERRED / CM_APPLY_BACKGROUND
   bool bg_running = false;            // a background scatter-add of the log is (possibly) still on the apply stream
@@ -364,7 +364,7 @@ struct cm_matrix {
   DevBuf d_fill_ix, d_fill_jx;
 
   // device work buffers
-  DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_coo_tmp;
+  DevBuf d_descs, d_item_base, d_rl, d_rpos, d_roff, d_cl, d_cpos, d_coff, d_uflags, d_radj, d_coo_tmp;
   DevBuf d_valoff, d_idxoff, d_itemoff, d_totals;
   DevBuf d_send_vals, d_send_meta, d_recv_vals, d_recv_meta, d_send_coo, d_recv_coo;
   DevBuf d_counts_all, d_dst_ptrs, d_coo_counts;
@@ -554,6 +554,7 @@ int upload_staged(cm_matrix *M, int npanel = 1) {
   CM_TRY(M->d_roff.ensure(4 * (size_t)npr * std::max(nupd, 1)));
   CM_TRY(M->d_coff.ensure(4 * (size_t)npc * std::max(nupd, 1)));
   CM_TRY(M->d_uflags.ensure(4 * (size_t)std::max(nupd, 1)));
+  CM_TRY(M->d_radj.ensure(4 * (size_t)npr * std::max(nupd, 1)));
   CM_CUDA_TRY(cudaMemsetAsync(M->d_uflags.p, 0, 4 * (size_t)std::max(nupd, 1), M->stream));
   return CM_OK;
 }
@@ -567,11 +568,12 @@ MapArenas map_arenas(cm_matrix *M) {
   ma.cpos = M->d_cpos.as<int>();
   ma.coff = M->d_coff.as<int>();
   ma.uflags = M->d_uflags.as<int>();
+  ma.radj = M->d_radj.as<int>();
   return ma;
 }
 
 // sort (optional) + scatter-add over nitems (key,item) pairs sitting in w.keys0 / w.items0
-int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, int max_blocks_per_sm = 0) {
+int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, long elements, long adjacent, int max_blocks_per_sm = 0) {
   if (nitems <= 0) return CM_OK;
   const uint64_t *items = w.items0.as<uint64_t>();
   const uint32_t *keys = w.keys0.as<uint32_t>();
@@ -579,7 +581,13 @@ int sort_and_apply(cm_matrix *M, ApplyWork &w, cudaStream_t st, long nitems, lon
   // atomics; RED pays one sector round trip per element. Dense flushes -> tile.
   // (a panel of a pipelined commit only reaches its share of the block's columns)
   const double density = (double)elements / ((double)M->m_local * (double)M->n_local * M->apply_share);
-  bool tile = M->apply_kernel == 2 || (M->apply_kernel == 0 && density >= M->tile_density);
+  // RED pays per 32-byte sector it touches, the tile kernel per element plus one sweep of the columns it reaches:
+  // with c = the share of elements whose row directly follows the previous one (runs of consecutive indices, K3),
+  // RED costs about 28.8 - 25 c ps per element, tiles 2 ps per element + 3.2 ps per element of the block (B200:
+  // NS-owner shape, c = 0: 28.8 / break-even at 0.12 hits per element; K3's hot owner, c = 0.98: RED 3.8 ps)
+  const double c = elements > 0 ? std::min(1.0, (double)adjacent / (double)elements) : 0.0;
+  const double tile_from = M->tile_density * 26.8 / (26.8 - 25.0 * c);
+  bool tile = M->apply_kernel == 2 || (M->apply_kernel == 0 && density >= tile_from);
   if (M->deterministic) tile = true;
   // the column sort pays when the flush is big enough for L2 locality to matter; a small sparse
   // flush (latency-bound commits of tiny updates) goes straight to RED
@@ -679,7 +687,7 @@ int flush_direct(cm_matrix *M, bool sync = true) {
       M->stats.kernel_launches += 2;
     }
     trace_mark(M, "flush: mapped, items built");
-    CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0));
+    CM_TRY(sort_and_apply(M, w, M->stream, nitems, M->staged_elems, 0, 0));
     trace_mark(M, "flush: scatter-add done");
     M->stats.elements_applied += M->staged_elems;
   }
@@ -784,8 +792,8 @@ int ensure_recv_arenas(cm_matrix *M, const std::vector<size_t> &need_vals, const
 }
 
 // owner side: messages -> Seg table + (key, item) pairs -> sort -> scatter-add
-int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long item_total, long elem_total, long max_seg,
-                   ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
+int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long item_total, long elem_total, long adj_total,
+                   long max_seg, ApplyWork &w, cudaStream_t st, int max_blocks_per_sm) {
   if (msgs.empty()) return CM_OK;
   CM_TRY(w.msgs.ensure(sizeof(MsgRef) * msgs.size()));
   CM_CUDA_TRY(cudaMemcpyAsync(w.msgs.p, msgs.data(), sizeof(MsgRef) * msgs.size(), cudaMemcpyHostToDevice, st));
@@ -795,7 +803,7 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
   launch_build_recv(M->dtype, w.msgs.as<MsgRef>(), (int)msgs.size(), max_seg, w.segs.as<Seg>(), w.keys0.as<uint32_t>(),
                     w.items0.as<uint64_t>(), st);
   M->stats.kernel_launches += 1;
-  CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, max_blocks_per_sm));
+  CM_TRY(sort_and_apply(M, w, st, item_total, elem_total, adj_total, max_blocks_per_sm));
   M->stats.elements_applied += elem_total;
   return CM_OK;
 }
@@ -805,14 +813,14 @@ int apply_messages(cm_matrix *M, std::vector<MsgRef> &msgs, long seg_total, long
 int apply_list(cm_matrix *M, const cm_matrix::PendMsg *first, const cm_matrix::PendMsg *last, ApplyWork &w, cudaStream_t st,
                int max_blocks_per_sm) {
   std::vector<MsgRef> msgs;
-  long seg_total = 0, item_total = 0, elem_total = 0, max_seg = 0;
+  long seg_total = 0, item_total = 0, elem_total = 0, adj_total = 0, max_seg = 0;
   for (const cm_matrix::PendMsg *pm = first; pm != last; ++pm) {
     if (pm->nseg > M->max_staged_updates)
       return fail(CM_ERR_INVALID, "a message holds %ld segments; the limit per scatter-add is %ld", pm->nseg, M->max_staged_updates);
     if (seg_total + pm->nseg > M->max_staged_updates) {
-      CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm));
+      CM_TRY(apply_messages(M, msgs, seg_total, item_total, elem_total, adj_total, max_seg, w, st, max_blocks_per_sm));
       msgs.clear();
-      seg_total = item_total = elem_total = max_seg = 0;
+      seg_total = item_total = elem_total = adj_total = max_seg = 0;
     }
     MsgRef m;
     m.meta = pm->meta;
@@ -822,10 +830,11 @@ int apply_list(cm_matrix *M, const cm_matrix::PendMsg *first, const cm_matrix::P
     seg_total += pm->nseg;
     item_total += pm->nitems;
     elem_total += pm->nelems;
+    adj_total += pm->nadj;
     max_seg = std::max(max_seg, pm->nseg);
     msgs.push_back(m);
   }
-  return apply_messages(M, msgs, seg_total, item_total, elem_total, max_seg, w, st, max_blocks_per_sm);
+  return apply_messages(M, msgs, seg_total, item_total, elem_total, adj_total, max_seg, w, st, max_blocks_per_sm);
 }
 
 // a background scatter-add (apply stream) must have finished before anything else touches the local
@@ -1214,7 +1223,7 @@ cm_matrix::PendMsg flushed_ref(cm_matrix *M, const CommitPlan &cp, size_t i) {
     meta = static_cast<char *>(M->peer_meta[cp.me]) + cp.fl_pos_m[i];
     vals = static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.fl_pos_v[i] * M->esz;
   }
-  return cm_matrix::PendMsg{meta, vals, f.c.nseg, f.c.nitems, f.c.nelems};
+  return cm_matrix::PendMsg{meta, vals, f.c.nseg, f.c.nitems, f.c.nelems, f.c.nadj};
 }
 
 // what this commit delivered to THIS rank, in stream order per source: the messages of threshold flushes
@@ -1229,7 +1238,7 @@ void delivered_messages(cm_matrix *M, const CommitPlan &cp, int k0, int k1, bool
       if (c.nvals == 0) continue;
       out.push_back(cm_matrix::PendMsg{static_cast<char *>(M->peer_meta[cp.me]) + cp.rbase_m[cp.ridx(cp.me, k, src)],
                                        static_cast<char *>(M->peer_vals[cp.me]) + (size_t)cp.rbase_v[cp.ridx(cp.me, k, src)] * M->esz,
-                                       c.nseg, c.nitems, c.nelems});
+                                       c.nseg, c.nitems, c.nelems, c.nadj});
     }
 }
 
@@ -1995,7 +2004,7 @@ int cm_destroy(cm_matrix *M) {
   M->payload_arena.release();
   M->index_arena.release();
   DevBuf *bufs[] = {&M->d_fill_ix, &M->d_fill_jx, &M->d_descs, &M->d_item_base, &M->d_rl, &M->d_rpos, &M->d_roff,
-                    &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
+                    &M->d_cl, &M->d_cpos, &M->d_coff, &M->d_uflags, &M->d_radj, &M->d_coo_tmp, &M->d_valoff, &M->d_idxoff, &M->d_itemoff, &M->d_totals,
                     &M->d_send_vals, &M->d_send_meta, &M->d_recv_vals,
                     &M->d_recv_meta, &M->d_send_coo, &M->d_recv_coo, &M->d_counts_all, &M->d_dst_ptrs, &M->d_coo_counts};
   for (DevBuf *b : bufs) b->release();

@@ -55,6 +55,7 @@ CASES = [
     (T, "test_save_load_reference_file_format", [(1, None), (4, None)]),
     (T, "test_multi_rank_threshold_flush", [(2,), (1,)]),
     (T, "test_flush_call_and_staging_limit_several_ranks", [()]),
+    (T, "test_scatter_add_choice_follows_row_contiguity", [()]),
 ] + [(E, name, params) for name, params in E.CASES]
 
 NAMES = [name for _, name, _ in CASES]

@@ -497,3 +497,28 @@ def test_flush_call_and_staging_limit_several_ranks():
     got = run_cuda(cfg, steps, flush_every=3)
     assert all(st["flushes"] >= 6 for st in got["stats"])
     assert_blocks_match(cfg, got, want)
+
+
+def test_scatter_add_choice_follows_row_contiguity():
+    """The owner picks the scatter-add per flush from what the sources report: hits per element of the block AND the
+    share of elements whose row directly follows the previous one. Runs of consecutive indices (K3's clustered sets)
+    make RED cheap (whole sectors), so the same volume that goes to the tile kernel with scattered rows stays on RED."""
+    cfg = Cfg(cm.F64, 2048, 2048, 2, 2, 64, 64, 1024)
+    rng = np.random.default_rng(79)
+
+    def runs(hi, k):  # k / 64 runs of 64 consecutive indices at block boundaries
+        blocks = np.sort(rng.choice(hi // 64, size=k // 64, replace=False))
+        return (blocks[:, None] * 64 + np.arange(64)[None, :]).reshape(-1).astype(np.int64)
+
+    for clustered in (True, False):
+        steps = []
+        for u in range(16):
+            for r in range(cfg.P):
+                ix = runs(cfg.m, 256) if clustered else sorted_unique(rng, cfg.m, 256)
+                jx = runs(cfg.n, 256) if clustered else sorted_unique(rng, cfg.n, 256)
+                steps.append(("slice", r, rand_payload(rng, cfg.dtype, (256, 256)), 256, 256, 256, False, ix, jx))
+        steps.append(("commit",))
+        got = run_cuda(cfg, steps)  # ~1 hit per element of every block
+        assert_blocks_match(cfg, got, run_checker(cfg, steps))
+        for st in got["stats"]:
+            assert (st["tile_launches"] == 0) == clustered, (clustered, st)

@@ -34,6 +34,7 @@ GROUPS = [
     "test_save_load_reference_file_format",
     "test_multi_rank_threshold_flush",
     "test_flush_call_and_staging_limit_several_ranks",
+    "test_scatter_add_choice_follows_row_contiguity",
     "device_api_single_rank",
     "pipelined_commit_chunks",
     "panels_wire_and_blocks",
