@@ -82,10 +82,13 @@ def test_both_exchange_modes(mode):
 
 def test_pipelined_commit_chunks():
     """a commit big enough to be cut into column panels and pipelined (scatter-add of panel k on the
-    apply stream while panel k+1 is packed across the exchange): > 32 Mi elements staged per rank"""
+    apply stream while panel k+1 is packed across the exchange): > 32 Mi elements staged per rank, and the owners'
+    bar (the busiest one receives 128 Mi by default) lowered to the same value"""
     import torch
     mode = 2
     cfg = Cfg(cm.F32, 1024, 1024, 2, 2, 64, 64, 512)
+    old_env = os.environ.get("CM_B200_PIPELINE_MIN_ELEMS")
+    os.environ["CM_B200_PIPELINE_MIN_ELEMS"] = str(32 << 20)
     world = cm.LoopbackWorld(4, 0)
     try:
         mats = world.run(lambda r: cm.Matrix(*cfg.args()))
@@ -126,6 +129,10 @@ def test_pipelined_commit_chunks():
         world.run(lambda r: mats[r].destroy())
     finally:
         world.close()
+        if old_env is None:
+            os.environ.pop("CM_B200_PIPELINE_MIN_ELEMS", None)
+        else:
+            os.environ["CM_B200_PIPELINE_MIN_ELEMS"] = old_env
 
 
 @pytest.mark.parametrize("grid", [(2, 3, 4, 8, 64, 100, 190), (3, 2, 8, 4, 96, 250, 150), (2, 4, 64, 64, 1024, 2000, 3000),
