@@ -24,7 +24,10 @@ from scenario import Cfg, run_checker  # noqa: E402
 
 
 def main():
-    for name, spec in SCENARIOS.items():
+    only = set(sys.argv[1:])  # fixture names to (re)generate; none = all (the reference applies messages in
+    for name, spec in SCENARIOS.items():  # arrival order, so regenerated blocks may differ in the last bit)
+        if only and name not in only:
+            continue
         cfg = Cfg(*spec["cfg"])
         steps = build_steps(spec)
         out = run_checker(cfg, steps, kind="ref", wire=True, threshold=spec.get("threshold"))

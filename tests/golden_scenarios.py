@@ -17,6 +17,10 @@ SCENARIOS = {
                           threshold=1 << 30),
     "default_threshold_f64": dict(cfg=(cm.F64, 160, 120, 2, 2, 64, 64, 1024), seed=104, kind="slices", nupd=3, m_u=150,
                                   n_u=110, threshold=None),
+    # both sides at the reference's default threshold: every bin / every rank ships from inside update() (:346, :614),
+    # several messages per (source, owner) and commit; the concatenated streams must still be the reference's
+    "threshold_flush_f64": dict(cfg=(cm.F64, 160, 120, 2, 2, 64, 64, 1024), seed=110, kind="slices", nupd=6, m_u=150,
+                                n_u=110, commit_every=3, threshold=10000, ours_threshold=10000),
     "single_rank_f64": dict(cfg=(cm.F64, 60, 150, 1, 1, 4, 8, 64), seed=105, kind="slices", nupd=4, m_u=30, n_u=40,
                             threshold=1 << 30),
     "nonsquare_grid_f64": dict(cfg=(cm.F64, 100, 190, 2, 3, 4, 8, 64), seed=109, kind="slices", nupd=2, m_u=40, n_u=50,
@@ -39,7 +43,8 @@ def build_steps(spec):
                 m_u, n_u = min(spec["m_u"], cfg.m), min(spec["n_u"], cfg.n)
                 ix, jx = sorted_unique(rng, cfg.m, m_u), sorted_unique(rng, cfg.n, n_u)
                 steps.append(("slice", r, rand_payload(rng, cfg.dtype, (n_u, m_u)), m_u, n_u, m_u, False, ix, jx))
-            steps.append(("commit",))
+            if (u + 1) % spec.get("commit_every", 1) == 0 or u + 1 == spec["nupd"]:
+                steps.append(("commit",))
     elif kind == "elements":
         for it in range(2):
             for r in range(cfg.P):

@@ -255,14 +255,16 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def test_cuda_matches_reference_golden(name):
     spec = SCENARIOS[name]
     cfg, golden = load_golden(os.path.join(GOLDEN, name + ".npz"))
-    got = run_cuda(cfg, build_steps(spec), wire=True)
+    got = run_cuda(cfg, build_steps(spec), wire=True, threshold=spec.get("ours_threshold"))
+    if "ours_threshold" in spec:
+        assert all(st["flushes"] > 0 for st in got["stats"])
     if cfg.nprow != cfg.npcol:
         golden = dict(golden, m_local=got["m_local"])  # reference ctor defect, SURVEY.md Appendix C-1
     assert_blocks_match(cfg, got, golden)
     if "wire_inds" in golden:
         assert_wire_matches_golden(cfg, got, golden, multiset=(spec["kind"] == "symmetric"))
     # and through the direct / non-captured path
-    assert_blocks_match(cfg, run_cuda(cfg, build_steps(spec)), golden)
+    assert_blocks_match(cfg, run_cuda(cfg, build_steps(spec), threshold=spec.get("ours_threshold")), golden)
 
 
 def test_accessors_descriptor_host_mirror_and_knobs():
