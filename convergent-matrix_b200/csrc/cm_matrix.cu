@@ -290,6 +290,7 @@ struct cm_matrix {
   size_t local_elems = 0;
   void *d_local = nullptr;
   void *h_mirror = nullptr;
+  bool mirror_pinned = false;  // page-locked (D2H at the link rate) unless that allocation failed
   bool mirror_valid = false;
   std::vector<void *> peer_local;  // remote read (operator(), :585-596): IPC / same-process
   std::vector<bool> peer_ipc_open;
@@ -2000,7 +2001,7 @@ int cm_destroy(cm_matrix *M) {
   release_flush_regions(M);        // (contains a barrier)
   M->ctx->tp->barrier(M->stream);  // nobody still reads my block
   cudaFree(M->d_local);
-  free(M->h_mirror);
+  if (M->mirror_pinned) cudaFreeHost(M->h_mirror); else free(M->h_mirror);
   M->payload_arena.release();
   M->index_arena.release();
   DevBuf *bufs[] = {&M->d_fill_ix, &M->d_fill_jx, &M->d_descs, &M->d_item_base, &M->d_rl, &M->d_rpos, &M->d_roff,
@@ -2158,7 +2159,14 @@ int cm_local_data_copy(cm_matrix *M, void *dst_host) {
 int cm_local_data_host(cm_matrix *M, const void **out) {
   if (!M || !out) return fail(CM_ERR_INVALID, "null argument");
   if (!M->h_mirror) {
-    M->h_mirror = malloc(M->local_elems * M->esz);
+    // page-locked: the copy of a 512 MiB block runs at the PCIe rate instead of through the driver's staging buffer
+    if (cudaMallocHost(&M->h_mirror, M->local_elems * M->esz) == cudaSuccess) {
+      M->mirror_pinned = true;
+    } else {
+      cudaGetLastError();
+      M->h_mirror = malloc(M->local_elems * M->esz);
+      M->mirror_pinned = false;
+    }
     if (!M->h_mirror) return fail(CM_ERR_NOMEM, "host mirror allocation failed");
     M->mirror_valid = false;
   }
