@@ -77,7 +77,7 @@ def test_cpp_reference_suite_port_on_the_test_double(emu_lib):
 
 def test_fuzz_scenarios(emu_lib):
     """a bounded slice of tests/emu/fuzz.py: random geometries / update shapes / index styles / knobs
-    (exchange modes, column panels, flag barrier, both scatter-add kernels) against the oracle"""
+    (exchange modes, column panels, threshold flushes on several ranks, apply policies, both scatter-add kernels) against the oracle"""
     p = subprocess.run([sys.executable, os.path.join(EMU, "fuzz.py"), "--seed", "0", "--count", "80"], capture_output=True,
                        text=True, timeout=900)
     assert p.returncode == 0 and "fails: 0" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
