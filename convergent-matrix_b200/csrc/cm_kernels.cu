@@ -24,7 +24,7 @@
 // is never part of libcm_b200.so). Under nvcc they are the plain CUDA spellings.
 #ifndef CM_EMU
 #define CM_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
-#define CM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define CM_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #endif
 
 namespace cmb {

@@ -83,7 +83,10 @@ BlockState::~BlockState() {
 static thread_local BlockState tl_block;
 
 ThreadCoords &coords() { return tl_block.tc; }
-unsigned char *dyn_smem() { return tl_block.smem.data(); }
+// dynamic shared memory starts on a 1024-byte boundary, as on the device
+unsigned char *dyn_smem() {
+  return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tl_block.smem.data()) + 1023) & ~(uintptr_t)1023);
+}
 
 static void yield() {
   BlockState &b = tl_block;
@@ -192,7 +195,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &t
   b.nthreads = nthreads;
   b.fibers.assign(nthreads, Fiber());
   b.warps.assign((nthreads + 31) / 32, WarpState());
-  b.smem.assign(smem ? smem : 1, 0xCD);  // shared memory starts out undefined on a GPU
+  b.smem.assign((smem ? smem : 1) + 1024, 0xCD);  // shared memory starts out undefined on a GPU (+ room to align its start)
   b.tc.blockDim = block;
   b.tc.gridDim = grid;
   for (unsigned bz = 0; bz < grid.z; ++bz)
