@@ -196,10 +196,12 @@ int cm_set_deterministic(cm_matrix *M, int on);
  * default; exposed so benches can show its effect. */
 int cm_set_sorted_sweep(cm_matrix *M, int on);
 
-/* which scatter-add kernel a flush uses: 0 = auto (column tiles in shared memory when the
- * flush holds >= tile_density update elements per element of the local block, RED.ADD
- * otherwise), 1 = always RED.ADD, 2 = always column tiles. tile_density <= 0 keeps the
- * current value (default 0.125). Deterministic mode always uses column tiles. */
+/* which scatter-add kernel a flush uses: 0 = auto, 1 = always RED.ADD, 2 = always column tiles in shared
+ * memory. Auto takes tiles when the flush holds >= tile_density * 26.8 / (26.8 - 25 c) update elements per element
+ * of the local block it can reach, c being the share of its elements whose row directly follows the previous row of
+ * their segment (RED pays per 32-byte sector, so runs of consecutive rows make it cheap): tile_density itself for
+ * scattered rows, about 12 x tile_density for fully clustered ones. tile_density <= 0 keeps the current value
+ * (default 0.125). Deterministic mode always uses column tiles. */
 int cm_set_apply_kernel(cm_matrix *M, int kernel, double tile_density);
 
 /* When the owner scatter-adds what commit() delivered (COLLECTIVE, nothing staged; extension — the
