@@ -81,3 +81,31 @@ def test_bench_workloads_are_the_baseline_configs():
     assert (k2["m"], k2["nprow"], k2["npcol"], k2["lld"], k2["m_u"], k2["commit_every"]) == (32768, 2, 4, 16384, 512, 256)
     k4 = bench.workload_spec("K4", 8)
     assert (k4["dtype"], k4["nprow"], k4["npcol"], k4["m_u"], k4["lld"]) == (1, 4, 2, 32, 8192)
+
+
+def test_bench_line_contract_on_the_recorded_lines():
+    """the JSON lines bench.py printed on B200 this round (profiles/r2/) carry every key of the bench contract,
+    and the reference arm's workload naming matches the GPU arm's"""
+    import glob
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "parity"}
+    lines = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2", "bench_*.json")))
+    assert lines
+    for path in lines:
+        b = json.load(open(path))
+        assert need <= set(b), (path, need - set(b))
+        assert b["metric"] == bench.METRIC and b["unit"] == "GB/s" and b["higher_is_better"] is True and b["scaling"] == "weak"
+        assert b["gpu_launches"] > 0 and "workload" in b["config"]
+        r = b["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        p = b["parity"]
+        assert p["checked"] and p["ok"] and p["wire_bit_exact"] and p["deterministic_bit_exact_run_to_run"]
+        if b["e2e"] is not None:
+            assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(b["e2e"]) and b["e2e"]["h2d_bytes_per_step"] > 0
+        if b["n_gpus"] == 1:
+            c = b["cpu_baseline"]
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "reference"
+        assert b["config"]["workload"] == bench.workload_spec(path.split("bench_")[1].split("_")[0].replace("k1weak", "K1").upper().replace("K1WEAK", "K1"), b["n_gpus"])["name"]
